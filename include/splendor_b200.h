@@ -1,0 +1,164 @@
+/*
+ * splendor_b200.h -- C ABI of the B200-native frontier-expansion library
+ * (libsplendor_b200.so, built from splendor-rl-gym_b200/csrc/ for sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of IamJasonBian/Splendor-RL-Gym: the
+ * per-turn frontier expansion of its solver (generate -> dedup -> score -> top-k).
+ * Every entry point names the reference interface (file:line in the reference tree)
+ * it replaces.  Plain pointers and sizes only: no torch / C++ types cross this line.
+ *
+ * Conventions
+ *   - every function returns an int32 status: 0 = ok, < 0 = SPL_E_* ; the message of
+ *     the last failure on a context is spl_last_error(ctx) (spl_last_error(NULL) for
+ *     failures of spl_create itself).  No C++ exception crosses the boundary.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors);
+ *     "host" pointers are ordinary host memory.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = the legacy default stream).  Calls are asynchronous on `stream`
+ *     unless they return a count through a host pointer, in which case they
+ *     synchronise that stream before returning.
+ *   - one context per device, used from one host thread at a time.
+ *   - there is NO CPU fallback: on a machine without a usable sm_100 device every
+ *     compute entry point fails with SPL_E_NODEVICE / SPL_E_CUDA.
+ *
+ * Packed state record (speedrun `State`, src/solver.py:308-318)
+ *   key  (spl_key, 128 bit, identity == (cards, gems) exactly as hashed at :318):
+ *        bits 0..14   gems[c] << 3c          (c = White, Blue, Green, Red, Black; 0..7 each)
+ *        bits 15..104 card i owned -> bit 15+i   (90 cards, src/cardparser.py:57-66)
+ *        bits 105..127 zero in caller-visible keys (used as epoch tag inside the visited table)
+ *        Unsigned 128-bit order of keys == order of the Python int
+ *        (sum(1 << card) << 15) | sum(gems[i] << 3i)  used by the `det` tie-break policy.
+ *   aux  (uint64, NOT part of identity -- first arrival supplies it, src/solver.py:447-450):
+ *        bits 0..15 saved | bits 16..23 pts | bits 24+5c..28+5c bonus[c]
+ *   link (uint64): parent_rank << 8 | ordinal, ordinal = index into list(iter(parent))
+ *        (buys of affordable not-owned cards in ascending card index, then takes in
+ *        table order; src/solver.py:357-388).
+ */
+#ifndef SPLENDOR_B200_H
+#define SPLENDOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPL_ABI_VERSION 1
+
+typedef struct spl_ctx spl_ctx;
+typedef struct spl_solver spl_solver;
+
+typedef struct { uint64_t lo, hi; } spl_key;
+
+/* status codes */
+enum {
+    SPL_OK = 0,
+    SPL_E_INVALID = -1,    /* bad argument */
+    SPL_E_NODEVICE = -2,   /* no CUDA device / not an sm_100 device */
+    SPL_E_CUDA = -3,       /* CUDA runtime error (message has the detail) */
+    SPL_E_NOMEM = -4,      /* device allocation failed */
+    SPL_E_TABLE_FULL = -5, /* visited table cannot take this level (grow failed) */
+    SPL_E_CAPACITY = -6,   /* caller buffer too small */
+    SPL_E_STATE = -7       /* call out of order (e.g. step after the search ended) */
+};
+
+/* heuristic ids == the reference registry HEURISTICS (src/solver.py:299-305);
+ * unknown names map to SIMPLE on the host side, as HEURISTICS.get(name, simple) does (:429). */
+enum { SPL_H_SIMPLE = 0, SPL_H_BALANCED = 1, SPL_H_AGGRESSIVE = 2, SPL_H_EFFICIENCY = 3 };
+
+/* noise policy for the `randint(1,100)*0.01` term (src/solver.py:215,247,260,284), SURVEY.md 8a-N */
+enum { SPL_NOISE_CONST = 0 /* randint -> 50 */, SPL_NOISE_HASH = 1 /* 1 + splitmix64(lo^hi) % 100 */ };
+
+/* tie-break policy of the beam cut `sorted(next_queue, key=h, reverse=True)[:beam]` (:452-456) */
+enum { SPL_TIE_STABLE = 0 /* arrival order, as Python's stable sort */, SPL_TIE_KEY = 1 /* key descending */ };
+
+typedef struct {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t reserved0;
+    uint64_t table_slots;      /* initial visited-table capacity in 32-byte slots (0 = default 2^22) */
+    uint64_t max_table_bytes;  /* growth ceiling for the visited table (0 = 60% of free device memory) */
+    uint64_t chunk_parents;    /* parents expanded per launch pair (0 = default 4 Mi; max 16 Mi) */
+} spl_config;
+
+/* per-level counters (the reference prints none of these; they feed parity tests and the roofline) */
+typedef struct {
+    int32_t level;        /* index of the `while queue` iteration (src/solver.py:434) */
+    int32_t ended;        /* 1 when the loop ended in this iteration (goal dequeued / frontier empty) */
+    int64_t frontier;     /* len(queue) at the top of the iteration */
+    int64_t expanded;     /* parents actually expanded on the device */
+    int64_t generated;    /* successors enumerated (== sum of len(list(parent))) */
+    int64_t unique;       /* len(next_queue): first arrivals not in the visited set */
+    int64_t kept;         /* len(queue) after the beam cut */
+    int64_t goal_rank;    /* rank of the first state with pts >= goal in queue order, or -1 */
+    int64_t visited;      /* len(trail) */
+    uint64_t table_slots; /* current visited-table capacity */
+    float ms_expand;      /* CUDA-event time of the expand+probe launches */
+    float ms_resolve;     /* ... of the resolve+emit(+score) launches */
+    float ms_select;      /* ... of the radix-select + cut */
+    float ms_sort;        /* ... of the rank-ordering sort */
+} spl_level_info;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int32_t spl_abi_version(void);
+const char *spl_last_error(const spl_ctx *ctx);
+
+/* Host-only table access (no device needed).  The tables are built once, natively, from
+ * the packed deck; they replace get_deck() (src/cardparser.py:64), get_takes()
+ * (src/gems.py:111-113) and possible_buys()/get_buys() (src/buys.py:13-17,39-41). */
+const uint32_t *spl_deck_table(int32_t *n_cards);                     /* cost|pt|bonus per card */
+int32_t spl_host_takes(const uint8_t gems[5], uint8_t out[100 * 5]);  /* -> count, take_gems order */
+int32_t spl_host_buys(const uint8_t key[5], uint8_t out[90]);         /* -> count, ascending cards */
+
+int32_t spl_create(const spl_config *cfg, spl_ctx **out);
+int32_t spl_destroy(spl_ctx *ctx);
+/* forget every visited state (trail = {}), keep the allocation */
+int32_t spl_reset_visited(spl_ctx *ctx, void *stream);
+int32_t spl_visited_count(spl_ctx *ctx, int64_t *n_host);
+
+/* ---- stage operators (caller-owned device buffers) ---------------------------------------- */
+
+/* State.__iter__ for a batch (src/solver.py:357-388): all successors of parents
+ * [0, n) in (parent rank, ordinal) order.  cand_link[j] = parent_rank << 8 | ordinal.
+ * Fails with SPL_E_CAPACITY (and reports the needed size in *n_out_host) if cap is too small. */
+int32_t spl_expand(spl_ctx *ctx, const spl_key *keys_dev, const uint64_t *aux_dev, int64_t n,
+                   spl_key *cand_keys_dev, uint64_t *cand_aux_dev, uint64_t *cand_link_dev,
+                   int64_t cap, int64_t *n_out_host, void *stream);
+
+/* `if next_step in trail: continue; trail[next_step] = puzzle; next_queue.append(next_step)`
+ * (src/solver.py:447-450) for a candidate list given in arrival order: keeps the FIRST
+ * arrival of every key never seen before (in this call or any earlier one on this
+ * context), in arrival order.  uniq_src[j] = index of the surviving candidate. */
+int32_t spl_dedup(spl_ctx *ctx, const spl_key *cand_keys_dev, const uint64_t *cand_aux_dev, int64_t n,
+                  spl_key *uniq_keys_dev, uint64_t *uniq_aux_dev, int64_t *uniq_src_dev,
+                  int64_t *n_out_host, void *stream);
+
+/* HEURISTICS[name](state) for a batch (src/solver.py:210-286), bit-exact IEEE doubles. */
+int32_t spl_score(spl_ctx *ctx, int32_t heuristic, int32_t noise, const spl_key *keys_dev,
+                  const uint64_t *aux_dev, int64_t n, double *scores_dev, void *stream);
+
+/* sorted(range(n), key=score, reverse=True)[:k] (src/solver.py:452-456) under a tie policy:
+ * writes the surviving indices in rank order. */
+int32_t spl_topk(spl_ctx *ctx, const double *scores_dev, const spl_key *keys_dev, int64_t n, int64_t k,
+                 int32_t tie_policy, int64_t *out_idx_dev, int64_t *n_out_host, void *stream);
+
+/* ---- fused level-synchronous solver: State.solve (src/solver.py:390-464) ------------------- */
+
+/* root_host: one packed state (key + aux) in HOST memory -- the `self` of solve().
+ * use_heuristic = 0 -> exhaustive BFS (queue = next_queue); else beam search. */
+int32_t spl_solver_create(spl_ctx *ctx, const spl_key *root_key_host, uint64_t root_aux_host,
+                          int32_t goal_pts, int32_t use_heuristic, int32_t heuristic, int64_t beam_width,
+                          int32_t tie_policy, int32_t noise, int32_t keep_links, spl_solver **out);
+int32_t spl_solver_destroy(spl_solver *s);
+/* one `while queue` iteration; returns SPL_OK and fills *info_host; info->ended tells the caller to stop */
+int32_t spl_solver_step(spl_solver *s, spl_level_info *info_host, void *stream);
+/* device views of the current queue (valid until the next step) */
+int32_t spl_solver_frontier(spl_solver *s, const spl_key **keys_dev, const uint64_t **aux_dev,
+                            const uint64_t **link_dev, int64_t *n_host);
+/* parent-chain walk (src/solver.py:459-464): ordinals[i] = index into list(iter(path[i])) of
+ * path[i+1]; ranks[i] = rank of path[i] in level i.  Returns the number of moves in *n_moves_host. */
+int32_t spl_solver_path(spl_solver *s, int64_t *ranks_host, int32_t *ordinals_host, int32_t cap,
+                        int32_t *n_moves_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLENDOR_B200_H */

@@ -1,0 +1,195 @@
+"""ctypes front-end of the CPU oracle (oracle/splendor_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference`
+legs may import this package; the product package (splendor-rl-gym_b200/) never does.
+"""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = _HERE / '_build' / 'liboracle.so'
+
+STATE_DTYPE = np.dtype([('lo', '<u8'), ('hi', '<u8'), ('aux', '<u8')])
+HEURISTIC_IDS = {'simple': 0, 'balanced': 1, 'aggressive': 2, 'efficiency': 3, 'competitive': 1}
+POLICY_IDS = {'stable': 0, 'det': 1}
+NOISE_IDS = {'const': 0, 'hash': 1}
+
+
+class LevelInfo(C.Structure):
+    _fields_ = [('level', C.c_int32), ('frontier', C.c_int64), ('expanded', C.c_int64),
+                ('generated', C.c_int64), ('unique', C.c_int64), ('kept', C.c_int64),
+                ('goal_rank', C.c_int64), ('visited', C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def build(force: bool = False) -> Path:
+    src = _HERE / 'splendor_oracle.c'
+    if force or not _LIB.exists() or _LIB.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(['make', '-C', str(_HERE), '-s'], check=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(_LIB))
+        L.orc_init.restype = C.c_int
+        L.orc_take_gems.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_buys.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_subtract_with_bonus.argtypes = [C.c_void_p] * 4
+        L.orc_expand.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_score.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_score.restype = C.c_double
+        L.orc_solver_new.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int]
+        L.orc_solver_new.restype = C.c_void_p
+        L.orc_solver_free.argtypes = [C.c_void_p]
+        L.orc_solver_step.argtypes = [C.c_void_p, C.POINTER(LevelInfo)]
+        L.orc_solver_nlevels.argtypes = [C.c_void_p]
+        L.orc_solver_level_size.argtypes = [C.c_void_p, C.c_int]
+        L.orc_solver_level_size.restype = C.c_int64
+        L.orc_solver_level_states.argtypes = [C.c_void_p, C.c_int]
+        L.orc_solver_level_states.restype = C.c_void_p
+        L.orc_solver_level_links.argtypes = [C.c_void_p, C.c_int]
+        L.orc_solver_level_links.restype = C.c_void_p
+        L.orc_solver_goal_rank.argtypes = [C.c_void_p]
+        L.orc_solver_goal_rank.restype = C.c_int64
+        L.orc_solver_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_takes_of.argtypes = [C.c_uint, C.c_void_p]
+        L.orc_init()
+        _lib = L
+    return _lib
+
+
+# ---------------------------------------------------------------- packing helpers (oracle-side)
+def pack_state(cards, bonus, gems, pts, saved) -> np.ndarray:
+    m = 0
+    for c in cards:
+        m |= 1 << c
+    g = 0
+    for i, x in enumerate(gems):
+        g |= x << (3 * i)
+    k = (m << 15) | g
+    aux = (saved & 0xffff) | (pts & 0xff) << 16
+    for i, b in enumerate(bonus):
+        aux |= (b & 31) << (24 + 5 * i)
+    s = np.zeros(1, STATE_DTYPE)
+    s['lo'] = k & ((1 << 64) - 1)
+    s['hi'] = k >> 64
+    s['aux'] = aux
+    return s
+
+
+def unpack_state(rec):
+    k = int(rec['lo']) | int(rec['hi']) << 64
+    aux = int(rec['aux'])
+    gems = tuple((k >> (3 * i)) & 7 for i in range(5))
+    m = k >> 15
+    cards = tuple(i for i in range(90) if (m >> i) & 1)
+    bonus = tuple((aux >> (24 + 5 * i)) & 31 for i in range(5))
+    return dict(cards=cards, bonus=bonus, gems=gems, pts=(aux >> 16) & 0xff, saved=aux & 0xffff, key=k)
+
+
+def take_gems(g):
+    a = np.array(g, np.uint8)
+    out = np.zeros((128, 5), np.uint8)
+    n = lib().orc_take_gems(a.ctypes.data, out.ctypes.data)
+    return [tuple(int(x) for x in r) for r in out[:n]]
+
+
+def buys(key):
+    a = np.array(key, np.uint8)
+    out = np.zeros(90, np.uint8)
+    n = lib().orc_buys(a.ctypes.data, out.ctypes.data)
+    return [int(x) for x in out[:n]]
+
+
+def subtract_with_bonus(gems, cost, bonus):
+    g, c, b = (np.array(x, np.uint8) for x in (gems, cost, bonus))
+    out = np.zeros(5, np.uint8)
+    saved = lib().orc_subtract_with_bonus(g.ctypes.data, c.ctypes.data, b.ctypes.data, out.ctypes.data)
+    return tuple(int(x) for x in out), saved
+
+
+def expand(state_rec: np.ndarray) -> np.ndarray:
+    out = np.zeros(192, STATE_DTYPE)
+    s = np.ascontiguousarray(state_rec).reshape(1)
+    n = lib().orc_expand(s.ctypes.data, out.ctypes.data)
+    return out[:n].copy()
+
+
+def score(states: np.ndarray, heuristic: str, noise: str = 'const') -> np.ndarray:
+    states = np.ascontiguousarray(states)
+    out = np.zeros(len(states), np.float64)
+    h, nz = HEURISTIC_IDS.get(heuristic, 0), NOISE_IDS[noise]
+    base = states.ctypes.data
+    L = lib()
+    for i in range(len(states)):
+        out[i] = L.orc_score(base + i * STATE_DTYPE.itemsize, h, nz)
+    return out
+
+
+class Solver:
+    """Level stepper over the oracle's restatement of State.solve (src/solver.py:390-464)."""
+
+    def __init__(self, goal_pts=15, *, use_heuristic=False, heuristic_name='simple', beam_width=300_000,
+                 policy='stable', noise='const', root=None):
+        if root is None:
+            root = pack_state((), (0,) * 5, (0,) * 5, 0, 0)
+        self._root = np.ascontiguousarray(root)
+        self._h = lib().orc_solver_new(self._root.ctypes.data, goal_pts, int(use_heuristic),
+                                       HEURISTIC_IDS.get(heuristic_name, 0), beam_width,
+                                       POLICY_IDS[policy], NOISE_IDS[noise])
+        self.infos = []
+        self.done = False
+
+    def step(self):
+        li = LevelInfo()
+        self.done = bool(lib().orc_solver_step(self._h, C.byref(li)))
+        d = li.as_dict()
+        self.infos.append(d)
+        return d
+
+    def run(self, max_levels=None):
+        while not self.done:
+            self.step()
+            if max_levels is not None and len(self.infos) >= max_levels:
+                break
+        return self.infos
+
+    @property
+    def nlevels(self):
+        return lib().orc_solver_nlevels(self._h)
+
+    def level(self, i):
+        """(states, links) of the queue at the top of while-iteration i (copies)."""
+        n = lib().orc_solver_level_size(self._h, i)
+        sp = lib().orc_solver_level_states(self._h, i)
+        lp = lib().orc_solver_level_links(self._h, i)
+        st = np.frombuffer((C.c_char * (n * STATE_DTYPE.itemsize)).from_address(sp), STATE_DTYPE).copy()
+        lk = np.frombuffer((C.c_char * (n * 8)).from_address(lp), np.uint64).copy()
+        return st, lk
+
+    def path(self):
+        out = np.zeros(self.nlevels, STATE_DTYPE)
+        n = lib().orc_solver_path(self._h, out.ctypes.data, len(out))
+        return out[:n]
+
+    def close(self):
+        if self._h:
+            lib().orc_solver_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,82 @@
+"""ctypes binding of libsplendor_b200.so (C ABI: include/splendor_b200.h).
+
+The shared library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is
+no Python or CPU fallback: if the library is missing, importing this module raises.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / 'libsplendor_b200.so'
+
+SPL_OK = 0
+ERRORS = {-1: 'SPL_E_INVALID', -2: 'SPL_E_NODEVICE', -3: 'SPL_E_CUDA', -4: 'SPL_E_NOMEM',
+          -5: 'SPL_E_TABLE_FULL', -6: 'SPL_E_CAPACITY', -7: 'SPL_E_STATE'}
+
+
+class SplendorB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f'{ERRORS.get(code, code)}: {msg}')
+        self.code = code
+
+
+class Key(C.Structure):
+    _fields_ = [('lo', C.c_uint64), ('hi', C.c_uint64)]
+
+
+class Config(C.Structure):
+    _fields_ = [('device', C.c_int32), ('reserved0', C.c_int32), ('table_slots', C.c_uint64),
+                ('max_table_bytes', C.c_uint64), ('chunk_parents', C.c_uint64)]
+
+
+class LevelInfo(C.Structure):
+    _fields_ = [('level', C.c_int32), ('ended', C.c_int32), ('frontier', C.c_int64), ('expanded', C.c_int64),
+                ('generated', C.c_int64), ('unique', C.c_int64), ('kept', C.c_int64), ('goal_rank', C.c_int64),
+                ('visited', C.c_int64), ('table_slots', C.c_uint64), ('ms_expand', C.c_float),
+                ('ms_resolve', C.c_float), ('ms_select', C.c_float), ('ms_sort', C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _load():
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback for this path.')
+    L = C.CDLL(str(LIB_PATH), mode=getattr(os, 'RTLD_LOCAL', 0))
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    sig = {
+        'spl_abi_version': (i32, []),
+        'spl_last_error': (C.c_char_p, [vp]),
+        'spl_deck_table': (C.POINTER(C.c_uint32), [C.POINTER(i32)]),
+        'spl_host_takes': (i32, [vp, vp]),
+        'spl_host_buys': (i32, [vp, vp]),
+        'spl_create': (i32, [C.POINTER(Config), C.POINTER(vp)]),
+        'spl_destroy': (i32, [vp]),
+        'spl_reset_visited': (i32, [vp, vp]),
+        'spl_visited_count': (i32, [vp, C.POINTER(i64)]),
+        'spl_expand': (i32, [vp, vp, vp, i64, vp, vp, vp, i64, C.POINTER(i64), vp]),
+        'spl_dedup': (i32, [vp, vp, vp, i64, vp, vp, vp, C.POINTER(i64), vp]),
+        'spl_score': (i32, [vp, i32, i32, vp, vp, i64, vp, vp]),
+        'spl_topk': (i32, [vp, vp, vp, i64, i64, i32, vp, C.POINTER(i64), vp]),
+        'spl_solver_create': (i32, [vp, C.POINTER(Key), u64, i32, i32, i32, i64, i32, i32, i32, C.POINTER(vp)]),
+        'spl_solver_destroy': (i32, [vp]),
+        'spl_solver_step': (i32, [vp, C.POINTER(LevelInfo), vp]),
+        'spl_solver_frontier': (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]),
+        'spl_solver_path': (i32, [vp, vp, vp, i32, C.POINTER(i32)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)  # AttributeError here == the library does not export the ABI
+        f.restype, f.argtypes = res, args
+    return L, tuple(sig)
+
+
+lib, EXPORTS = _load()
+
+
+def check(code, ctx=None):
+    if code != SPL_OK:
+        msg = lib.spl_last_error(ctx)
+        raise SplendorB200Error(code, msg.decode() if msg else '')

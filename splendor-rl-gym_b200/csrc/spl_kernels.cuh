@@ -1,0 +1,755 @@
+// spl_kernels.cuh -- the sm_100a kernels of the frontier-expansion path.
+//
+//   count_scan_kernel     per-parent fan-out + exclusive offsets (decoupled look-back)
+//   expand_kernel<MODE>   successor enumeration (State.__iter__) fused with the visited-table
+//                         probe/insert (MODE_PROBE) or materialising candidates (MODE_LIST)
+//   probe_list_kernel     visited-table probe/insert of a materialised candidate list
+//   resolve_kernel<SRC>   first-arrival winner resolution + ordered emission (+ scoring)
+//   score_kernel          heuristics on a batch
+//   sel_* / cut_kernel    radix select of the beam threshold + arrival-order cut
+//   sort_* / gather       stable LSD radix sort into rank order
+//
+// Every kernel is HBM/L2-latency bound integer work: no tensor cores (no dense contraction).
+#pragma once
+#include "spl_common.cuh"
+
+namespace spl {
+
+struct Counters {            // device-resident scalars, zeroed per use by the host driver
+    unsigned long long total_cands;   // candidates in this chunk
+    unsigned long long n_new;         // successful inserts in this chunk (== winners)
+    unsigned long long n_emitted;     // winners emitted so far in this level
+    unsigned long long sk_min, sk_max;  // range of order-preserving score keys in this level
+    long long goal_rank;              // min rank with pts >= goal (or LLONG_MAX)
+    unsigned int error;               // 1 = probe overflow (table full)
+    unsigned int ticket[4];           // dynamic tile tickets
+};
+
+struct SelState {            // radix-select state (device)
+    unsigned long long prefix;  // high bits of the threshold found so far (in x = sk - sk_min space)
+    unsigned long long k_rem;   // rank still to resolve inside the current bucket
+    unsigned long long c_gt;    // elements strictly above the current bucket
+    unsigned long long pad;
+};
+
+// ------------------------------------------------------------------ per-parent derivation
+struct SmemTabs {
+    uint64_t buy_lo[NCOL][8];
+    uint64_t buy_hi[NCOL][8];
+    uint32_t card[SPL_NUM_CARDS + 2];
+};
+
+__device__ __forceinline__ void load_tabs(SmemTabs &s, const DevTables *__restrict__ g) {
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(g);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(&s);
+    for (int i = threadIdx.x; i < 2 * NCOL * 8; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < SPL_NUM_CARDS; i += blockDim.x) s.card[i] = g->card[i];
+}
+
+// buys mask (key layout) and take-table entry of one parent: State.__iter__ :360-369, :381
+__device__ __forceinline__ void derive_parent(const SmemTabs &s, const uint32_t *__restrict__ takes_idx, uint64_t lo,
+                                              uint64_t hi, uint64_t aux, uint64_t &bm_lo, uint64_t &bm_hi,
+                                              uint32_t &nb, uint32_t &tk) {
+    const uint32_t g = (uint32_t)(lo & GEM_MASK);
+    bm_lo = ~lo;
+    bm_hi = ~hi & HI_KEY_MASK;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+        uint32_t v = ((g >> (3 * c)) & 7) + (uint32_t)((aux >> (24 + 5 * c)) & 31);
+        v = v > 7 ? 7 : v;  // min(g + b, MAX_GEMS)
+        bm_lo &= s.buy_lo[c][v];
+        bm_hi &= s.buy_hi[c][v];
+    }
+    nb = __popcll(bm_lo) + __popcll(bm_hi);
+    tk = __ldg(takes_idx + g);
+}
+
+__device__ __forceinline__ int nth_set_bit64(uint64_t m, int n) {
+    const uint32_t l = (uint32_t)m, h = (uint32_t)(m >> 32);
+    const int c = __popc(l);
+    return n < c ? nth_set_bit32(l, n) : 32 + nth_set_bit32(h, n - c);
+}
+
+// ord-th successor of a parent in list(iter(parent)) order: buys ascending, then takes.
+// State.buy_card :338-355 / subtract_with_bonus gems.py:116-129 / increase_bonus :141-143
+__device__ __forceinline__ void make_child(const SmemTabs &s, const uint16_t *__restrict__ takes_edges, uint64_t lo,
+                                           uint64_t hi, uint64_t aux, uint64_t bm_lo, uint64_t bm_hi, uint32_t nb,
+                                           uint32_t tk, uint32_t ord, uint64_t &clo, uint64_t &chi, uint64_t &caux) {
+    if (ord < nb) {
+        const int c0 = __popcll(bm_lo);
+        const int pos = (int)ord < c0 ? nth_set_bit64(bm_lo, ord) : 64 + nth_set_bit64(bm_hi, ord - c0);
+        const uint32_t cd = s.card[pos - 15];
+        const uint32_t g = (uint32_t)(lo & GEM_MASK);
+        uint32_t ng = 0, saved = 0;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            const int cost = (cd >> (3 * c)) & 7;
+            const int b = (int)((aux >> (24 + 5 * c)) & 31);
+            const int gc = (g >> (3 * c)) & 7;
+            const int pay = max(cost - b, 0);
+            saved += cost - pay;
+            ng |= (uint32_t)max(gc - pay, 0) << (3 * c);
+        }
+        clo = (lo & ~GEM_MASK) | ng;
+        chi = hi;
+        if (pos < 64) clo |= 1ull << pos; else chi |= 1ull << (pos - 64);
+        caux = aux + saved + ((uint64_t)((cd >> 15) & 7) << 16) + (1ull << (24 + 5 * ((cd >> 18) & 7)));
+    } else {
+        const uint32_t e = __ldg(takes_edges + (tk >> 8) + (ord - nb));
+        clo = (lo & ~GEM_MASK) | e;
+        chi = hi;
+        caux = aux;
+    }
+}
+
+// ------------------------------------------------------------------ visited table probe
+// Returns the slot index the candidate resolved to (new insert or same-epoch duplicate), or DEAD
+// if the key was inserted in an earlier epoch.  `tinv` = ~t, t = arrival index in this epoch:
+// atomicMax(~t) keeps the FIRST arrival (src/solver.py:447-450) regardless of thread order.
+__device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t klo,
+                                                 uint64_t khi, uint64_t tinv, uint32_t &n_new, unsigned int *error) {
+    uint64_t i = slot_of(hash_key(klo, khi), cap);
+    const uint64_t want_hi = khi | (tag << TAG_SHIFT);
+    for (int probes = 0; probes < MAX_PROBE; ++probes) {
+        uint64_t *slot = table + (i << 2);
+        uint64_t a, b;
+        ld_cg_u64x2(slot, a, b);
+        if ((a | b) == 0) {  // empty: claim with one 128-bit CAS
+            cas128(slot, 0, 0, klo, want_hi, a, b);
+            if ((a | b) == 0) {
+                atomicMax(reinterpret_cast<unsigned long long *>(slot + 2), (unsigned long long)tinv);
+                ++n_new;
+                return (uint32_t)i;
+            }
+        }
+        if (a == klo && (b & HI_KEY_MASK) == khi) {
+            if ((b >> TAG_SHIFT) != tag) return DEAD;
+            atomicMax(reinterpret_cast<unsigned long long *>(slot + 2), (unsigned long long)tinv);
+            return (uint32_t)i;
+        }
+        if (++i == cap) i = 0;
+    }
+    atomicExch(error, 1u);
+    return DEAD;
+}
+
+// ------------------------------------------------------------------ count + scan
+__global__ void __launch_bounds__(TILE) count_scan_kernel(const Rec *__restrict__ front, int64_t n_par,
+                                                          const DevTables *__restrict__ tabs,
+                                                          const uint32_t *__restrict__ takes_idx,
+                                                          uint32_t *__restrict__ off, uint64_t *status,
+                                                          Counters *ctr, int ticket_id) {
+    __shared__ SmemTabs s;
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    load_tabs(s, tabs);
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t p = (int64_t)tile * TILE + threadIdx.x;
+    uint32_t cnt = 0;
+    if (p < n_par) {
+        Rec r;
+        ld_rec(front + p, r);
+        uint64_t bl, bh;
+        uint32_t nb, tk;
+        derive_parent(s, takes_idx, r.lo, r.hi, r.aux, bl, bh, nb, tk);
+        cnt = nb + (tk & 0xff);
+    }
+    uint32_t total;
+    const uint32_t excl = block_excl_scan(cnt, warp_sums, total);
+    if (threadIdx.x == 0) {
+        s_base = lookback_exclusive(status, tile, total, 0);
+        if ((int64_t)(tile + 1) * TILE >= n_par) ctr->total_cands = s_base + total;
+    }
+    __syncthreads();
+    if (p < n_par) off[p] = (uint32_t)(s_base + excl);
+}
+
+// ------------------------------------------------------------------ expand (+ probe)
+enum { MODE_PROBE = 0, MODE_LIST = 1 };
+
+struct ExpandSmem {
+    SmemTabs tabs;
+    uint64_t lo[TILE], hi[TILE], aux[TILE], bm_lo[TILE], bm_hi[TILE];
+    uint32_t tk[TILE], nb[TILE], pref[TILE + 1];
+};
+
+// load a tile of parents, derive masks; pref[] = tile-local exclusive candidate offsets
+__device__ __forceinline__ void load_tile(ExpandSmem &S, const Rec *__restrict__ front, int64_t n_par,
+                                          const uint32_t *__restrict__ takes_idx, const uint32_t *__restrict__ off,
+                                          uint32_t total, uint32_t tile, uint32_t &c0, uint32_t &ncand) {
+    const int64_t p0 = (int64_t)tile * TILE, p = p0 + threadIdx.x;
+    c0 = off[p0];
+    const uint32_t c1 = (p0 + TILE < n_par) ? off[p0 + TILE] : total;
+    ncand = c1 - c0;
+    if (p < n_par) {
+        Rec r;
+        ld_rec(front + p, r);
+        uint64_t bl, bh;
+        uint32_t nb, tk;
+        derive_parent(S.tabs, takes_idx, r.lo, r.hi, r.aux, bl, bh, nb, tk);
+        S.lo[threadIdx.x] = r.lo; S.hi[threadIdx.x] = r.hi; S.aux[threadIdx.x] = r.aux;
+        S.bm_lo[threadIdx.x] = bl; S.bm_hi[threadIdx.x] = bh;
+        S.tk[threadIdx.x] = tk; S.nb[threadIdx.x] = nb;
+        S.pref[threadIdx.x] = off[p] - c0;
+    } else {
+        S.pref[threadIdx.x] = ncand;
+    }
+    if (threadIdx.x == 0) S.pref[TILE] = ncand;
+}
+
+// parent (tile-local) owning tile-local candidate i
+__device__ __forceinline__ uint32_t owner_of(const uint32_t *pref, uint32_t i) {
+    uint32_t lo = 0, hi = TILE;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pref[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE) expand_kernel(const Rec *__restrict__ front, int64_t n_par,
+                                                      const DevTables *__restrict__ tabs,
+                                                      const uint32_t *__restrict__ takes_idx,
+                                                      const uint16_t *__restrict__ takes_edges,
+                                                      const uint32_t *__restrict__ off, uint32_t total,
+                                                      uint64_t *__restrict__ table, uint64_t cap, uint64_t tag,
+                                                      uint32_t *__restrict__ cand_slot, Rec *__restrict__ cand_out,
+                                                      int64_t rank_base, Counters *ctr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ExpandSmem &S = *reinterpret_cast<ExpandSmem *>(smem_raw);
+    load_tabs(S.tabs, tabs);
+    __syncthreads();
+    uint32_t c0, ncand;
+    load_tile(S, front, n_par, takes_idx, off, total, blockIdx.x, c0, ncand);
+    __syncthreads();
+    uint32_t n_new = 0;
+    for (uint32_t i = threadIdx.x; i < ncand; i += TILE) {
+        const uint32_t j = owner_of(S.pref, i);
+        const uint32_t ord = i - S.pref[j];
+        uint64_t clo, chi, caux;
+        make_child(S.tabs, takes_edges, S.lo[j], S.hi[j], S.aux[j], S.bm_lo[j], S.bm_hi[j], S.nb[j], S.tk[j], ord, clo,
+                   chi, caux);
+        const uint64_t t = (uint64_t)c0 + i;
+        if (MODE == MODE_PROBE) {
+            cand_slot[t] = probe_insert(table, cap, tag, clo, chi, ~t, n_new, &ctr->error);
+        } else {
+            Rec r{clo, chi, caux, ((uint64_t)(rank_base + (int64_t)blockIdx.x * TILE + j) << 8) | ord};
+            st_rec(cand_out + t, r);
+        }
+    }
+    if (MODE == MODE_PROBE) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, d);
+        if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&ctr->n_new, (unsigned long long)n_new);
+    }
+}
+
+// probe/insert of a materialised candidate list (stage operator spl_dedup; multi-GPU owner side)
+__global__ void __launch_bounds__(TILE) probe_list_kernel(const spl_key *__restrict__ keys, int64_t n,
+                                                          uint64_t *__restrict__ table, uint64_t cap, uint64_t tag,
+                                                          uint32_t *__restrict__ cand_slot, Counters *ctr) {
+    const int64_t t = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    uint32_t n_new = 0;
+    if (t < n) {
+        uint64_t a, b;
+        ld_cg_u64x2(reinterpret_cast<const uint64_t *>(keys + t), a, b);
+        cand_slot[t] = probe_insert(table, cap, tag, a, b & HI_KEY_MASK, ~(uint64_t)t, n_new, &ctr->error);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, d);
+    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&ctr->n_new, (unsigned long long)n_new);
+}
+
+// ------------------------------------------------------------------ heuristics
+// Bit-exact restatement of src/solver.py:210-286: every pow comes from a host-built LUT
+// (libm pow, as CPython's float_pow), every * and + is a separately rounded IEEE double
+// (__dmul_rn/__dadd_rn cannot be contracted into FMA).
+__device__ __forceinline__ double score_state(int h, int noise_mode, uint64_t lo, uint64_t hi, uint64_t aux,
+                                              const ScoreLuts &L) {
+    const uint32_t pts = (uint32_t)((aux >> 16) & 0xff), saved = (uint32_t)(aux & 0xffff);
+    const uint32_t g = (uint32_t)(lo & GEM_MASK);
+    uint32_t sum_g = 0, sum_b = 0, nnz = 0;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+        sum_g += (g >> (3 * c)) & 7;
+        const uint32_t b = (uint32_t)((aux >> (24 + 5 * c)) & 31);
+        sum_b += b;
+        nnz += b > 0;
+    }
+    const int r = noise_mode == 1 ? 1 + (int)(mix64(lo, hi) % 100ull) : 50;
+    const double noise = __dmul_rn((double)r, 0.01);
+    const int hh = (h >= 0 && h <= 3) ? h : 0;
+    const double P = __ldg(L.pts + hh * 256 + pts);
+    const double Sv = __ldg(L.saved + hh * 65536 + saved);
+    double acc;
+    switch (hh) {
+        case 1: {  // balanced :218-249
+            const uint32_t ncards = __popcll(lo >> 15) + __popcll(hi & HI_KEY_MASK);
+            acc = __dadd_rn(__dmul_rn(P, 100.0), __dmul_rn(Sv, 10.0));
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(L.small + 0 * 512 + sum_g + 2 * sum_b), 5.0));
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(L.small + 1 * 512 + ncards), 3.0));
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(L.small + 2 * 512 + nnz), 2.0));
+            break;
+        }
+        case 2:  // aggressive :252-262
+            acc = __dadd_rn(__dmul_rn(P, 200.0), __dmul_rn(Sv, 5.0));
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(L.small + 3 * 512 + sum_b), 2.0));
+            break;
+        case 3:  // efficiency :265-286
+            acc = __dadd_rn(__dmul_rn(P, 50.0), __dmul_rn(Sv, 30.0));
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(L.small + 4 * 512 + sum_b), 20.0));
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(L.small + 5 * 512 + nnz), 10.0));
+            break;
+        default:  // simple :210-215
+            acc = __dmul_rn(Sv, P);
+            break;
+    }
+    return __dadd_rn(acc, noise);
+}
+
+__global__ void __launch_bounds__(TILE) score_kernel(const spl_key *__restrict__ keys, const uint64_t *__restrict__ aux,
+                                                     int64_t n, int h, int noise_mode, ScoreLuts L,
+                                                     double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) out[i] = score_state(h, noise_mode, keys[i].lo, keys[i].hi & HI_KEY_MASK, aux[i], L);
+}
+
+// ------------------------------------------------------------------ resolve + ordered emission
+enum { SRC_PARENT = 0, SRC_LIST = 1 };
+constexpr int MAX_TILE_WORDS = (TILE * 190 + 31) / 32 + 1;  // win bitmask words of a parent tile
+
+struct ResolveSmem {
+    ExpandSmem E;
+    uint32_t win[MAX_TILE_WORDS];
+    uint32_t wpre[MAX_TILE_WORDS];
+    uint32_t warp_sums[TILE / 32 + 1];
+    uint32_t tile;
+    uint64_t base;
+};
+
+// One CTA = one tile of TILE parents (SRC_PARENT) or TILE*32 listed candidates (SRC_LIST).
+// Pass 1 finds the winners (table slot still holds ~t of the first arrival); look-back turns the
+// per-tile winner counts into global output ranks; pass 2 re-derives each winner from its
+// parent (no second gather) and writes it, with its score, in arrival order.
+template <int SRC, bool SCORE>
+__global__ void __launch_bounds__(TILE) resolve_kernel(const Rec *__restrict__ front, int64_t n_par,
+                                                       const DevTables *__restrict__ tabs,
+                                                       const uint32_t *__restrict__ takes_idx,
+                                                       const uint16_t *__restrict__ takes_edges,
+                                                       const uint32_t *__restrict__ off, uint32_t total,
+                                                       const uint64_t *__restrict__ table,
+                                                       const uint32_t *__restrict__ cand_slot,
+                                                       const spl_key *__restrict__ list_keys,
+                                                       const uint64_t *__restrict__ list_aux, int64_t rank_base,
+                                                       uint64_t out_base, Rec *__restrict__ out,
+                                                       uint64_t *__restrict__ out_sk, int64_t *__restrict__ out_src,
+                                                       int h, int noise_mode, ScoreLuts L, uint64_t *status,
+                                                       Counters *ctr, int ticket_id) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(smem_raw);
+    if (SRC == SRC_PARENT) load_tabs(S.E.tabs, tabs);
+    if (threadIdx.x == 0) S.tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    uint32_t c0, ncand;
+    if (SRC == SRC_PARENT) {
+        load_tile(S.E, front, n_par, takes_idx, off, total, tile, c0, ncand);
+    } else {
+        c0 = tile * (TILE * 32u);
+        ncand = min((uint32_t)(TILE * 32), total - c0);
+    }
+    // ---- pass 1: winner flags
+    const uint32_t nwords = (ncand + 31) >> 5;
+    uint32_t mywins = 0;
+    for (uint32_t i0 = 0; i0 < ncand; i0 += TILE) {
+        const uint32_t i = i0 + threadIdx.x;
+        bool win = false;
+        if (i < ncand) {
+            const uint32_t sidx = cand_slot[c0 + i];
+            if (sidx != DEAD) {
+                const uint64_t v = ld_cg_u64(table + ((uint64_t)sidx << 2) + 2);
+                win = (~v) == (uint64_t)(c0 + i);
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, win);
+        if ((threadIdx.x & 31) == 0 && ((i0 + threadIdx.x) >> 5) < nwords) {
+            S.win[(i0 + threadIdx.x) >> 5] = bal;
+            mywins += __popc(bal);
+        }
+    }
+    uint32_t tile_wins;
+    block_excl_scan(mywins, S.warp_sums, tile_wins);
+    if (threadIdx.x == 0) {
+        S.base = out_base + lookback_exclusive(status, tile, tile_wins, 0);
+        if ((uint64_t)c0 + ncand >= total) ctr->n_emitted = S.base + tile_wins;
+    }
+    // ---- word prefix of winner counts (exclusive), processed TILE words at a time
+    uint32_t carry = 0;
+    for (uint32_t w0 = 0; w0 < nwords; w0 += TILE) {
+        const uint32_t w = w0 + threadIdx.x;
+        const uint32_t c = w < nwords ? __popc(S.win[w]) : 0;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(c, S.warp_sums, tot);
+        if (w < nwords) S.wpre[w] = carry + ex;
+        carry += tot;
+    }
+    __syncthreads();
+    // ---- pass 2: emit winners in arrival order
+    uint64_t kmin = ~0ull, kmax = 0;
+    for (uint32_t w = threadIdx.x; w < nwords; w += TILE) {
+        uint32_t bits = S.win[w];
+        uint64_t pos = S.base + S.wpre[w];
+        while (bits) {
+            const uint32_t i = (w << 5) + (__ffs(bits) - 1);
+            bits &= bits - 1;
+            Rec r;
+            if (SRC == SRC_PARENT) {
+                const uint32_t j = owner_of(S.E.pref, i);
+                const uint32_t ord = i - S.E.pref[j];
+                make_child(S.E.tabs, takes_edges, S.E.lo[j], S.E.hi[j], S.E.aux[j], S.E.bm_lo[j], S.E.bm_hi[j],
+                           S.E.nb[j], S.E.tk[j], ord, r.lo, r.hi, r.aux);
+                r.link = ((uint64_t)(rank_base + (int64_t)tile * TILE + j) << 8) | ord;
+            } else {
+                const uint64_t t = (uint64_t)c0 + i;
+                r.lo = list_keys[t].lo;
+                r.hi = list_keys[t].hi & HI_KEY_MASK;
+                r.aux = list_aux[t];
+                r.link = t;
+                if (out_src) out_src[pos] = (int64_t)t;
+            }
+            st_rec(out + pos, r);
+            if (SCORE) {
+                const double sc = score_state(h, noise_mode, r.lo, r.hi, r.aux, L);
+                const uint64_t k = flip_f64((uint64_t)__double_as_longlong(sc));
+                out_sk[pos] = k;
+                kmin = min(kmin, k);
+                kmax = max(kmax, k);
+            }
+            ++pos;
+        }
+    }
+    if (SCORE) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+        }
+        if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+            atomicMin(&ctr->sk_min, (unsigned long long)kmin);
+            atomicMax(&ctr->sk_max, (unsigned long long)kmax);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ goal test (src/solver.py:443-445)
+__global__ void __launch_bounds__(TILE) goal_kernel(const Rec *__restrict__ front, int64_t n, int goal, Counters *ctr) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    long long r = 0x7fffffffffffffffll;
+    if (i < n) {
+        const uint64_t aux = front[i].aux;
+        if ((int)((aux >> 16) & 0xff) >= goal) r = i;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, d));
+    if ((threadIdx.x & 31) == 0 && r != 0x7fffffffffffffffll) atomicMin(&ctr->goal_rank, r);
+}
+
+// ------------------------------------------------------------------ radix select (beam threshold)
+constexpr int SEL_BITS = 11;
+constexpr int SEL_BINS = 1 << SEL_BITS;
+
+// histogram of digit (x >> shift) & (2^bits - 1) over elements whose higher bits equal st->prefix
+__global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restrict__ sk, int64_t n, uint64_t sk_min,
+                                                        int shift, int bits, int first, const SelState *st,
+                                                        uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[SEL_BINS];
+    for (int i = threadIdx.x; i < SEL_BINS; i += TILE) sh[i] = 0;
+    __syncthreads();
+    const uint64_t prefix = first ? 0 : st->prefix;
+    const int hs = shift + bits;  // bits above the digit must match the prefix
+    const uint32_t dmask = (1u << bits) - 1;
+    for (int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x; i < n; i += (int64_t)gridDim.x * TILE) {
+        const uint64_t x = sk[i] - sk_min;
+        const bool match = first || hs >= 64 || (x >> hs) == (prefix >> hs);
+        const uint32_t d = (uint32_t)(x >> shift) & dmask;
+        const unsigned act = __ballot_sync(__activemask(), match);
+        if (match) {
+            const unsigned peers = __match_any_sync(act, d);
+            if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SEL_BINS; i += TILE)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// choose the bucket holding the k_rem-th largest element; 1 CTA of 1024 threads, 2 bins each
+__global__ void __launch_bounds__(1024) sel_pick_kernel(uint32_t *hist, int shift, int first, uint64_t k, SelState *st) {
+    __shared__ unsigned long long s_scan[1024];
+    const int t = threadIdx.x;
+    const uint32_t h0 = hist[SEL_BINS - 1 - 2 * t], h1 = hist[SEL_BINS - 2 - 2 * t];  // descending bins
+    hist[SEL_BINS - 1 - 2 * t] = 0;
+    hist[SEL_BINS - 2 - 2 * t] = 0;
+    s_scan[t] = (unsigned long long)h0 + h1;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned long long v = t >= d ? s_scan[t - d] : 0;
+        __syncthreads();
+        s_scan[t] += v;
+        __syncthreads();
+    }
+    const unsigned long long k_rem = first ? k : st->k_rem;
+    const unsigned long long c_gt = first ? 0 : st->c_gt;
+    const unsigned long long prefix = first ? 0 : st->prefix;
+    const unsigned long long incl = s_scan[t], excl = incl - ((unsigned long long)h0 + h1);
+    __syncthreads();
+    if (excl < k_rem && k_rem <= incl) {
+        unsigned long long above = excl;
+        int bin = SEL_BINS - 1 - 2 * t;
+        if (above + h0 < k_rem) { above += h0; bin -= 1; }
+        st->prefix = prefix | ((unsigned long long)bin << shift);
+        st->k_rem = k_rem - above;
+        st->c_gt = c_gt + above;
+    }
+}
+
+// ------------------------------------------------------------------ beam cut in arrival order
+// keep x > T, plus the first k_rem arrivals with x == T (Python's stable sort keeps equal keys in
+// arrival order, src/solver.py:453).  Emits (y = sk_max - sk, src index) pairs for the rank sort.
+constexpr int CUT_ITEMS = 8;
+__global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ sk, int64_t n, uint64_t sk_min,
+                                                   uint64_t sk_max, int keep_all, const SelState *st,
+                                                   uint64_t *__restrict__ out_y, uint32_t *__restrict__ out_idx,
+                                                   uint64_t *status_tie, uint64_t *status_keep, Counters *ctr,
+                                                   int ticket_id) {
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_tie_base, s_keep_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t T = keep_all ? 0 : st->prefix, quota = keep_all ? 0 : st->k_rem;
+    const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * CUT_ITEMS;
+    uint64_t x[CUT_ITEMS];
+    uint32_t ties = 0;
+#pragma unroll
+    for (int q = 0; q < CUT_ITEMS; ++q) {
+        x[q] = (b0 + q < n) ? sk[b0 + q] - sk_min : 0;
+        ties += (b0 + q < n) && !keep_all && x[q] == T;
+    }
+    uint32_t tot;
+    uint32_t tie_ex = block_excl_scan(ties, warp_sums, tot);
+    if (threadIdx.x == 0) s_tie_base = keep_all ? 0 : lookback_exclusive(status_tie, tile, tot, 0);
+    __syncthreads();
+    uint64_t tie_rank = s_tie_base + tie_ex;
+    uint32_t keepmask = 0, kept = 0;
+#pragma unroll
+    for (int q = 0; q < CUT_ITEMS; ++q) {
+        bool k = false;
+        if (b0 + q < n) {
+            if (keep_all) k = true;
+            else if (x[q] > T) k = true;
+            else if (x[q] == T) { k = tie_rank < quota; ++tie_rank; }
+        }
+        keepmask |= (uint32_t)k << q;
+        kept += k;
+    }
+    const uint32_t keep_ex = block_excl_scan(kept, warp_sums, tot);
+    if (threadIdx.x == 0) s_keep_base = lookback_exclusive(status_keep, tile, tot, 0);
+    __syncthreads();
+    uint64_t pos = s_keep_base + keep_ex;
+#pragma unroll
+    for (int q = 0; q < CUT_ITEMS; ++q)
+        if (keepmask >> q & 1) {
+            out_y[pos] = (sk_max - sk_min) - x[q];
+            out_idx[pos] = (uint32_t)(b0 + q);
+            ++pos;
+        }
+}
+
+// ------------------------------------------------------------------ stable LSD radix sort of (y, idx) pairs
+constexpr int SORT_BITS = 8;
+constexpr int SORT_BINS = 1 << SORT_BITS;
+constexpr int SORT_ITEMS = 16;                    // per thread; one warp owns 512 consecutive elements
+constexpr int SORT_TILE = TILE * SORT_ITEMS;      // 4096 elements per CTA
+
+__global__ void __launch_bounds__(TILE) sort_hist_kernel(const uint64_t *__restrict__ y, int64_t n, int shift,
+                                                         uint32_t *__restrict__ matrix, uint32_t ntiles) {
+    __shared__ uint32_t sh[SORT_BINS];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    for (int q = 0; q < SORT_ITEMS; ++q) {
+        const int64_t i = base + q * TILE + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(uint32_t)(y[i] >> shift) & (SORT_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    matrix[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = sh[threadIdx.x];  // digit-major
+}
+
+// generic exclusive scan of u32 (decoupled look-back), 256 threads x 8 items
+constexpr int SCAN_ITEMS = 8;
+__global__ void __launch_bounds__(TILE) scan_u32_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                        int64_t n, uint64_t *status, Counters *ctr, int ticket_id) {
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; ++q) {
+        v[q] = (b0 + q < n) ? in[b0 + q] : 0;
+        sum += v[q];
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(sum, warp_sums, tot);
+    if (threadIdx.x == 0) s_base = lookback_exclusive(status, tile, tot, 0);
+    __syncthreads();
+    uint32_t run = (uint32_t)s_base + ex;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; ++q)
+        if (b0 + q < n) { out[b0 + q] = run; run += v[q]; }
+}
+
+__global__ void __launch_bounds__(TILE) sort_scatter_kernel(const uint64_t *__restrict__ y_in,
+                                                            const uint32_t *__restrict__ idx_in, int64_t n, int shift,
+                                                            const uint32_t *__restrict__ matrix_scanned,
+                                                            uint32_t ntiles, uint64_t *__restrict__ y_out,
+                                                            uint32_t *__restrict__ idx_out) {
+    __shared__ uint32_t whist[TILE / 32][SORT_BINS];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (TILE / 32) * SORT_BINS; i += TILE) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)w * (32 * SORT_ITEMS);
+    uint64_t yy[SORT_ITEMS];
+    uint32_t ii[SORT_ITEMS];
+    // pass A: per-warp digit counts over the warp's contiguous 512-element segment
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS; ++q) {
+        const int64_t i = wbase + q * 32 + lane;
+        const bool ok = i < n;
+        yy[q] = ok ? y_in[i] : 0;
+        ii[q] = ok ? idx_in[i] : 0;
+        const uint32_t d = (uint32_t)(yy[q] >> shift) & (SORT_BINS - 1);
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(act, d);
+            if (lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {  // exclusive over warps, plus the tile's global base for each digit
+        const uint32_t d = threadIdx.x;
+        uint32_t run = matrix_scanned[(uint64_t)d * ntiles + blockIdx.x];
+        for (int ww = 0; ww < TILE / 32; ++ww) {
+            const uint32_t c = whist[ww][d];
+            whist[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // pass B: stable scatter
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS; ++q) {
+        const int64_t i = wbase + q * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = (uint32_t)(yy[q] >> shift) & (SORT_BINS - 1);
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(act, d);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+            const uint32_t pos = whist[w][d] + rank;
+            y_out[pos] = yy[q];
+            idx_out[pos] = ii[q];
+            __syncwarp(peers);
+            if (lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+// frontier[rank] = uniq[idx[rank]]
+__global__ void __launch_bounds__(TILE) gather_rec_kernel(const Rec *__restrict__ src, const uint32_t *__restrict__ idx,
+                                                          int64_t n, Rec *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) {
+        Rec r;
+        ld_rec(src + idx[i], r);
+        st_rec(dst + i, r);
+    }
+}
+
+__global__ void __launch_bounds__(TILE) idx_widen_kernel(const uint32_t *__restrict__ idx, int64_t n,
+                                                         int64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) out[i] = idx[i];
+}
+
+// pack / unpack between the C-ABI SoA views (keys, aux, link) and AoS records
+__global__ void __launch_bounds__(TILE) pack_rec_kernel(const spl_key *__restrict__ keys, const uint64_t *__restrict__ aux,
+                                                        int64_t n, Rec *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) {
+        Rec r{keys[i].lo, keys[i].hi & HI_KEY_MASK, aux[i], ~0ull};
+        st_rec(out + i, r);
+    }
+}
+__global__ void __launch_bounds__(TILE) unpack_rec_kernel(const Rec *__restrict__ in, int64_t n, spl_key *__restrict__ keys,
+                                                          uint64_t *__restrict__ aux, uint64_t *__restrict__ link) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) {
+        Rec r;
+        ld_rec(in + i, r);
+        if (keys) { keys[i].lo = r.lo; keys[i].hi = r.hi; }
+        if (aux) aux[i] = r.aux;
+        if (link) link[i] = r.link;
+    }
+}
+__global__ void __launch_bounds__(TILE) flip_scores_kernel(const double *__restrict__ sc, int64_t n,
+                                                           uint64_t *__restrict__ sk, Counters *ctr) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    uint64_t kmin = ~0ull, kmax = 0;
+    if (i < n) {
+        const uint64_t k = flip_f64((uint64_t)__double_as_longlong(sc[i]));
+        sk[i] = k;
+        kmin = kmax = k;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+    }
+    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+        atomicMin(&ctr->sk_min, (unsigned long long)kmin);
+        atomicMax(&ctr->sk_max, (unsigned long long)kmax);
+    }
+}
+
+// move every occupied slot of an old table into a larger one (tags preserved)
+__global__ void __launch_bounds__(TILE) rehash_kernel(const uint64_t *__restrict__ old_table, uint64_t old_cap,
+                                                      uint64_t *__restrict__ table, uint64_t cap, Counters *ctr) {
+    const uint64_t s = (uint64_t)blockIdx.x * TILE + threadIdx.x;
+    if (s >= old_cap) return;
+    uint64_t a, b;
+    ld_cg_u64x2(old_table + (s << 2), a, b);
+    if ((a | b) == 0) return;
+    uint64_t i = slot_of(hash_key(a, b & HI_KEY_MASK), cap);
+    for (int probes = 0; probes < MAX_PROBE; ++probes) {
+        uint64_t oa, ob;
+        cas128(table + (i << 2), 0, 0, a, b, oa, ob);
+        if ((oa | ob) == 0) return;
+        if (++i == cap) i = 0;
+    }
+    atomicExch(&ctr->error, 1u);
+}
+
+}  // namespace spl

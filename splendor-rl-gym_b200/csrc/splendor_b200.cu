@@ -1,0 +1,744 @@
+// splendor_b200.cu -- C-ABI entry points (include/splendor_b200.h) and the native host driver of
+// the level-synchronous search.  Build: nvcc -gencode arch=compute_100a,code=sm_100a (see
+// __graft_entry__.build()).  No CPU fallback: without a usable device every compute call fails.
+#include "../../include/splendor_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "spl_kernels.cuh"
+#include "spl_tables.cuh"
+
+using namespace spl;
+
+static std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grow to at least `bytes` (geometric), optionally preserving the first `keep` bytes
+    cudaError_t ensure(size_t bytes, size_t keep, cudaStream_t st) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = std::max(bytes, cap + cap / 2);
+        ncap = (ncap + 255) & ~(size_t)255;
+        void *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess && ncap > bytes) {  // retry with the exact size
+            cudaGetLastError();
+            ncap = (bytes + 255) & ~(size_t)255;
+            e = cudaMalloc(&np, ncap);
+        }
+        if (e != cudaSuccess) return e;
+        if (keep && p) {
+            e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    void swap(DevBuf &o) { std::swap(p, o.p); std::swap(cap, o.cap); }
+};
+
+struct spl_ctx {
+    int device = 0;
+    std::string err;
+    // visited table
+    uint64_t *table = nullptr;
+    uint64_t cap = 0, max_table_bytes = 0, occupied = 0;
+    uint32_t epoch = 0;
+    uint64_t chunk_parents = 0;
+    // constant tables
+    DevTables *d_tabs = nullptr;
+    uint32_t *d_takes_idx = nullptr;
+    uint16_t *d_takes_edges = nullptr;
+    double *d_lut = nullptr;
+    ScoreLuts luts{};
+    // scalars
+    Counters *d_ctr = nullptr, *h_ctr = nullptr;
+    SelState *d_sel = nullptr, *h_sel = nullptr;
+    uint32_t *d_hist = nullptr;
+    DevBuf status[3];
+    // scratch
+    DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], matrix, matrix2;
+    cudaEvent_t ev[8]{};
+    long long launches = 0;
+};
+
+static int fail(spl_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(c, call)                                                                             \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                 \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? SPL_E_NOMEM : SPL_E_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                            \
+        }                                                                                       \
+    } while (0)
+#define CKS(c, expr)              \
+    do {                          \
+        int s_ = (expr);          \
+        if (s_ != SPL_OK) return s_; \
+    } while (0)
+
+static inline unsigned nblk(int64_t n, int per = TILE) { return (unsigned)((n + per - 1) / per); }
+static inline int bitlen(uint64_t x) { return x ? 64 - __builtin_clzll(x) : 0; }
+
+extern "C" {
+
+int32_t spl_abi_version(void) { return SPL_ABI_VERSION; }
+
+const char *spl_last_error(const spl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+const uint32_t *spl_deck_table(int32_t *n_cards) {
+    if (n_cards) *n_cards = SPL_NUM_CARDS;
+    return SPL_DECK_PACKED;
+}
+
+int32_t spl_host_takes(const uint8_t gems[5], uint8_t out[100 * 5]) {
+    const HostTables &T = host_tables();
+    uint32_t key = 0;
+    for (int c = 0; c < NCOL; ++c) {
+        if (gems[c] > 7) return SPL_E_INVALID;
+        key |= (uint32_t)gems[c] << (3 * c);
+    }
+    const uint32_t e = T.takes_idx[key], n = e & 0xff, off = e >> 8;
+    for (uint32_t i = 0; i < n; ++i)
+        for (int c = 0; c < NCOL; ++c) out[i * 5 + c] = (T.takes_edges[off + i] >> (3 * c)) & 7;
+    return (int32_t)n;
+}
+
+int32_t spl_host_buys(const uint8_t key[5], uint8_t out[90]) {
+    const HostTables &T = host_tables();
+    uint64_t lo = ~0ull, hi = ~0ull;
+    for (int c = 0; c < NCOL; ++c) {
+        if (key[c] > 7) return SPL_E_INVALID;
+        lo &= T.dev.buy_lo[c][key[c]];
+        hi &= T.dev.buy_hi[c][key[c]];
+    }
+    int n = 0;
+    for (int i = 0; i < SPL_NUM_CARDS; ++i) {
+        const int b = 15 + i;
+        if (b < 64 ? (lo >> b) & 1 : (hi >> (b - 64)) & 1) out[n++] = (uint8_t)i;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ context
+static int alloc_table(spl_ctx *c, uint64_t slots, cudaStream_t st) {
+    if (slots >= 0xFFFFFFFEull) slots = 0xFFFFFFFEull;
+    CK(c, cudaMalloc(&c->table, slots * 32));
+    CK(c, cudaMemsetAsync(c->table, 0, slots * 32, st));
+    c->cap = slots;
+    return SPL_OK;
+}
+
+int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, SPL_E_INVALID, "spl_create: null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SPL_E_NODEVICE, "spl_create: no CUDA device (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SPL_E_INVALID, "spl_create: bad device %d", cfg->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, SPL_E_NODEVICE, "spl_create: device %d is sm_%d%d; this build is sm_100a only", cfg->device,
+                    prop.major, prop.minor);
+    spl_ctx *c = new spl_ctx();
+    c->device = cfg->device;
+#define CKC(call)                                                                                             \
+    do {                                                                                                      \
+        cudaError_t e2_ = (call);                                                                             \
+        if (e2_ != cudaSuccess) {                                                                             \
+            cudaGetLastError();                                                                               \
+            int r_ = fail(nullptr, e2_ == cudaErrorMemoryAllocation ? SPL_E_NOMEM : SPL_E_CUDA, "%s: %s", #call, \
+                          cudaGetErrorString(e2_));                                                           \
+            delete c;                                                                                         \
+            return r_;                                                                                        \
+        }                                                                                                     \
+    } while (0)
+    CKC(cudaSetDevice(c->device));
+    size_t free_b = 0, total_b = 0;
+    CKC(cudaMemGetInfo(&free_b, &total_b));
+    c->max_table_bytes = cfg->max_table_bytes ? cfg->max_table_bytes : (uint64_t)(free_b * 0.6);
+    c->chunk_parents = cfg->chunk_parents ? std::min<uint64_t>(cfg->chunk_parents, 16ull << 20) : (4ull << 20);
+    c->chunk_parents = std::max<uint64_t>(c->chunk_parents, TILE);
+    const HostTables &T = host_tables();
+    CKC(cudaMalloc(&c->d_tabs, sizeof(DevTables)));
+    CKC(cudaMemcpy(c->d_tabs, &T.dev, sizeof(DevTables), cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&c->d_takes_idx, T.takes_idx.size() * 4));
+    CKC(cudaMemcpy(c->d_takes_idx, T.takes_idx.data(), T.takes_idx.size() * 4, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&c->d_takes_edges, T.takes_edges.size() * 2));
+    CKC(cudaMemcpy(c->d_takes_edges, T.takes_edges.data(), T.takes_edges.size() * 2, cudaMemcpyHostToDevice));
+    const size_t n_lut = T.lut_pts.size() + T.lut_saved.size() + T.lut_small.size();
+    CKC(cudaMalloc(&c->d_lut, n_lut * 8));
+    CKC(cudaMemcpy(c->d_lut, T.lut_pts.data(), T.lut_pts.size() * 8, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(c->d_lut + T.lut_pts.size(), T.lut_saved.data(), T.lut_saved.size() * 8, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(c->d_lut + T.lut_pts.size() + T.lut_saved.size(), T.lut_small.data(), T.lut_small.size() * 8,
+                   cudaMemcpyHostToDevice));
+    c->luts.pts = c->d_lut;
+    c->luts.saved = c->d_lut + T.lut_pts.size();
+    c->luts.small = c->d_lut + T.lut_pts.size() + T.lut_saved.size();
+    CKC(cudaMalloc(&c->d_ctr, sizeof(Counters)));
+    CKC(cudaMallocHost(&c->h_ctr, sizeof(Counters)));
+    CKC(cudaMalloc(&c->d_sel, sizeof(SelState)));
+    CKC(cudaMallocHost(&c->h_sel, sizeof(SelState)));
+    CKC(cudaMalloc(&c->d_hist, SEL_BINS * 4));
+    CKC(cudaMemset(c->d_hist, 0, SEL_BINS * 4));
+    for (auto &ev : c->ev) CKC(cudaEventCreate(&ev));
+    uint64_t slots = cfg->table_slots ? cfg->table_slots : (1ull << 22);
+    slots = std::min<uint64_t>(slots, c->max_table_bytes / 32);
+    slots = std::max<uint64_t>(slots, 1024);
+    if (alloc_table(c, slots, 0) != SPL_OK) {
+        g_create_error = c->err;
+        delete c;
+        return SPL_E_NOMEM;
+    }
+    CKC(cudaDeviceSynchronize());
+#undef CKC
+    *out = c;
+    return SPL_OK;
+}
+
+int32_t spl_destroy(spl_ctx *c) {
+    if (!c) return SPL_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->table); cudaFree(c->d_tabs); cudaFree(c->d_takes_idx); cudaFree(c->d_takes_edges);
+    cudaFree(c->d_lut); cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr); cudaFree(c->d_sel); cudaFreeHost(c->h_sel);
+    cudaFree(c->d_hist);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    delete c;
+    return SPL_OK;
+}
+
+int32_t spl_reset_visited(spl_ctx *c, void *stream) {
+    if (!c) return SPL_E_INVALID;
+    CK(c, cudaMemsetAsync(c->table, 0, c->cap * 32, (cudaStream_t)stream));
+    c->occupied = 0;
+    c->epoch = 0;
+    return SPL_OK;
+}
+
+int32_t spl_visited_count(spl_ctx *c, int64_t *n_host) {
+    if (!c || !n_host) return SPL_E_INVALID;
+    *n_host = (int64_t)c->occupied;
+    return SPL_OK;
+}
+
+// ------------------------------------------------------------------ internal helpers
+static int zero_ctr(spl_ctx *c, cudaStream_t st) {
+    Counters z;
+    memset(&z, 0, sizeof z);
+    z.sk_min = ~0ull;
+    z.goal_rank = 0x7fffffffffffffffll;
+    *c->h_ctr = z;
+    CK(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, st));
+    return SPL_OK;
+}
+static int read_ctr(spl_ctx *c, cudaStream_t st) {
+    CK(c, cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+static int reset_ticket(spl_ctx *c, int id, cudaStream_t st) {
+    CK(c, cudaMemsetAsync(&c->d_ctr->ticket[id], 0, 4, st));
+    return SPL_OK;
+}
+static int prep_status(spl_ctx *c, int which, size_t ntiles, cudaStream_t st) {
+    CK(c, c->status[which].ensure((ntiles + 1) * 8, 0, st));
+    CK(c, cudaMemsetAsync(c->status[which].p, 0, (ntiles + 1) * 8, st));
+    return SPL_OK;
+}
+
+// grow the visited table so that `need` more inserts keep the load factor <= 0.7 (if memory allows)
+static int ensure_table(spl_ctx *c, uint64_t need, cudaStream_t st) {
+    while ((double)(c->occupied + need) > 0.7 * (double)c->cap) {
+        uint64_t ncap = c->cap * 2;
+        if (ncap >= 0xFFFFFFFEull) ncap = 0xFFFFFFFEull;
+        if (ncap * 32 > c->max_table_bytes) ncap = c->max_table_bytes / 32;
+        if (ncap <= c->cap + c->cap / 8) break;  // cannot grow meaningfully
+        uint64_t *nt = nullptr;
+        cudaError_t e = cudaMalloc(&nt, ncap * 32);
+        if (e != cudaSuccess) { cudaGetLastError(); break; }
+        CK(c, cudaMemsetAsync(nt, 0, ncap * 32, st));
+        rehash_kernel<<<nblk((int64_t)c->cap), TILE, 0, st>>>(c->table, c->cap, nt, ncap, c->d_ctr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CK(c, cudaStreamSynchronize(st));
+        cudaFree(c->table);
+        c->table = nt;
+        c->cap = ncap;
+    }
+    if (c->occupied + need / 8 > c->cap - c->cap / 16)
+        return fail(c, SPL_E_TABLE_FULL, "visited table full: %llu occupied + %llu candidates vs %llu slots (max_table_bytes=%llu)",
+                    (unsigned long long)c->occupied, (unsigned long long)need, (unsigned long long)c->cap,
+                    (unsigned long long)c->max_table_bytes);
+    return SPL_OK;
+}
+
+static int next_epoch(spl_ctx *c, uint64_t &tag) {
+    if (c->epoch >= TAG_MAX) return fail(c, SPL_E_STATE, "epoch tag exhausted");
+    tag = ++c->epoch;
+    return SPL_OK;
+}
+
+// count + offsets for parents front[0..n): leaves total in h_ctr->total_cands (synchronises)
+static int run_count(spl_ctx *c, const Rec *front, int64_t n, cudaStream_t st) {
+    const unsigned nt = nblk(n);
+    CK(c, c->off.ensure((size_t)n * 4 + 4, 0, st));
+    CKS(c, prep_status(c, 0, nt, st));
+    CKS(c, reset_ticket(c, 0, st));
+    count_scan_kernel<<<nt, TILE, 0, st>>>(front, n, c->d_tabs, c->d_takes_idx, c->off.as<uint32_t>(),
+                                            c->status[0].as<uint64_t>(), c->d_ctr, 0);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return read_ctr(c, st);
+}
+
+// radix select of the k-th largest score key; leaves threshold/quota in d_sel (x-space) and h_sel
+static int run_select(spl_ctx *c, const uint64_t *sk, int64_t n, int64_t k, uint64_t sk_min, uint64_t sk_max,
+                      cudaStream_t st) {
+    const int nbits = bitlen(sk_max - sk_min);
+    const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
+    int top = nbits, first = 1;
+    if (nbits == 0) {  // every score equal: threshold x = 0, quota k
+        c->h_sel->prefix = 0; c->h_sel->k_rem = (unsigned long long)k; c->h_sel->c_gt = 0; c->h_sel->pad = 0;
+        CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
+        CK(c, cudaStreamSynchronize(st));
+        return SPL_OK;
+    }
+    while (top > 0) {
+        const int bits = std::min(SEL_BITS, top), shift = top - bits;
+        sel_hist_kernel<<<grid, TILE, 0, st>>>(sk, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+        sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, shift, first, (uint64_t)k, c->d_sel);
+        c->launches += 2;
+        first = 0;
+        top = shift;
+    }
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+// arrival-order cut + stable descending rank sort.  On return idx[*which] holds the kept source
+// indices in rank order (kept = min(k, n)).
+static int run_cut_sort(spl_ctx *c, const uint64_t *sk, int64_t n, int64_t k, uint64_t sk_min, uint64_t sk_max,
+                        int *which, int64_t *kept_out, cudaStream_t st) {
+    const int64_t kept = std::min(n, k);
+    const int keep_all = n <= k;
+    if (!keep_all) CKS(c, run_select(c, sk, n, k, sk_min, sk_max, st));
+    const uint64_t T = keep_all ? 0 : c->h_sel->prefix;
+    for (int b = 0; b < 2; ++b) {
+        CK(c, c->y[b].ensure((size_t)kept * 8 + 8, 0, st));
+        CK(c, c->idx[b].ensure((size_t)kept * 4 + 4, 0, st));
+    }
+    const unsigned ct = nblk(n, TILE * CUT_ITEMS);
+    CKS(c, prep_status(c, 1, ct, st));
+    CKS(c, prep_status(c, 2, ct, st));
+    CKS(c, reset_ticket(c, 1, st));
+    cut_kernel<<<ct, TILE, 0, st>>>(sk, n, sk_min, sk_max, keep_all, c->d_sel, c->y[0].as<uint64_t>(),
+                                     c->idx[0].as<uint32_t>(), c->status[1].as<uint64_t>(),
+                                     c->status[2].as<uint64_t>(), c->d_ctr, 1);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    // y = sk_max - sk in [0, sk_max - sk_min - T]
+    const int nbits = bitlen((sk_max - sk_min) - T);
+    int cur = 0;
+    const unsigned nt = nblk(kept, SORT_TILE);
+    if (nbits > 0 && kept > 1) {
+        const size_t msz = (size_t)SORT_BINS * nt;
+        CK(c, c->matrix.ensure(msz * 4, 0, st));
+        CK(c, c->matrix2.ensure(msz * 4, 0, st));
+        const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
+        for (int shift = 0; shift < nbits; shift += SORT_BITS) {
+            sort_hist_kernel<<<nt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), kept, shift, c->matrix.as<uint32_t>(), nt);
+            CKS(c, prep_status(c, 1, st_tiles, st));
+            CKS(c, reset_ticket(c, 2, st));
+            scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
+                                                        c->status[1].as<uint64_t>(), c->d_ctr, 2);
+            sort_scatter_kernel<<<nt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), c->idx[cur].as<uint32_t>(), kept, shift,
+                                                      c->matrix2.as<uint32_t>(), nt, c->y[cur ^ 1].as<uint64_t>(),
+                                                      c->idx[cur ^ 1].as<uint32_t>());
+            c->launches += 3;
+            cur ^= 1;
+        }
+        CK(c, cudaGetLastError());
+    }
+    *which = cur;
+    *kept_out = kept;
+    return SPL_OK;
+}
+
+// ------------------------------------------------------------------ stage operators
+int32_t spl_expand(spl_ctx *c, const spl_key *keys, const uint64_t *aux, int64_t n, spl_key *ck, uint64_t *ca,
+                   uint64_t *cl, int64_t cap, int64_t *n_out, void *stream) {
+    if (!c || !n_out || n < 0 || n > (16ll << 20)) return fail(c, SPL_E_INVALID, "spl_expand: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0) return SPL_OK;
+    CK(c, c->tmp_rec.ensure((size_t)n * 32, 0, st));
+    pack_rec_kernel<<<nblk(n), TILE, 0, st>>>(keys, aux, n, c->tmp_rec.as<Rec>());
+    ++c->launches;
+    CKS(c, zero_ctr(c, st));
+    CKS(c, run_count(c, c->tmp_rec.as<Rec>(), n, st));
+    const int64_t total = (int64_t)c->h_ctr->total_cands;
+    *n_out = total;
+    if (total > cap) return fail(c, SPL_E_CAPACITY, "spl_expand: %lld successors, capacity %lld", (long long)total, (long long)cap);
+    if (total == 0) return SPL_OK;
+    CK(c, c->tmp_rec2.ensure((size_t)total * 32, 0, st));
+    expand_kernel<MODE_LIST><<<nblk(n), TILE, sizeof(ExpandSmem), st>>>(
+        c->tmp_rec.as<Rec>(), n, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
+        nullptr, 0, 0, nullptr, c->tmp_rec2.as<Rec>(), 0, c->d_ctr);
+    unpack_rec_kernel<<<nblk(total), TILE, 0, st>>>(c->tmp_rec2.as<Rec>(), total, ck, ca, cl);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+int32_t spl_dedup(spl_ctx *c, const spl_key *ck, const uint64_t *ca, int64_t n, spl_key *uk, uint64_t *ua, int64_t *usrc,
+                  int64_t *n_out, void *stream) {
+    if (!c || !n_out || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dedup: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0) return SPL_OK;
+    CKS(c, zero_ctr(c, st));
+    CKS(c, ensure_table(c, (uint64_t)n, st));
+    uint64_t tag;
+    CKS(c, next_epoch(c, tag));
+    CK(c, c->cand_slot.ensure((size_t)n * 4, 0, st));
+    probe_list_kernel<<<nblk(n), TILE, 0, st>>>(ck, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    if (c->h_ctr->error) return fail(c, SPL_E_TABLE_FULL, "spl_dedup: probe overflow (table full)");
+    const int64_t n_new = (int64_t)c->h_ctr->n_new;
+    c->occupied += n_new;
+    *n_out = n_new;
+    if (n_new == 0) return SPL_OK;
+    CK(c, c->tmp_rec.ensure((size_t)n_new * 32, 0, st));
+    const unsigned nt = nblk(n, TILE * 32);
+    CKS(c, prep_status(c, 0, nt, st));
+    CKS(c, reset_ticket(c, 0, st));
+    resolve_kernel<SRC_LIST, false><<<nt, TILE, sizeof(ResolveSmem), st>>>(
+        nullptr, 0, c->d_tabs, c->d_takes_idx, c->d_takes_edges, nullptr, (uint32_t)n, c->table,
+        c->cand_slot.as<uint32_t>(), ck, ca, 0, 0, c->tmp_rec.as<Rec>(), nullptr, usrc, 0, 0, c->luts,
+        c->status[0].as<uint64_t>(), c->d_ctr, 0);
+    unpack_rec_kernel<<<nblk(n_new), TILE, 0, st>>>(c->tmp_rec.as<Rec>(), n_new, uk, ua, nullptr);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+int32_t spl_score(spl_ctx *c, int32_t heuristic, int32_t noise, const spl_key *keys, const uint64_t *aux, int64_t n,
+                  double *scores, void *stream) {
+    if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_score: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return SPL_OK;
+    score_kernel<<<nblk(n), TILE, 0, st>>>(keys, aux, n, heuristic, noise, c->luts, scores);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+int32_t spl_topk(spl_ctx *c, const double *scores, const spl_key *keys, int64_t n, int64_t k, int32_t tie_policy,
+                 int64_t *out_idx, int64_t *n_out, void *stream) {
+    (void)keys;
+    if (!c || !n_out || n < 0 || n >= (1ll << 32) || k < 0) return fail(c, SPL_E_INVALID, "spl_topk: bad arguments");
+    if (tie_policy != SPL_TIE_STABLE) return fail(c, SPL_E_INVALID, "spl_topk: tie policy %d not available yet", tie_policy);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0 || k == 0) return SPL_OK;
+    CKS(c, zero_ctr(c, st));
+    CK(c, c->sk.ensure((size_t)n * 8, 0, st));
+    flip_scores_kernel<<<nblk(n), TILE, 0, st>>>(scores, n, c->sk.as<uint64_t>(), c->d_ctr);
+    ++c->launches;
+    CKS(c, read_ctr(c, st));
+    int which = 0;
+    int64_t kept = 0;
+    CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), n, k, c->h_ctr->sk_min, c->h_ctr->sk_max, &which, &kept, st));
+    idx_widen_kernel<<<nblk(kept), TILE, 0, st>>>(c->idx[which].as<uint32_t>(), kept, out_idx);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(st));
+    *n_out = kept;
+    return SPL_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ fused solver
+struct spl_solver {
+    spl_ctx *c = nullptr;
+    int goal = 15, use_h = 0, heuristic = 0, tie = 0, noise = 0, keep_links = 1;
+    int64_t beam = 300000;
+    DevBuf front, uniq;
+    int64_t n_front = 0;
+    int level = 0;
+    bool ended = false;
+    int64_t goal_rank = -1;
+    std::vector<DevBuf *> links;   // per level: link column of the queue (device, 8 B per state)
+    std::vector<int64_t> level_n;
+    ~spl_solver() { for (auto *b : links) delete b; }
+};
+
+static int save_links(spl_solver *s, cudaStream_t st) {
+    spl_ctx *c = s->c;
+    DevBuf *b = new DevBuf();
+    s->links.push_back(b);
+    s->level_n.push_back(s->n_front);
+    if (!s->keep_links || s->n_front == 0) return SPL_OK;
+    CK(c, b->ensure((size_t)s->n_front * 8, 0, st));
+    unpack_rec_kernel<<<nblk(s->n_front), TILE, 0, st>>>(s->front.as<Rec>(), s->n_front, nullptr, nullptr, b->as<uint64_t>());
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+extern "C" {
+
+int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux, int32_t goal, int32_t use_h,
+                          int32_t heuristic, int64_t beam, int32_t tie, int32_t noise, int32_t keep_links,
+                          spl_solver **out) {
+    if (!c || !root_key || !out) return fail(c, SPL_E_INVALID, "spl_solver_create: null argument");
+    if (use_h && beam < 1) return fail(c, SPL_E_INVALID, "spl_solver_create: beam_width must be >= 1");
+    if (use_h && tie != SPL_TIE_STABLE) return fail(c, SPL_E_INVALID, "spl_solver_create: tie policy %d not available yet", tie);
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = 0;
+    spl_solver *s = new spl_solver();
+    s->c = c; s->goal = goal; s->use_h = use_h; s->heuristic = heuristic; s->beam = beam; s->tie = tie;
+    s->noise = noise; s->keep_links = keep_links;
+    int rc = spl_reset_visited(c, st);
+    if (rc == SPL_OK) {
+        Rec r{root_key->lo, root_key->hi & HI_KEY_MASK, root_aux, ~0ull};
+        cudaError_t e = s->front.ensure(32, 0, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->front.p, &r, 32, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) rc = fail(c, SPL_E_CUDA, "root upload: %s", cudaGetErrorString(e));
+    }
+    if (rc == SPL_OK) rc = zero_ctr(c, st);
+    if (rc == SPL_OK) {  // trail = {self: None}
+        uint64_t tag;
+        rc = next_epoch(c, tag);
+        if (rc == SPL_OK) {
+            cudaError_t e = c->cand_slot.ensure(4, 0, st);
+            if (e != cudaSuccess) rc = fail(c, SPL_E_NOMEM, "cand_slot alloc");
+            else {
+                probe_list_kernel<<<1, TILE, 0, st>>>(reinterpret_cast<const spl_key *>(s->front.p), 1, c->table, c->cap, tag,
+                                                      c->cand_slot.as<uint32_t>(), c->d_ctr);
+                ++c->launches;
+                c->occupied = 1;
+            }
+        }
+    }
+    s->n_front = 1;
+    if (rc == SPL_OK) rc = save_links(s, st);
+    if (rc == SPL_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(c, SPL_E_CUDA, "solver create sync failed");
+    if (rc != SPL_OK) { delete s; return rc; }
+    *out = s;
+    return SPL_OK;
+}
+
+int32_t spl_solver_destroy(spl_solver *s) {
+    if (s) { cudaSetDevice(s->c->device); cudaDeviceSynchronize(); delete s; }
+    return SPL_OK;
+}
+
+int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
+    if (!s || !info) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    if (s->ended) return fail(c, SPL_E_STATE, "spl_solver_step: the search has already ended");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    memset(info, 0, sizeof *info);
+    info->level = s->level;
+    info->frontier = s->n_front;
+    info->goal_rank = -1;
+    const int64_t n = s->n_front;
+    const Rec *front = s->front.as<Rec>();
+    float ms[4] = {0, 0, 0, 0};
+    // ---- goal test on the queue (src/solver.py:443-445): the first state in queue order with
+    // pts >= goal ends the search; the states before it would be expanded and discarded.
+    CKS(c, zero_ctr(c, st));
+    goal_kernel<<<nblk(n), TILE, 0, st>>>(front, n, s->goal, c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    if (c->h_ctr->goal_rank != 0x7fffffffffffffffll) {
+        s->ended = true;
+        s->goal_rank = c->h_ctr->goal_rank;
+        info->ended = 1;
+        info->goal_rank = s->goal_rank;
+        info->visited = (int64_t)c->occupied;
+        info->table_slots = c->cap;
+        return SPL_OK;
+    }
+    // ---- expand + dedup by chunks of parents
+    int64_t n_uniq = 0, generated = 0;
+    uint64_t sk_min = ~0ull, sk_max = 0;
+    for (int64_t p0 = 0; p0 < n; p0 += (int64_t)c->chunk_parents) {
+        const int64_t np = std::min<int64_t>((int64_t)c->chunk_parents, n - p0);
+        const unsigned nt = nblk(np);
+        CKS(c, zero_ctr(c, st));
+        CK(c, cudaEventRecord(c->ev[0], st));
+        CKS(c, run_count(c, front + p0, np, st));
+        const uint64_t total = c->h_ctr->total_cands;
+        generated += (int64_t)total;
+        if (total == 0) continue;
+        if (total >= 0xFFFFFFFFull) return fail(c, SPL_E_INVALID, "chunk produced %llu candidates (>= 2^32)", (unsigned long long)total);
+        CKS(c, ensure_table(c, total, st));
+        uint64_t tag;
+        CKS(c, next_epoch(c, tag));
+        CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
+        expand_kernel<MODE_PROBE><<<nt, TILE, sizeof(ExpandSmem), st>>>(
+            front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
+            c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev[1], st));
+        CKS(c, read_ctr(c, st));
+        if (c->h_ctr->error) return fail(c, SPL_E_TABLE_FULL, "visited table full during level %d (slots=%llu, occupied=%llu)",
+                                         s->level, (unsigned long long)c->cap, (unsigned long long)c->occupied);
+        const int64_t n_new = (int64_t)c->h_ctr->n_new;
+        c->occupied += n_new;
+        if (n_new) {
+            CK(c, s->uniq.ensure((size_t)(n_uniq + n_new) * 32, (size_t)n_uniq * 32, st));
+            if (s->use_h) CK(c, c->sk.ensure((size_t)(n_uniq + n_new) * 8, (size_t)n_uniq * 8, st));
+            CKS(c, prep_status(c, 0, nt, st));
+            CKS(c, reset_ticket(c, 0, st));
+            CK(c, cudaEventRecord(c->ev[2], st));
+            if (s->use_h)
+                resolve_kernel<SRC_PARENT, true><<<nt, TILE, sizeof(ResolveSmem), st>>>(
+                    front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
+                    c->table, c->cand_slot.as<uint32_t>(), nullptr, nullptr, p0, (uint64_t)n_uniq, s->uniq.as<Rec>(),
+                    c->sk.as<uint64_t>(), nullptr, s->heuristic, s->noise, c->luts, c->status[0].as<uint64_t>(), c->d_ctr, 0);
+            else
+                resolve_kernel<SRC_PARENT, false><<<nt, TILE, sizeof(ResolveSmem), st>>>(
+                    front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
+                    c->table, c->cand_slot.as<uint32_t>(), nullptr, nullptr, p0, (uint64_t)n_uniq, s->uniq.as<Rec>(),
+                    nullptr, nullptr, s->heuristic, s->noise, c->luts, c->status[0].as<uint64_t>(), c->d_ctr, 0);
+            ++c->launches;
+            CK(c, cudaGetLastError());
+            CK(c, cudaEventRecord(c->ev[3], st));
+            CKS(c, read_ctr(c, st));
+            if ((int64_t)c->h_ctr->n_emitted != n_uniq + n_new)
+                return fail(c, SPL_E_CUDA, "internal: emitted %llu winners, expected %lld", (unsigned long long)c->h_ctr->n_emitted,
+                            (long long)(n_uniq + n_new));
+            if (s->use_h) { sk_min = std::min<uint64_t>(sk_min, c->h_ctr->sk_min); sk_max = std::max<uint64_t>(sk_max, c->h_ctr->sk_max); }
+            n_uniq += n_new;
+            float t;
+            cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
+            ms[1] += t;
+        }
+        float t;
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
+        ms[0] += t;
+    }
+    info->expanded = n;
+    info->generated = generated;
+    info->unique = n_uniq;
+    // ---- beam cut (src/solver.py:452-456) or plain BFS hand-over
+    int64_t kept = n_uniq;
+    if (s->use_h && n_uniq > 0) {
+        int which = 0;
+        CK(c, cudaEventRecord(c->ev[4], st));
+        CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), n_uniq, s->beam, sk_min, sk_max, &which, &kept, st));
+        CK(c, cudaEventRecord(c->ev[5], st));
+        CK(c, s->front.ensure((size_t)kept * 32, 0, st));
+        gather_rec_kernel<<<nblk(kept), TILE, 0, st>>>(s->uniq.as<Rec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<Rec>());
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev[6], st));
+        CK(c, cudaStreamSynchronize(st));
+        float t;
+        cudaEventElapsedTime(&t, c->ev[4], c->ev[5]);
+        ms[2] = t;
+        cudaEventElapsedTime(&t, c->ev[5], c->ev[6]);
+        ms[3] = t;
+    } else {
+        s->front.swap(s->uniq);
+    }
+    s->n_front = kept;
+    s->level += 1;
+    info->kept = kept;
+    info->visited = (int64_t)c->occupied;
+    info->table_slots = c->cap;
+    info->ms_expand = ms[0]; info->ms_resolve = ms[1]; info->ms_select = ms[2]; info->ms_sort = ms[3];
+    if (kept == 0) {  // frontier exhausted: `puzzle` is the last dequeued state (src/solver.py:438,459)
+        s->ended = true;
+        s->goal_rank = n - 1;
+        s->n_front = n;
+        s->level -= 1;
+        info->ended = 1;
+        return SPL_OK;
+    }
+    CKS(c, save_links(s, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+int32_t spl_solver_frontier(spl_solver *s, const spl_key **keys, const uint64_t **aux, const uint64_t **link, int64_t *n) {
+    // AoS view: the three pointers address fields of 32-byte records (stride 32 bytes).
+    if (!s || !n) return SPL_E_INVALID;
+    const char *b = reinterpret_cast<const char *>(s->front.p);
+    if (keys) *keys = reinterpret_cast<const spl_key *>(b);
+    if (aux) *aux = reinterpret_cast<const uint64_t *>(b + 16);
+    if (link) *link = reinterpret_cast<const uint64_t *>(b + 24);
+    *n = s->n_front;
+    return SPL_OK;
+}
+
+int32_t spl_solver_path(spl_solver *s, int64_t *ranks, int32_t *ordinals, int32_t cap, int32_t *n_moves) {
+    if (!s || !ranks || !ordinals || !n_moves) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    if (!s->ended) return fail(c, SPL_E_STATE, "spl_solver_path: the search has not ended");
+    if (!s->keep_links) return fail(c, SPL_E_STATE, "spl_solver_path: solver was created with keep_links = 0");
+    const int L = s->level;  // level index of the final state
+    if (L + 1 > cap) return fail(c, SPL_E_CAPACITY, "spl_solver_path: need %d entries", L + 1);
+    CK(c, cudaSetDevice(c->device));
+    int64_t r = s->goal_rank;
+    for (int l = L; l >= 0; --l) {
+        ranks[l] = r;
+        if (l > 0) {
+            uint64_t link = 0;
+            CK(c, cudaMemcpy(&link, s->links[l]->as<uint64_t>() + r, 8, cudaMemcpyDeviceToHost));
+            ordinals[l - 1] = (int32_t)(link & 0xff);
+            r = (int64_t)(link >> 8);
+        }
+    }
+    *n_moves = L;
+    return SPL_OK;
+}
+
+}  // extern "C"

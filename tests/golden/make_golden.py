@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Generate golden fixtures for the frontier-expansion path FROM THE REFERENCE ITSELF.
+
+Runs only in the authoring container (needs /root/reference); the GPU box never runs
+this.  It imports the unmodified reference modules (src/solver.py, src/gems.py,
+src/buys.py, src/cardparser.py) and drives them with a stepper that mirrors the
+`while queue` loop of src/solver.py:434-457 while calling the reference's own
+`State.__iter__`, `State.__hash__`, `HEURISTICS[...]` and `sorted(...)`.
+
+The only patches applied to the reference are the ones SURVEY.md §8a-N names:
+  * `src.buys.BUYS_PATH` -> a /tmp file (the reference tree is read-only),
+  * `src.solver.randint` -> a deterministic noise source (the reference draws its
+    tie-break noise from the unseeded global Mersenne Twister),
+  * plug-in entries added to `HEURISTICS` (the reference's own extension point,
+    src/solver.py:299-305,429) for the key-tie-break (`det`) policy.
+
+Usage:  python tests/golden/make_golden.py [--bfs-depth 8] [--out tests/golden]
+"""
+import argparse
+import hashlib
+import json
+import os
+import struct
+import sys
+import time
+from pathlib import Path
+
+REF = os.environ.get('SPLENDOR_REFERENCE', '/root/reference')
+import setuptools  # noqa: E402  (more_itertools is vendored inside setuptools)
+
+sys.path.append(os.path.join(os.path.dirname(setuptools.__file__), '_vendor'))
+sys.path.insert(0, REF)
+
+import src.buys as ref_buys  # noqa: E402
+
+ref_buys.BUYS_PATH = Path('/tmp/splendor_ref_buys.pickle')
+
+import src.solver as ref_solver  # noqa: E402
+from src.gems import get_takes, subtract_with_bonus, take_gems  # noqa: E402
+from src.solver import HEURISTICS, State, deck  # noqa: E402
+
+M64 = (1 << 64) - 1
+
+
+def key_int(s) -> int:
+    """Canonical 128-bit key: card mask << 15 | gems (3 bits each)."""
+    m = 0
+    for c in s.cards:
+        m |= 1 << c
+    g = 0
+    for i, x in enumerate(s.gems):
+        g |= x << (3 * i)
+    return (m << 15) | g
+
+
+def mix64(x: int) -> int:
+    """splitmix64 finaliser over the folded 128-bit key (noise policy `hash`)."""
+    x = (x ^ (x >> 64)) & M64
+    x = (x + 0x9E3779B97F4A7C15) & M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+    return x ^ (x >> 31)
+
+
+class Noise:
+    """Deterministic stand-in for `random.randint` inside src.solver."""
+
+    def __init__(self):
+        self.mode = 'const'
+        self.cur = 50
+
+    def __call__(self, a, b):
+        return self.cur
+
+
+NOISE = Noise()
+ref_solver.randint = NOISE
+
+
+def _with_noise(fn):
+    def h(s):
+        if NOISE.mode == 'hash':
+            NOISE.cur = 1 + mix64(key_int(s)) % 100
+        else:
+            NOISE.cur = 50
+        return fn(s)
+    return h
+
+
+BASE = {n: HEURISTICS[n] for n in ('simple', 'balanced', 'aggressive', 'efficiency', 'competitive')}
+for _n, _f in BASE.items():
+    HEURISTICS[_n + '@stable'] = _with_noise(_f)                       # ties -> arrival order
+    HEURISTICS[_n + '@det'] = (lambda f: (lambda s: (f(s), key_int(s))))(_with_noise(_f))  # ties -> key desc
+
+
+def level_digest(states, parents=None):
+    """Order-independent sums + order-dependent sha over (key, saved) records."""
+    n = len(states)
+    sl = sh = xl = xh = 0
+    ssaved = spts = 0
+    h = hashlib.sha256()
+    for s in states:
+        k = key_int(s)
+        lo, hi = k & M64, k >> 64
+        sl = (sl + lo) & M64
+        sh = (sh + hi) & M64
+        xl ^= lo
+        xh ^= hi
+        ssaved += s.saved
+        spts += s.pts
+        h.update(struct.pack('<QQH', lo, hi, s.saved))
+    d = dict(n=n, sum_lo=sl, sum_hi=sh, xor_lo=xl, xor_hi=xh, sum_saved=ssaved, sum_pts=spts,
+             sha=h.hexdigest())
+    if parents is not None:
+        d['sum_parent_rank'] = sum(p for p, _ in parents)
+        d['sum_ordinal'] = sum(o for _, o in parents)
+    return d
+
+
+def stepper(goal_pts, use_heuristic, hname, beam, max_levels=None, keep_levels=False):
+    """Mirror of src/solver.py:425-457 that records per-level digests."""
+    root = State.newgame()
+    queue = [root]
+    trail = {root: None}
+    heuristic = HEURISTICS.get(hname, ref_solver.simple_heuristic)
+    levels = []
+    expanded_total = generated_total = 0
+    turn = 0
+    puzzle = root
+    t0 = time.time()
+    kept_levels = []
+    while queue:
+        next_queue = []
+        links = []
+        expanded = generated = 0
+        goal_rank = None
+        for rank, puzzle in enumerate(queue):
+            if puzzle.pts >= goal_pts:
+                next_queue.clear()
+                links.clear()
+                goal_rank = rank
+                break
+            expanded += 1
+            for ordinal, nxt in enumerate(puzzle):
+                generated += 1
+                if nxt in trail:
+                    continue
+                trail[nxt] = puzzle
+                next_queue.append(nxt)
+                links.append((rank, ordinal))
+        expanded_total += expanded
+        generated_total += generated
+        rec = dict(level=turn, frontier=len(queue), expanded=expanded, generated=generated,
+                   goal_rank=goal_rank, unique=level_digest(next_queue, links))
+        if use_heuristic:
+            order = sorted(range(len(next_queue)), key=lambda i: heuristic(next_queue[i]), reverse=True)[:beam]
+            queue = [next_queue[i] for i in order]
+            rec['kept'] = level_digest(queue, [links[i] for i in order])
+        else:
+            queue = next_queue
+        rec['secs'] = round(time.time() - t0, 3)
+        levels.append(rec)
+        if keep_levels:
+            kept_levels.append(queue)
+        turn += 1
+        print(f'  level {turn}: frontier={len(queue)} generated={generated} t={rec["secs"]}s', file=sys.stderr)
+        if max_levels is not None and turn >= max_levels:
+            break
+    sol = []
+    while puzzle:
+        sol.append(puzzle)
+        puzzle = trail[puzzle]
+    sol.reverse()
+    out = dict(goal=goal_pts, use_heuristic=use_heuristic, heuristic=hname, beam=beam,
+               moves=len(sol) - 1, expanded=expanded_total, generated=generated_total,
+               visited=len(trail), levels=levels,
+               path=[dict(repr=repr(s), key=str(key_int(s)), pts=s.pts, saved=s.saved,
+                          bonus=list(s.bonus), cards=list(s.cards), gems=list(s.gems)) for s in sol])
+    return (out, kept_levels) if keep_levels else out
+
+
+def gen_tables():
+    takes = get_takes()
+    h = hashlib.sha256()
+    edges = 0
+    for g in sorted(takes):
+        h.update(bytes(g))
+        h.update(struct.pack('<H', len(takes[g])))
+        for t in takes[g]:
+            h.update(bytes(t))
+            edges += 1
+    buys = ref_buys.possible_buys()
+    hb = hashlib.sha256()
+    refs = 0
+    for g in sorted(buys):
+        hb.update(bytes(g))
+        hb.update(struct.pack('<H', len(buys[g])))
+        hb.update(bytes(buys[g]))
+        refs += len(buys[g])
+    sample_hands = [(0,0,0,0,0),(6,0,0,0,0),(7,0,0,0,0),(2,1,1,0,0),(2,2,2,1,1),(4,4,0,0,0),
+                    (3,3,2,0,0),(3,3,3,0,0),(4,4,1,0,0),(2,2,2,2,2),(7,3,0,0,0),(4,3,2,1,0),
+                    (1,2,0,0,3),(0,0,2,2,6),(3,2,2,2,1),(5,5,0,0,0),(7,2,1,0,0),(1,1,1,1,6)]
+    sample_keys = [(0,0,0,0,0),(0,0,0,0,2),(0,4,0,0,0),(0,0,0,2,4),(4,4,0,1,0),(7,7,7,7,7),
+                   (3,3,3,3,3),(2,5,1,0,7),(6,0,6,0,6)]
+    return dict(
+        deck=[dict(cost=list(c.cost), pt=c.pt, bonus=c.bonus.value, str_id=c.str_id) for c in deck],
+        takes=dict(keys=len(takes), live=sum(1 for v in takes.values() if v), edges=edges,
+                   max_fanout=max(len(v) for v in takes.values()), sha=h.hexdigest(),
+                   samples={','.join(map(str, g)): [list(t) for t in take_gems(g)] for g in sample_hands}),
+        buys=dict(keys=len(buys), refs=refs, sha=hb.hexdigest(),
+                  samples={','.join(map(str, g)): list(buys[g]) for g in sample_keys}),
+        subtract_with_bonus=[dict(gems=g, cost=c, bonus=b, out=[list(subtract_with_bonus(g, c, b)[0]),
+                                                               subtract_with_bonus(g, c, b)[1]])
+                             for g, c, b in [((5,4,3,2,1),(1,2,3,4,5),(0,1,2,3,4)),
+                                             ((4,3,0,7,2),(0,0,0,5,0),(0,0,0,0,0)),
+                                             ((4,3,0,2,2),(0,0,0,0,3),(1,0,0,0,0)),
+                                             ((7,7,7,7,7),(3,3,5,3,0),(2,0,6,1,1))]],
+    )
+
+
+def gen_successors_and_scores(levels, per_level=24):
+    """Sample reachable states; record their full ordered successor lists and f64 scores."""
+    import random
+    rng = random.Random(1234)
+    picks = []
+    for q in levels:
+        picks += rng.sample(q, min(per_level, len(q)))
+    succ = []
+    for s in picks:
+        kids = [dict(key=str(key_int(c)), saved=c.saved, pts=c.pts, bonus=list(c.bonus)) for c in s]
+        succ.append(dict(cards=list(s.cards), gems=list(s.gems), bonus=list(s.bonus), pts=s.pts,
+                         saved=s.saved, key=str(key_int(s)), children=kids))
+    scores = []
+    for s in picks:
+        row = dict(key=str(key_int(s)), saved=s.saved, pts=s.pts, bonus=list(s.bonus),
+                   gems=list(s.gems), ncards=len(s.cards))
+        for mode in ('const', 'hash'):
+            NOISE.mode = mode
+            for n in ('simple', 'balanced', 'aggressive', 'efficiency'):
+                v = HEURISTICS[n + '@stable'](s)
+                row[f'{n}:{mode}'] = struct.unpack('<Q', struct.pack('<d', v))[0]
+        NOISE.mode = 'const'
+        scores.append(row)
+    # synthetic wide-range states (as tests/test_heuristics.py builds them: fields need not be consistent)
+    for pts, saved, bonus, gems, ncards in [(0,0,(0,0,0,0,0),(0,0,0,0,0),0),(2,5,(0,0,0,0,0),(0,0,0,0,0),0),
+                                            (12,5,(0,0,0,0,0),(0,0,0,0,0),0),(15,28,(3,2,4,1,5),(1,0,2,0,0),15),
+                                            (22,61,(5,5,5,4,4),(0,0,0,0,0),23),(7,1000,(18,0,0,0,0),(7,3,0,0,0),18),
+                                            (140,65535,(18,18,18,18,18),(2,2,2,2,2),90)]:
+        cards = tuple(range(ncards))
+        s = State(cards=cards, bonus=bonus, gems=gems, pts=pts, saved=saved)
+        row = dict(key=str(key_int(s)), saved=saved, pts=pts, bonus=list(bonus), gems=list(gems), ncards=ncards)
+        for mode in ('const', 'hash'):
+            NOISE.mode = mode
+            for n in ('simple', 'balanced', 'aggressive', 'efficiency'):
+                v = HEURISTICS[n + '@stable'](s)
+                row[f'{n}:{mode}'] = struct.unpack('<Q', struct.pack('<d', v))[0]
+        NOISE.mode = 'const'
+        scores.append(row)
+    return succ, scores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--bfs-depth', type=int, default=8)
+    ap.add_argument('--out', default=str(Path(__file__).parent))
+    ap.add_argument('--only', default='')
+    a = ap.parse_args()
+    out = Path(a.out)
+    only = set(a.only.split(',')) if a.only else None
+
+    def want(x):
+        return only is None or x in only
+
+    if want('tables'):
+        json.dump(gen_tables(), open(out / 'tables.json', 'w'), indent=0)
+        print('tables done', file=sys.stderr)
+
+    if want('bfs'):
+        t0 = time.time()
+        bfs, lv = stepper(10**9, False, 'simple', 0, max_levels=a.bfs_depth, keep_levels=True)
+        bfs['path'] = []
+        bfs['wall_s'] = round(time.time() - t0, 2)
+        json.dump(bfs, open(out / 'bfs_levels.json', 'w'), indent=0)
+        succ, scores = gen_successors_and_scores([[State.newgame()]] + lv[:7])
+        json.dump(succ, open(out / 'successors.json', 'w'))
+        json.dump(scores, open(out / 'scores.json', 'w'), indent=0)
+        del lv
+        # reference's own unmodified solve(): BFS winning lines (tests/test_solver.py:92-113)
+        lines = {}
+        for goal in (3, 4):
+            lines[str(goal)] = [repr(s) for s in State.newgame().solve(goal_pts=goal, verbose=False)]
+        json.dump(lines, open(out / 'bfs_lines.json', 'w'), indent=0)
+
+    if want('beam'):
+        runs = []
+        cfgs = []
+        for h in ('simple', 'balanced', 'aggressive', 'efficiency'):
+            for pol in ('stable', 'det'):
+                for noise in ('const', 'hash'):
+                    cfgs.append((h, pol, noise, 6, 1000))
+                    cfgs.append((h, pol, noise, 15, 1000))
+        cfgs += [('aggressive', 'stable', 'const', 15, 20000), ('aggressive', 'det', 'const', 15, 20000),
+                 ('balanced', 'det', 'hash', 15, 20000), ('simple', 'stable', 'const', 10, 5000),
+                 ('efficiency', 'stable', 'hash', 15, 7)]
+        for h, pol, noise, goal, beam in cfgs:
+            NOISE.mode = noise
+            t0 = time.time()
+            r = stepper(goal, True, f'{h}@{pol}', beam)
+            r.update(policy=pol, noise=noise, base=h, wall_s=round(time.time() - t0, 2))
+            # cross-check with the reference's unmodified solve()
+            sol = State.newgame().solve(goal_pts=goal, use_heuristic=True, heuristic_name=f'{h}@{pol}',
+                                        beam_width=beam, verbose=False)
+            assert [repr(s) for s in sol] == [p['repr'] for p in r['path']], (h, pol, noise, goal, beam)
+            assert [s.saved for s in sol] == [p['saved'] for p in r['path']]
+            runs.append(r)
+            print(f'beam {h}@{pol}/{noise} goal={goal} beam={beam}: moves={r["moves"]} '
+                  f'expanded={r["expanded"]} visited={r["visited"]} {r["wall_s"]}s', file=sys.stderr)
+        NOISE.mode = 'const'
+        json.dump(runs, open(out / 'beam_runs.json', 'w'), indent=0)
+
+
+if __name__ == '__main__':
+    main()
