@@ -91,10 +91,12 @@ typedef struct {
     int64_t goal_rank;    /* rank of the first state with pts >= goal in queue order, or -1 */
     int64_t visited;      /* len(trail) */
     uint64_t table_slots; /* current visited-table capacity */
-    float ms_expand;      /* CUDA-event time of the expand+probe launches */
+    float ms_count;       /* CUDA-event time of the fan-out count + offset scan launches */
+    float ms_expand;      /* ... of the expand+probe launches (the dominant kernel) */
     float ms_resolve;     /* ... of the resolve+emit(+score) launches */
     float ms_select;      /* ... of the radix-select + cut */
-    float ms_sort;        /* ... of the rank-ordering sort */
+    float ms_sort;        /* ... of the rank-ordering sort + gather */
+    float reserved1;
 } spl_level_info;
 
 /* ---- library / context ------------------------------------------------------------------ */
@@ -113,6 +115,10 @@ int32_t spl_destroy(spl_ctx *ctx);
 /* forget every visited state (trail = {}), keep the allocation */
 int32_t spl_reset_visited(spl_ctx *ctx, void *stream);
 int32_t spl_visited_count(spl_ctx *ctx, int64_t *n_host);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+int32_t spl_launch_count(spl_ctx *ctx, int64_t *n_host);
+/* host<->device bytes copied by this context so far (bench.py's e2e accounting) */
+int32_t spl_transfer_bytes(spl_ctx *ctx, int64_t *h2d_host, int64_t *d2h_host);
 
 /* ---- stage operators (caller-owned device buffers) ---------------------------------------- */
 

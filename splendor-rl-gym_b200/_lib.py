@@ -33,8 +33,8 @@ class Config(C.Structure):
 class LevelInfo(C.Structure):
     _fields_ = [('level', C.c_int32), ('ended', C.c_int32), ('frontier', C.c_int64), ('expanded', C.c_int64),
                 ('generated', C.c_int64), ('unique', C.c_int64), ('kept', C.c_int64), ('goal_rank', C.c_int64),
-                ('visited', C.c_int64), ('table_slots', C.c_uint64), ('ms_expand', C.c_float),
-                ('ms_resolve', C.c_float), ('ms_select', C.c_float), ('ms_sort', C.c_float)]
+                ('visited', C.c_int64), ('table_slots', C.c_uint64), ('ms_count', C.c_float), ('ms_expand', C.c_float),
+                ('ms_resolve', C.c_float), ('ms_select', C.c_float), ('ms_sort', C.c_float), ('reserved1', C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -57,6 +57,8 @@ def _load():
         'spl_destroy': (i32, [vp]),
         'spl_reset_visited': (i32, [vp, vp]),
         'spl_visited_count': (i32, [vp, C.POINTER(i64)]),
+        'spl_launch_count': (i32, [vp, C.POINTER(i64)]),
+        'spl_transfer_bytes': (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         'spl_expand': (i32, [vp, vp, vp, i64, vp, vp, vp, i64, C.POINTER(i64), vp]),
         'spl_dedup': (i32, [vp, vp, vp, i64, vp, vp, vp, C.POINTER(i64), vp]),
         'spl_score': (i32, [vp, i32, i32, vp, vp, i64, vp, vp]),

@@ -92,7 +92,11 @@ __device__ __host__ __forceinline__ uint64_t mix64(uint64_t lo, uint64_t hi) {
 }
 
 // order-preserving map double -> u64 (larger double <=> larger u64; handles negative scores)
-__device__ __host__ __forceinline__ uint64_t flip_f64(uint64_t b) { return (b >> 63) ? ~b : (b | 0x8000000000000000ull); }
+// -0.0 is canonicalised to +0.0 first: Python's sort compares them equal (ties -> arrival order).
+__device__ __host__ __forceinline__ uint64_t flip_f64(uint64_t b) {
+    if (b == 0x8000000000000000ull) b = 0;
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
 __device__ __host__ __forceinline__ uint64_t unflip_f64(uint64_t k) { return (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k; }
 
 // ------------------------------------------------------------------ block primitives (TILE threads)

@@ -75,8 +75,10 @@ struct spl_ctx {
     DevBuf status[3];
     // scratch
     DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], matrix, matrix2;
+    DevBuf pool_front, pool_uniq;      // frontier buffers lent to the active solver
+    std::vector<DevBuf *> pool_links;  // link columns of finished solves, reused by the next one
     cudaEvent_t ev[8]{};
-    long long launches = 0;
+    long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
 static int fail(spl_ctx *c, int code, const char *fmt, ...) {
@@ -232,6 +234,7 @@ int32_t spl_destroy(spl_ctx *c) {
     cudaFree(c->table); cudaFree(c->d_tabs); cudaFree(c->d_takes_idx); cudaFree(c->d_takes_edges);
     cudaFree(c->d_lut); cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr); cudaFree(c->d_sel); cudaFreeHost(c->h_sel);
     cudaFree(c->d_hist);
+    for (auto *b : c->pool_links) delete b;
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     delete c;
     return SPL_OK;
@@ -251,6 +254,19 @@ int32_t spl_visited_count(spl_ctx *c, int64_t *n_host) {
     return SPL_OK;
 }
 
+int32_t spl_launch_count(spl_ctx *c, int64_t *n_host) {
+    if (!c || !n_host) return SPL_E_INVALID;
+    *n_host = c->launches;
+    return SPL_OK;
+}
+
+int32_t spl_transfer_bytes(spl_ctx *c, int64_t *h2d_host, int64_t *d2h_host) {
+    if (!c || !h2d_host || !d2h_host) return SPL_E_INVALID;
+    *h2d_host = c->h2d_bytes;
+    *d2h_host = c->d2h_bytes;
+    return SPL_OK;
+}
+
 // ------------------------------------------------------------------ internal helpers
 static int zero_ctr(spl_ctx *c, cudaStream_t st) {
     Counters z;
@@ -259,11 +275,13 @@ static int zero_ctr(spl_ctx *c, cudaStream_t st) {
     z.goal_rank = 0x7fffffffffffffffll;
     *c->h_ctr = z;
     CK(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, st));
+    c->h2d_bytes += sizeof z;
     return SPL_OK;
 }
 static int read_ctr(spl_ctx *c, cudaStream_t st) {
     CK(c, cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += sizeof(Counters);
     return SPL_OK;
 }
 static int reset_ticket(spl_ctx *c, int id, cudaStream_t st) {
@@ -344,6 +362,7 @@ static int run_select(spl_ctx *c, const uint64_t *sk, int64_t n, int64_t k, uint
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += sizeof(SelState);
     return SPL_OK;
 }
 
@@ -511,12 +530,18 @@ struct spl_solver {
     int64_t goal_rank = -1;
     std::vector<DevBuf *> links;   // per level: link column of the queue (device, 8 B per state)
     std::vector<int64_t> level_n;
-    ~spl_solver() { for (auto *b : links) delete b; }
+    ~spl_solver() {
+        c->pool_front.swap(front);
+        c->pool_uniq.swap(uniq);
+        for (auto *b : links) c->pool_links.push_back(b);
+    }
 };
 
 static int save_links(spl_solver *s, cudaStream_t st) {
     spl_ctx *c = s->c;
-    DevBuf *b = new DevBuf();
+    DevBuf *b;
+    if (c->pool_links.empty()) b = new DevBuf();
+    else { b = c->pool_links.back(); c->pool_links.pop_back(); }
     s->links.push_back(b);
     s->level_n.push_back(s->n_front);
     if (!s->keep_links || s->n_front == 0) return SPL_OK;
@@ -540,11 +565,15 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
     spl_solver *s = new spl_solver();
     s->c = c; s->goal = goal; s->use_h = use_h; s->heuristic = heuristic; s->beam = beam; s->tie = tie;
     s->noise = noise; s->keep_links = keep_links;
+    s->front.swap(c->pool_front);
+    s->uniq.swap(c->pool_uniq);
+    std::sort(c->pool_links.begin(), c->pool_links.end(), [](DevBuf *a, DevBuf *b) { return a->cap > b->cap; });
     int rc = spl_reset_visited(c, st);
     if (rc == SPL_OK) {
         Rec r{root_key->lo, root_key->hi & HI_KEY_MASK, root_aux, ~0ull};
         cudaError_t e = s->front.ensure(32, 0, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->front.p, &r, 32, cudaMemcpyHostToDevice, st);
+        c->h2d_bytes += 32;
         if (e != cudaSuccess) rc = fail(c, SPL_E_CUDA, "root upload: %s", cudaGetErrorString(e));
     }
     if (rc == SPL_OK) rc = zero_ctr(c, st);
@@ -587,7 +616,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     info->goal_rank = -1;
     const int64_t n = s->n_front;
     const Rec *front = s->front.as<Rec>();
-    float ms[4] = {0, 0, 0, 0};
+    float ms[5] = {0, 0, 0, 0, 0};  // count, expand, resolve, select, sort
     // ---- goal test on the queue (src/solver.py:443-445): the first state in queue order with
     // pts >= goal ends the search; the states before it would be expanded and discarded.
     CKS(c, zero_ctr(c, st));
@@ -613,6 +642,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         CKS(c, zero_ctr(c, st));
         CK(c, cudaEventRecord(c->ev[0], st));
         CKS(c, run_count(c, front + p0, np, st));
+        CK(c, cudaEventRecord(c->ev[7], st));
         const uint64_t total = c->h_ctr->total_cands;
         generated += (int64_t)total;
         if (total == 0) continue;
@@ -621,6 +651,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         uint64_t tag;
         CKS(c, next_epoch(c, tag));
         CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
+        CK(c, cudaEventRecord(c->ev[7], st));
         expand_kernel<MODE_PROBE><<<nt, TILE, sizeof(ExpandSmem), st>>>(
             front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
             c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
@@ -659,11 +690,13 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
             n_uniq += n_new;
             float t;
             cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
-            ms[1] += t;
+            ms[2] += t;
         }
         float t;
-        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[7]);
         ms[0] += t;
+        cudaEventElapsedTime(&t, c->ev[7], c->ev[1]);
+        ms[1] += t;
     }
     info->expanded = n;
     info->generated = generated;
@@ -683,9 +716,9 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         CK(c, cudaStreamSynchronize(st));
         float t;
         cudaEventElapsedTime(&t, c->ev[4], c->ev[5]);
-        ms[2] = t;
+        ms[3] = t;  // select + cut + sort (split below by run_cut_sort's own event)
         cudaEventElapsedTime(&t, c->ev[5], c->ev[6]);
-        ms[3] = t;
+        ms[4] = t;
     } else {
         s->front.swap(s->uniq);
     }
@@ -694,7 +727,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     info->kept = kept;
     info->visited = (int64_t)c->occupied;
     info->table_slots = c->cap;
-    info->ms_expand = ms[0]; info->ms_resolve = ms[1]; info->ms_select = ms[2]; info->ms_sort = ms[3];
+    info->ms_count = ms[0]; info->ms_expand = ms[1]; info->ms_resolve = ms[2]; info->ms_select = ms[3]; info->ms_sort = ms[4];
     if (kept == 0) {  // frontier exhausted: `puzzle` is the last dequeued state (src/solver.py:438,459)
         s->ended = true;
         s->goal_rank = n - 1;
@@ -733,6 +766,7 @@ int32_t spl_solver_path(spl_solver *s, int64_t *ranks, int32_t *ordinals, int32_
         if (l > 0) {
             uint64_t link = 0;
             CK(c, cudaMemcpy(&link, s->links[l]->as<uint64_t>() + r, 8, cudaMemcpyDeviceToHost));
+            c->d2h_bytes += 8;
             ordinals[l - 1] = (int32_t)(link & 0xff);
             r = (int64_t)(link >> 8);
         }

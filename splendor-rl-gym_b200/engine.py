@@ -117,6 +117,16 @@ class Engine:
         check(lib.spl_visited_count(self._h, C.byref(n)), self._h)
         return n.value
 
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(lib.spl_launch_count(self._h, C.byref(n)), self._h)
+        return n.value
+
+    def transfer_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(lib.spl_transfer_bytes(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
     # -------------------------------------------------------------- stage operators
     def expand(self, keys: torch.Tensor, aux: torch.Tensor):
         """State.__iter__ for a batch (src/solver.py:357-388) -> (cand_keys [m,2], cand_aux [m], cand_link [m])."""

@@ -88,7 +88,7 @@ def test_expand_matches_reference_successors(eng, golden):
 
 
 def test_expand_edge_cases(eng):
-    # empty batch, a hand of 10 gems (returns), all 7s in one colour, and a state with no successors
+    # empty batch, a hand of 10 gems (returns), all 7s in one colour, a hand above 10 gems, a full deck
     k, a, l = eng.expand(torch.empty((0, 2), dtype=torch.int64, device=eng.tdev), torch.empty(0, dtype=torch.int64, device=eng.tdev))
     assert k.shape[0] == 0
     cases = [((), z5(), (2, 2, 2, 2, 2), 0, 0), ((), z5(), (7, 3, 0, 0, 0), 0, 0), ((), z5(), (7, 7, 7, 7, 7), 0, 0),
@@ -102,7 +102,8 @@ def test_expand_edge_cases(eng):
         for o in range(len(w)):
             assert (ck[pos, 0], ck[pos, 1], ca[pos], cl[pos]) == (w['lo'][o], w['hi'][o], w['aux'][o], rank << 8 | o)
             pos += 1
-    assert len(want[2]) == 0  # total > 10: no takes, nothing affordable
+    assert len(want[2]) == 90  # total > 10: no takes, but every card is affordable
+    assert len(want[3]) == 15  # owns the whole deck: only takes
     assert len(want[4]) == 90 + 15  # every card affordable on bonuses alone
 
 

@@ -1,0 +1,46 @@
+"""Ad-hoc timing of the level solver on the GPU box (not part of the test suite)."""
+import argparse
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+
+import splendor_rl_gym_b200 as S
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--goal', type=int, default=15)
+ap.add_argument('--beam', type=int, default=300_000)
+ap.add_argument('--heuristic', default='aggressive')
+ap.add_argument('--bfs', type=int, default=0, help='run pure BFS for this many levels instead')
+ap.add_argument('--slots', type=int, default=0)
+ap.add_argument('--chunk', type=int, default=0)
+ap.add_argument('--reps', type=int, default=2)
+a = ap.parse_args()
+
+slots = a.slots or max(1 << 22, int(a.beam * 110 / 0.6))
+eng = S.Engine(0, table_slots=slots, chunk_parents=a.chunk)
+k, aux = S.State.newgame().record()
+for rep in range(a.reps):
+    torch.cuda.synchronize()
+    t0 = time.time()
+    if a.bfs:
+        sol = eng.solver(k, aux, 255, False, 'simple', 0, keep_links=False)
+        infos = sol.run(max_levels=a.bfs)
+    else:
+        sol = eng.solver(k, aux, a.goal, True, a.heuristic, a.beam, 'stable', 'const')
+        infos = sol.run()
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    exp = sum(i['expanded'] for i in infos)
+    gen = sum(i['generated'] for i in infos)
+    print(f'rep {rep}: levels={len(infos)} expanded={exp} generated={gen} visited={infos[-1]["visited"]} '
+          f'wall={dt:.3f}s -> {exp / dt / 1e6:.2f} M expanded/s, {gen / dt / 1e6:.1f} M generated/s  '
+          f'mem={torch.cuda.mem_get_info()[0] / 2**30:.1f} GiB free')
+    if rep == a.reps - 1:
+        for i in infos:
+            print('  L%-2d front=%-10d gen=%-11d uniq=%-10d kept=%-9d ms: count %.2f expand %.2f resolve %.2f select %.2f sort %.2f' % (
+                i['level'], i['frontier'], i['generated'], i['unique'], i['kept'], i['ms_count'], i['ms_expand'],
+                i['ms_resolve'], i['ms_select'], i['ms_sort']))
+    sol.close()
