@@ -50,6 +50,13 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(a) : "l"(p));
     return a;
 }
+// whole 32 B visited-table slot in one request (LDG.E.256.STRONG.GPU): {lo, hi|tag, ~t, spare}
+__device__ __forceinline__ void ld_slot(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &v) {
+    uint64_t d;
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(v), "=l"(d) : "l"(p));
+    (void)d;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ld_rec(const Rec *p, Rec &r) {  // 256-bit load (LDG.E.256 on sm_100)
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];"
                  : "=l"(r.lo), "=l"(r.hi), "=l"(r.aux), "=l"(r.link)
@@ -80,7 +87,19 @@ __device__ __host__ __forceinline__ uint64_t hash_key(uint64_t lo, uint64_t hi) 
     x ^= x >> 32;
     return x;
 }
-__device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t cap) { return __umul64hi(h, cap); }
+// Home slot: always the EVEN slot of a 64-byte pair.  The DRAM access granule on B200 is 64 B
+// (ncu: ~2 sectors read per probe miss), so the first linear-probing step stays in the line
+// that the home probe already fetched.
+#ifndef SPL_PAIR
+#define SPL_PAIR 0   // measured: pairing adds clustering and is 5% slower (profiles/README.md r1b)
+#endif
+__device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t cap) {
+#if SPL_PAIR
+    return __umul64hi(h, cap >> 1) << 1;
+#else
+    return __umul64hi(h, cap);
+#endif
+}
 
 // splitmix64 finaliser over the folded key: noise policy `hash`
 __device__ __host__ __forceinline__ uint64_t mix64(uint64_t lo, uint64_t hi) {

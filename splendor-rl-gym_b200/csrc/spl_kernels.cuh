@@ -103,17 +103,19 @@ __device__ __forceinline__ void make_child(const SmemTabs &s, const uint16_t *__
 }
 
 // ------------------------------------------------------------------ visited table probe
-// Returns the slot index the candidate resolved to (new insert or same-epoch duplicate), or DEAD
-// if the key was inserted in an earlier epoch.  `tinv` = ~t, t = arrival index in this epoch:
+// Returns the slot index the candidate resolved to (new insert, or same-epoch duplicate that may
+// still be the first arrival), or DEAD if the key was inserted in an earlier epoch or an EARLIER
+// arrival of this epoch already holds the slot.  `tinv` = ~t, t = arrival index in this epoch:
 // atomicMax(~t) keeps the FIRST arrival (src/solver.py:447-450) regardless of thread order.
-__device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t klo,
-                                                 uint64_t khi, uint64_t tinv, uint32_t &n_new, unsigned int *error) {
-    uint64_t i = slot_of(hash_key(klo, khi), cap);
+// `i` is the home slot (slot_of(hash_key())), usually prefetched into L2 a few iterations ago.
+template <bool PRELOADED>
+__device__ __forceinline__ uint32_t probe_at(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t i,
+                                             uint64_t klo, uint64_t khi, uint64_t tinv, uint32_t &n_new,
+                                             unsigned int *error, uint64_t a = 0, uint64_t b = 0, uint64_t v = 0) {
     const uint64_t want_hi = khi | (tag << TAG_SHIFT);
     for (int probes = 0; probes < MAX_PROBE; ++probes) {
         uint64_t *slot = table + (i << 2);
-        uint64_t a, b;
-        ld_cg_u64x2(slot, a, b);
+        if (!PRELOADED || probes > 0) ld_slot(slot, a, b, v);
         if ((a | b) == 0) {  // empty: claim with one 128-bit CAS
             cas128(slot, 0, 0, klo, want_hi, a, b);
             if ((a | b) == 0) {
@@ -121,9 +123,11 @@ __device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, u
                 ++n_new;
                 return (uint32_t)i;
             }
+            v = 0;
         }
         if (a == klo && (b & HI_KEY_MASK) == khi) {
             if ((b >> TAG_SHIFT) != tag) return DEAD;
+            if (v > tinv) return DEAD;  // an earlier arrival is already registered (~t only grows)
             atomicMax(reinterpret_cast<unsigned long long *>(slot + 2), (unsigned long long)tinv);
             return (uint32_t)i;
         }
@@ -131,6 +135,10 @@ __device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, u
     }
     atomicExch(error, 1u);
     return DEAD;
+}
+__device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t klo,
+                                                 uint64_t khi, uint64_t tinv, uint32_t &n_new, unsigned int *error) {
+    return probe_at<false>(table, cap, tag, slot_of(hash_key(klo, khi), cap), klo, khi, tinv, n_new, error);
 }
 
 // ------------------------------------------------------------------ count + scan
@@ -211,6 +219,99 @@ __device__ __forceinline__ uint32_t owner_of(const uint32_t *pref, uint32_t i) {
     return lo;
 }
 
+// gems after buying the card at key bit `pos` (subtract_with_bonus, src/gems.py:116-129); also
+// returns the gems saved and the packed card.  The pre-purchase bonus is used (src/solver.py:346-347).
+__device__ __forceinline__ uint32_t buy_gems(const SmemTabs &s, uint64_t lo, uint64_t aux, int pos, uint32_t &saved,
+                                             uint32_t &cd) {
+    cd = s.card[pos - 15];
+    const uint32_t g = (uint32_t)(lo & GEM_MASK);
+    uint32_t ng = 0;
+    saved = 0;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+        const int cost = (cd >> (3 * c)) & 7;
+        const int b = (int)((aux >> (24 + 5 * c)) & 31);
+        const int gc = (g >> (3 * c)) & 7;
+        const int pay = max(cost - b, 0);
+        saved += cost - pay;
+        ng |= (uint32_t)max(gc - pay, 0) << (3 * c);
+    }
+    return ng;
+}
+
+#ifndef SPL_PIPE
+#define SPL_PIPE 0   // measured on B200 (profiles/README.md r1b): lookahead only adds L2 requests -- the probe stream is
+                     // bound by the DRAM random-access rate, not by exposed latency
+#endif
+#ifndef SPL_PF
+#define SPL_PF 1   // 0: no lookahead, 1: prefetch.global.L2 of the home slot, 2: cp.async of the home slot into smem
+#endif
+constexpr int PIPE = SPL_PIPE;  // probes in flight per thread: lookahead distance in loop iterations
+constexpr int PIPE_N = SPL_PIPE > 0 ? SPL_PIPE : 1;
+constexpr int BUY_WIN = 4096;  // buy-list window (entries) staged in shared memory
+
+struct ExpandSmem2 {
+    SmemTabs tabs;
+    uint64_t lo[TILE], hi[TILE], aux[TILE];
+    uint32_t tk[TILE], nb[TILE], pref[TILE], prefb[TILE + 1];
+    uint16_t units[TILE / 32][128];   // per warp: (parent lane << 2 | round) of every 32-take unit
+    uint16_t blist[BUY_WIN];          // (parent << 7 | key bit) of every buy successor in the window
+    uint64_t r_klo[PIPE_N][TILE], r_khi[PIPE_N][TILE];  // pipeline ring: keys whose home slot is being fetched
+    uint32_t r_idx[PIPE_N][TILE], r_t[PIPE_N][TILE];
+#if SPL_PF == 2
+    ulonglong2 r_ab[PIPE_N][TILE];   // async copy of the home slot: key halves ...
+    uint64_t r_v[PIPE_N][TILE];      // ... and its ~t word
+#endif
+    uint32_t warp_sums[TILE / 32 + 1];
+};
+
+template <class SM>
+__device__ __forceinline__ void stage_issue(SM &S, uint32_t slot_i, uint64_t *table, uint64_t cap, uint64_t klo,
+                                            uint64_t khi) {
+    const unsigned tid = threadIdx.x;
+    const uint64_t idx = slot_of(hash_key(klo, khi), cap);
+    S.r_klo[slot_i][tid] = klo;
+    S.r_khi[slot_i][tid] = khi;
+    S.r_idx[slot_i][tid] = (uint32_t)idx;
+#if SPL_PF == 1
+    prefetch_l2(table + (idx << 2));
+#elif SPL_PF == 2
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&S.r_ab[slot_i][tid]);
+    const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(&S.r_v[slot_i][tid]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(table + (idx << 2)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1), "l"(table + (idx << 2) + 2) : "memory");
+#endif
+}
+__device__ __forceinline__ void stage_commit() {
+#if SPL_PF == 2
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <class SM>
+__device__ __forceinline__ void stage_consume(SM &S, uint32_t slot_i, uint64_t *table, uint64_t cap, uint64_t tag,
+                                              uint32_t *cand_slot, uint32_t &n_new, unsigned int *error) {
+    const unsigned tid = threadIdx.x;
+#if SPL_PF == 2
+    asm volatile("cp.async.wait_group %0;" ::"n"(PIPE_N - 1) : "memory");
+#endif
+    const uint32_t tt = S.r_t[slot_i][tid];
+    if (tt != DEAD) {
+#if SPL_PF == 2
+        const ulonglong2 ab = S.r_ab[slot_i][tid];
+        cand_slot[tt] = probe_at<true>(table, cap, tag, S.r_idx[slot_i][tid], S.r_klo[slot_i][tid], S.r_khi[slot_i][tid],
+                                       ~(uint64_t)tt, n_new, error, ab.x, ab.y, S.r_v[slot_i][tid]);
+#else
+        cand_slot[tt] = probe_at<false>(table, cap, tag, S.r_idx[slot_i][tid], S.r_klo[slot_i][tid], S.r_khi[slot_i][tid],
+                                        ~(uint64_t)tt, n_new, error);
+#endif
+    }
+}
+
+// One CTA expands one tile of TILE parents.  Successors are enumerated in two divergence-free
+// streams -- gem takes (warp-uniform units of 32 consecutive table edges of one parent, coalesced)
+// and card buys (a compacted list built by warp-ballot-free bit iteration) -- and every probe of
+// the visited table is software-pipelined PIPE iterations behind an L2 prefetch of its home slot.
+// Arrival index t = off[parent] + ordinal is unchanged by the processing order.
 template <int MODE>
 __global__ void __launch_bounds__(TILE) expand_kernel(const Rec *__restrict__ front, int64_t n_par,
                                                       const DevTables *__restrict__ tabs,
@@ -221,31 +322,117 @@ __global__ void __launch_bounds__(TILE) expand_kernel(const Rec *__restrict__ fr
                                                       uint32_t *__restrict__ cand_slot, Rec *__restrict__ cand_out,
                                                       int64_t rank_base, Counters *ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ExpandSmem &S = *reinterpret_cast<ExpandSmem *>(smem_raw);
+    ExpandSmem2 &S = *reinterpret_cast<ExpandSmem2 *>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     load_tabs(S.tabs, tabs);
     __syncthreads();
-    uint32_t c0, ncand;
-    load_tile(S, front, n_par, takes_idx, off, total, blockIdx.x, c0, ncand);
+    // ---- parents of this tile
+    const int64_t p0 = (int64_t)blockIdx.x * TILE, p = p0 + tid;
+    const uint32_t c0 = off[p0];
+    uint64_t bm_lo = 0, bm_hi = 0;
+    uint32_t nb = 0, tk = 0;
+    if (p < n_par) {
+        Rec r;
+        ld_rec(front + p, r);
+        derive_parent(S.tabs, takes_idx, r.lo, r.hi, r.aux, bm_lo, bm_hi, nb, tk);
+        S.lo[tid] = r.lo; S.hi[tid] = r.hi; S.aux[tid] = r.aux;
+        S.pref[tid] = off[p] - c0;
+    }
+    S.tk[tid] = tk;
+    S.nb[tid] = nb;
+    uint32_t total_buys;
+    const uint32_t prefb = block_excl_scan(nb, S.warp_sums, total_buys);
+    S.prefb[tid] = prefb;
+    if (tid == 0) S.prefb[TILE] = total_buys;
+    // ---- take units of this warp's 32 parents
+    const uint32_t nt_mine = tk & 0xff, my_units = (nt_mine + 31) >> 5;
+    const uint32_t uoff = warp_incl_scan(my_units) - my_units;
+    const uint32_t nu = __shfl_sync(0xffffffffu, uoff + my_units, 31);
+    for (uint32_t r = 0; r < my_units; ++r) S.units[w][uoff + r] = (uint16_t)(lane << 2 | r);
     __syncthreads();
     uint32_t n_new = 0;
-    for (uint32_t i = threadIdx.x; i < ncand; i += TILE) {
-        const uint32_t j = owner_of(S.pref, i);
-        const uint32_t ord = i - S.pref[j];
-        uint64_t clo, chi, caux;
-        make_child(S.tabs, takes_edges, S.lo[j], S.hi[j], S.aux[j], S.bm_lo[j], S.bm_hi[j], S.nb[j], S.tk[j], ord, clo,
-                   chi, caux);
-        const uint64_t t = (uint64_t)c0 + i;
-        if (MODE == MODE_PROBE) {
-            cand_slot[t] = probe_insert(table, cap, tag, clo, chi, ~t, n_new, &ctr->error);
-        } else {
-            Rec r{clo, chi, caux, ((uint64_t)(rank_base + (int64_t)blockIdx.x * TILE + j) << 8) | ord};
-            st_rec(cand_out + t, r);
+    // ---- gem takes (src/solver.py:381-388)
+    for (uint32_t u = 0; u < nu + PIPE; ++u) {
+        if (MODE == MODE_PROBE && PIPE > 0 && u >= PIPE)  // consume the stage issued PIPE iterations ago
+            stage_consume(S, u % PIPE_N, table, cap, tag, cand_slot, n_new, &ctr->error);
+        if (u < nu) {
+            const uint32_t unit = S.units[w][u], j = (w << 5) + (unit >> 2), q = ((unit & 3) << 5) + lane;
+            const uint32_t tkj = S.tk[j];
+            const bool act = q < (tkj & 0xff);
+            uint32_t tt = DEAD;
+            if (act) {
+                const uint32_t e = __ldg(takes_edges + (tkj >> 8) + q);
+                const uint64_t klo = (S.lo[j] & ~GEM_MASK) | e, khi = S.hi[j];
+                tt = c0 + S.pref[j] + S.nb[j] + q;
+                if (MODE == MODE_PROBE) {
+                    if (PIPE > 0) stage_issue(S, u % PIPE_N, table, cap, klo, khi);
+                    else cand_slot[tt] = probe_insert(table, cap, tag, klo, khi, ~(uint64_t)tt, n_new, &ctr->error);
+                } else {
+                    Rec r{klo, khi, S.aux[j], ((uint64_t)(rank_base + p0 + j) << 8) | (S.nb[j] + q)};
+                    st_rec(cand_out + tt, r);
+                }
+            }
+            if (MODE == MODE_PROBE && PIPE > 0) S.r_t[u % PIPE_N][tid] = tt;
+        }
+        if (MODE == MODE_PROBE && PIPE > 0) stage_commit();
+    }
+    // ---- card buys (src/solver.py:369-374), window by window
+    for (uint32_t w0 = 0; w0 < total_buys; w0 += BUY_WIN) {
+        __syncthreads();
+        {   // each parent lists its affordable, not-owned cards in ascending index order
+            uint32_t q = prefb;
+            uint64_t m = bm_lo;
+            while (m) {
+                const int pos = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                if (q >= w0 && q < w0 + BUY_WIN) S.blist[q - w0] = (uint16_t)(tid << 7 | pos);
+                ++q;
+            }
+            m = bm_hi;
+            while (m) {
+                const int pos = 64 + __ffsll((long long)m) - 1;
+                m &= m - 1;
+                if (q >= w0 && q < w0 + BUY_WIN) S.blist[q - w0] = (uint16_t)(tid << 7 | pos);
+                ++q;
+            }
+        }
+        __syncthreads();
+        const uint32_t nbw = min((uint32_t)BUY_WIN, total_buys - w0), rounds = (nbw + TILE - 1) / TILE;
+        for (uint32_t u = 0; u < rounds + PIPE; ++u) {
+            if (MODE == MODE_PROBE && PIPE > 0 && u >= PIPE)
+                stage_consume(S, u % PIPE_N, table, cap, tag, cand_slot, n_new, &ctr->error);
+            if (u < rounds) {
+                const uint32_t i = u * TILE + tid;
+                uint32_t tt = DEAD;
+                if (i < nbw) {
+                    const uint32_t ent = S.blist[i], j = ent >> 7;
+                    const int pos = ent & 127;
+                    const uint64_t lo = S.lo[j], aux = S.aux[j];
+                    uint32_t saved, cd;
+                    const uint32_t ng = buy_gems(S.tabs, lo, aux, pos, saved, cd);
+                    uint64_t klo = (lo & ~GEM_MASK) | ng, khi = S.hi[j];
+                    if (pos < 64) klo |= 1ull << pos; else khi |= 1ull << (pos - 64);
+                    const uint32_t ord = w0 + i - S.prefb[j];
+                    tt = c0 + S.pref[j] + ord;
+                    if (MODE == MODE_PROBE) {
+                        if (PIPE > 0) stage_issue(S, u % PIPE_N, table, cap, klo, khi);
+                        else cand_slot[tt] = probe_insert(table, cap, tag, klo, khi, ~(uint64_t)tt, n_new, &ctr->error);
+                    } else {
+                        const uint64_t caux = aux + saved + ((uint64_t)((cd >> 15) & 7) << 16) +
+                                              (1ull << (24 + 5 * ((cd >> 18) & 7)));
+                        Rec r{klo, khi, caux, ((uint64_t)(rank_base + p0 + j) << 8) | ord};
+                        st_rec(cand_out + tt, r);
+                    }
+                }
+                if (MODE == MODE_PROBE && PIPE > 0) S.r_t[u % PIPE_N][tid] = tt;
+            }
+            if (MODE == MODE_PROBE && PIPE > 0) stage_commit();
         }
     }
     if (MODE == MODE_PROBE) {
 #pragma unroll
         for (int d = 16; d; d >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, d);
-        if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&ctr->n_new, (unsigned long long)n_new);
+        if (lane == 0 && n_new) atomicAdd(&ctr->n_new, (unsigned long long)n_new);
     }
 }
 
@@ -363,23 +550,28 @@ __global__ void __launch_bounds__(TILE) resolve_kernel(const Rec *__restrict__ f
         c0 = tile * (TILE * 32u);
         ncand = min((uint32_t)(TILE * 32), total - c0);
     }
-    // ---- pass 1: winner flags
+    // ---- pass 1: winner flags (4 independent slot gathers in flight per thread)
     const uint32_t nwords = (ncand + 31) >> 5;
     uint32_t mywins = 0;
-    for (uint32_t i0 = 0; i0 < ncand; i0 += TILE) {
-        const uint32_t i = i0 + threadIdx.x;
-        bool win = false;
-        if (i < ncand) {
-            const uint32_t sidx = cand_slot[c0 + i];
-            if (sidx != DEAD) {
-                const uint64_t v = ld_cg_u64(table + ((uint64_t)sidx << 2) + 2);
-                win = (~v) == (uint64_t)(c0 + i);
-            }
+    for (uint32_t i0 = 0; i0 < ncand; i0 += 4 * TILE) {
+        uint32_t sidx[4];
+        uint64_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = i0 + k * TILE + threadIdx.x;
+            sidx[k] = i < ncand ? cand_slot[c0 + i] : DEAD;
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, win);
-        if ((threadIdx.x & 31) == 0 && ((i0 + threadIdx.x) >> 5) < nwords) {
-            S.win[(i0 + threadIdx.x) >> 5] = bal;
-            mywins += __popc(bal);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = sidx[k] != DEAD ? ld_cg_u64(table + ((uint64_t)sidx[k] << 2) + 2) : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = i0 + k * TILE + threadIdx.x;
+            const bool win = sidx[k] != DEAD && (~v[k]) == (uint64_t)(c0 + i);
+            const uint32_t bal = __ballot_sync(0xffffffffu, win);
+            if ((threadIdx.x & 31) == 0 && (i >> 5) < nwords) {
+                S.win[i >> 5] = bal;
+                mywins += __popc(bal);
+            }
         }
     }
     uint32_t tile_wins;

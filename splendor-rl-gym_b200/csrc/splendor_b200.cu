@@ -151,6 +151,7 @@ int32_t spl_host_buys(const uint8_t key[5], uint8_t out[90]) {
 // ------------------------------------------------------------------ context
 static int alloc_table(spl_ctx *c, uint64_t slots, cudaStream_t st) {
     if (slots >= 0xFFFFFFFEull) slots = 0xFFFFFFFEull;
+    slots &= ~1ull;  // whole 64-byte slot pairs
     CK(c, cudaMalloc(&c->table, slots * 32));
     CK(c, cudaMemsetAsync(c->table, 0, slots * 32, st));
     c->cap = slots;
@@ -213,6 +214,8 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaMalloc(&c->d_hist, SEL_BINS * 4));
     CKC(cudaMemset(c->d_hist, 0, SEL_BINS * 4));
     for (auto &ev : c->ev) CKC(cudaEventCreate(&ev));
+    CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
+    CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     uint64_t slots = cfg->table_slots ? cfg->table_slots : (1ull << 22);
     slots = std::min<uint64_t>(slots, c->max_table_bytes / 32);
     slots = std::max<uint64_t>(slots, 1024);
@@ -300,6 +303,7 @@ static int ensure_table(spl_ctx *c, uint64_t need, cudaStream_t st) {
         uint64_t ncap = c->cap * 2;
         if (ncap >= 0xFFFFFFFEull) ncap = 0xFFFFFFFEull;
         if (ncap * 32 > c->max_table_bytes) ncap = c->max_table_bytes / 32;
+        ncap &= ~1ull;
         if (ncap <= c->cap + c->cap / 8) break;  // cannot grow meaningfully
         uint64_t *nt = nullptr;
         cudaError_t e = cudaMalloc(&nt, ncap * 32);
@@ -433,7 +437,7 @@ int32_t spl_expand(spl_ctx *c, const spl_key *keys, const uint64_t *aux, int64_t
     if (total > cap) return fail(c, SPL_E_CAPACITY, "spl_expand: %lld successors, capacity %lld", (long long)total, (long long)cap);
     if (total == 0) return SPL_OK;
     CK(c, c->tmp_rec2.ensure((size_t)total * 32, 0, st));
-    expand_kernel<MODE_LIST><<<nblk(n), TILE, sizeof(ExpandSmem), st>>>(
+    expand_kernel<MODE_LIST><<<nblk(n), TILE, sizeof(ExpandSmem2), st>>>(
         c->tmp_rec.as<Rec>(), n, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
         nullptr, 0, 0, nullptr, c->tmp_rec2.as<Rec>(), 0, c->d_ctr);
     unpack_rec_kernel<<<nblk(total), TILE, 0, st>>>(c->tmp_rec2.as<Rec>(), total, ck, ca, cl);
@@ -652,7 +656,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         CKS(c, next_epoch(c, tag));
         CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
         CK(c, cudaEventRecord(c->ev[7], st));
-        expand_kernel<MODE_PROBE><<<nt, TILE, sizeof(ExpandSmem), st>>>(
+        expand_kernel<MODE_PROBE><<<nt, TILE, sizeof(ExpandSmem2), st>>>(
             front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
             c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
         ++c->launches;

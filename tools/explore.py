@@ -39,6 +39,10 @@ for rep in range(a.reps):
           f'wall={dt:.3f}s -> {exp / dt / 1e6:.2f} M expanded/s, {gen / dt / 1e6:.1f} M generated/s  '
           f'mem={torch.cuda.mem_get_info()[0] / 2**30:.1f} GiB free')
     if rep == a.reps - 1:
+        print('SUMMARY lib=%s wall=%.1fms expand=%.2f resolve=%.2f select=%.2f sort=%.2f count=%.2f' % (
+            __import__('os').environ.get('SPLENDOR_B200_LIB', 'default').split('/')[-1], dt * 1e3,
+            *(sum(i['ms_' + k] for i in infos) for k in ('expand', 'resolve', 'select', 'sort', 'count'))))
+    if rep == a.reps - 1 and not __import__('os').environ.get('QUIET'):
         for i in infos:
             print('  L%-2d front=%-10d gen=%-11d uniq=%-10d kept=%-9d ms: count %.2f expand %.2f resolve %.2f select %.2f sort %.2f' % (
                 i['level'], i['frontier'], i['generated'], i['unique'], i['kept'], i['ms_count'], i['ms_expand'],
