@@ -23,13 +23,15 @@ struct Counters {            // device-resident scalars, zeroed per use by the h
     long long goal_rank;              // min rank with pts >= goal (or LLONG_MAX)
     unsigned int error;               // 1 = probe overflow (table full)
     unsigned int ticket[4];           // dynamic tile tickets
+    unsigned long long key_or[2], key_and[2];  // OR / AND of the kept keys (det policy: which key bits vary)
 };
 
 struct SelState {            // radix-select state (device)
     unsigned long long prefix;  // high bits of the threshold found so far (in x = sk - sk_min space)
     unsigned long long k_rem;   // rank still to resolve inside the current bucket
     unsigned long long c_gt;    // elements strictly above the current bucket
-    unsigned long long pad;
+    unsigned long long tie_count;  // size of the bucket chosen by the last pick
+    unsigned long long khi, klo;   // det policy: key threshold among score ties (keys >= it are kept)
 };
 
 // ------------------------------------------------------------------ per-parent derivation
@@ -655,21 +657,38 @@ __global__ void __launch_bounds__(TILE) goal_kernel(const Rec *__restrict__ fron
 constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS;
 
-// histogram of digit (x >> shift) & (2^bits - 1) over elements whose higher bits equal st->prefix
-__global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restrict__ sk, int64_t n, uint64_t sk_min,
-                                                        int shift, int bits, int first, const SelState *st,
-                                                        uint32_t *__restrict__ hist) {
+// histogram of digit (x >> shift) & (2^bits - 1) over elements whose higher bits equal the prefix.
+// WORD 0: x = sk - sk_min (score).  WORD 1 / 2 (det policy): key.hi / key.lo of the elements whose
+// score equals the score threshold (and, for WORD 2, whose key.hi equals the hi threshold).
+template <int WORD>
+__global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restrict__ sk, const Rec *__restrict__ recs,
+                                                        int64_t n, uint64_t sk_min, int shift, int bits, int first,
+                                                        const SelState *st, uint32_t *__restrict__ hist) {
     __shared__ uint32_t sh[SEL_BINS];
     for (int i = threadIdx.x; i < SEL_BINS; i += TILE) sh[i] = 0;
     __syncthreads();
-    const uint64_t prefix = first ? 0 : st->prefix;
+    const uint64_t prefix = first ? 0 : (WORD == 0 ? st->prefix : WORD == 1 ? st->khi : st->klo);
+    const uint64_t T = WORD == 0 ? 0 : st->prefix, Thi = WORD == 2 ? st->khi : 0;
     const int hs = shift + bits;  // bits above the digit must match the prefix
     const uint32_t dmask = (1u << bits) - 1;
-    for (int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x; i < n; i += (int64_t)gridDim.x * TILE) {
-        const uint64_t x = sk[i] - sk_min;
-        const bool match = first || hs >= 64 || (x >> hs) == (prefix >> hs);
+    for (int64_t base = (int64_t)blockIdx.x * TILE; base < n; base += (int64_t)gridDim.x * TILE) {
+        const int64_t i = base + threadIdx.x;
+        bool match = i < n;
+        uint64_t x = 0;
+        if (match) {
+            x = sk[i] - sk_min;
+            if (WORD > 0) {
+                match = x == T;
+                if (match) {
+                    const uint64_t hi = recs[i].hi;
+                    if (WORD == 1) x = hi;
+                    else { match = hi == Thi; x = recs[i].lo; }
+                }
+            }
+            match = match && (first || hs >= 64 || (x >> hs) == (prefix >> hs));
+        }
         const uint32_t d = (uint32_t)(x >> shift) & dmask;
-        const unsigned act = __ballot_sync(__activemask(), match);
+        const unsigned act = __ballot_sync(0xffffffffu, match);
         if (match) {
             const unsigned peers = __match_any_sync(act, d);
             if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
@@ -680,8 +699,10 @@ __global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restri
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-// choose the bucket holding the k_rem-th largest element; 1 CTA of 1024 threads, 2 bins each
-__global__ void __launch_bounds__(1024) sel_pick_kernel(uint32_t *hist, int shift, int first, uint64_t k, SelState *st) {
+// choose the bucket holding the k_rem-th largest element; 1 CTA of 1024 threads, 2 bins each.
+// `first` = first pass of this word (its prefix starts at 0); `init_k` = very first pass (k_rem = k).
+__global__ void __launch_bounds__(1024) sel_pick_kernel(uint32_t *hist, int word, int shift, int first, int init_k,
+                                                        uint64_t k, SelState *st) {
     __shared__ unsigned long long s_scan[1024];
     const int t = threadIdx.x;
     const uint32_t h0 = hist[SEL_BINS - 1 - 2 * t], h1 = hist[SEL_BINS - 2 - 2 * t];  // descending bins
@@ -695,18 +716,20 @@ __global__ void __launch_bounds__(1024) sel_pick_kernel(uint32_t *hist, int shif
         s_scan[t] += v;
         __syncthreads();
     }
-    const unsigned long long k_rem = first ? k : st->k_rem;
-    const unsigned long long c_gt = first ? 0 : st->c_gt;
-    const unsigned long long prefix = first ? 0 : st->prefix;
+    unsigned long long *pf = word == 0 ? &st->prefix : word == 1 ? &st->khi : &st->klo;
+    const unsigned long long k_rem = init_k ? k : st->k_rem;
+    const unsigned long long c_gt = init_k ? 0 : st->c_gt;
+    const unsigned long long prefix = first ? 0 : *pf;
     const unsigned long long incl = s_scan[t], excl = incl - ((unsigned long long)h0 + h1);
     __syncthreads();
     if (excl < k_rem && k_rem <= incl) {
-        unsigned long long above = excl;
+        unsigned long long above = excl, cnt = h0;
         int bin = SEL_BINS - 1 - 2 * t;
-        if (above + h0 < k_rem) { above += h0; bin -= 1; }
-        st->prefix = prefix | ((unsigned long long)bin << shift);
+        if (above + h0 < k_rem) { above += h0; bin -= 1; cnt = h1; }
+        *pf = prefix | ((unsigned long long)bin << shift);
         st->k_rem = k_rem - above;
         st->c_gt = c_gt + above;
+        st->tie_count = cnt;
     }
 }
 
@@ -764,6 +787,70 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
         }
 }
 
+// det policy (ties -> larger canonical key first): keep x > T, plus the score ties whose key is >=
+// the key threshold found by the WORD 1/2 select passes (or every tie when `all_ties`).  Order of
+// emission is irrelevant here (the composite sort below fixes the ranks); also accumulates the
+// OR / AND of the kept keys so that sort passes over constant key digits can be skipped.
+__global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restrict__ sk, const Rec *__restrict__ recs,
+                                                       int64_t n, uint64_t sk_min, uint64_t sk_max, int keep_all,
+                                                       int all_ties, const SelState *st, uint64_t *__restrict__ out_y,
+                                                       uint64_t *__restrict__ out_klo, uint64_t *__restrict__ out_khi,
+                                                       uint32_t *__restrict__ out_idx, uint64_t *status_keep,
+                                                       Counters *ctr, int ticket_id) {
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_keep_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t T = keep_all ? 0 : st->prefix, Thi = st->khi, Tlo = st->klo;
+    const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * CUT_ITEMS;
+    uint64_t x[CUT_ITEMS], lo[CUT_ITEMS], hi[CUT_ITEMS];
+    uint32_t keepmask = 0, kept = 0;
+    uint64_t or_lo = 0, or_hi = 0, and_lo = ~0ull, and_hi = ~0ull;
+#pragma unroll
+    for (int q = 0; q < CUT_ITEMS; ++q) {
+        bool k = false;
+        if (b0 + q < n) {
+            x[q] = sk[b0 + q] - sk_min;
+            lo[q] = recs[b0 + q].lo;
+            hi[q] = recs[b0 + q].hi;
+            if (keep_all || x[q] > T) k = true;
+            else if (x[q] == T) k = all_ties || hi[q] > Thi || (hi[q] == Thi && lo[q] >= Tlo);
+            if (k) { or_lo |= lo[q]; or_hi |= hi[q]; and_lo &= lo[q]; and_hi &= hi[q]; }
+        }
+        keepmask |= (uint32_t)k << q;
+        kept += k;
+    }
+    uint32_t tot;
+    const uint32_t keep_ex = block_excl_scan(kept, warp_sums, tot);
+    if (threadIdx.x == 0) s_keep_base = lookback_exclusive(status_keep, tile, tot, 0);
+    __syncthreads();
+    uint64_t pos = s_keep_base + keep_ex;
+#pragma unroll
+    for (int q = 0; q < CUT_ITEMS; ++q)
+        if (keepmask >> q & 1) {
+            out_y[pos] = (sk_max - sk_min) - x[q];
+            out_klo[pos] = ~lo[q];                 // ascending sort of ~key == descending key
+            out_khi[pos] = ~hi[q] & HI_KEY_MASK;
+            out_idx[pos] = (uint32_t)(b0 + q);
+            ++pos;
+        }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        or_lo |= __shfl_xor_sync(0xffffffffu, or_lo, d);
+        or_hi |= __shfl_xor_sync(0xffffffffu, or_hi, d);
+        and_lo &= __shfl_xor_sync(0xffffffffu, and_lo, d);
+        and_hi &= __shfl_xor_sync(0xffffffffu, and_hi, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&ctr->key_or[0], (unsigned long long)or_lo);
+        atomicOr(&ctr->key_or[1], (unsigned long long)or_hi);
+        atomicAnd(&ctr->key_and[0], (unsigned long long)and_lo);
+        atomicAnd(&ctr->key_and[1], (unsigned long long)and_hi);
+    }
+}
+
 // ------------------------------------------------------------------ stable LSD radix sort of (y, idx) pairs
 constexpr int SORT_BITS = 8;
 constexpr int SORT_BINS = 1 << SORT_BITS;
@@ -811,26 +898,32 @@ __global__ void __launch_bounds__(TILE) scan_u32_kernel(const uint32_t *__restri
         if (b0 + q < n) { out[b0 + q] = run; run += v[q]; }
 }
 
-__global__ void __launch_bounds__(TILE) sort_scatter_kernel(const uint64_t *__restrict__ y_in,
+// `dig` = the array the digit is taken from (one of the payload arrays).  WIDE also moves the
+// two inverted key words (det policy composite sort).
+template <bool WIDE>
+__global__ void __launch_bounds__(TILE) sort_scatter_kernel(const uint64_t *__restrict__ dig,
+                                                            const uint64_t *__restrict__ y_in,
                                                             const uint32_t *__restrict__ idx_in, int64_t n, int shift,
                                                             const uint32_t *__restrict__ matrix_scanned,
                                                             uint32_t ntiles, uint64_t *__restrict__ y_out,
-                                                            uint32_t *__restrict__ idx_out) {
+                                                            uint32_t *__restrict__ idx_out,
+                                                            const uint64_t *__restrict__ klo_in,
+                                                            const uint64_t *__restrict__ khi_in,
+                                                            uint64_t *__restrict__ klo_out,
+                                                            uint64_t *__restrict__ khi_out) {
     __shared__ uint32_t whist[TILE / 32][SORT_BINS];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (TILE / 32) * SORT_BINS; i += TILE) (&whist[0][0])[i] = 0;
     __syncthreads();
     const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)w * (32 * SORT_ITEMS);
-    uint64_t yy[SORT_ITEMS];
-    uint32_t ii[SORT_ITEMS];
+    uint32_t dd[SORT_ITEMS];
     // pass A: per-warp digit counts over the warp's contiguous 512-element segment
 #pragma unroll
     for (int q = 0; q < SORT_ITEMS; ++q) {
         const int64_t i = wbase + q * 32 + lane;
         const bool ok = i < n;
-        yy[q] = ok ? y_in[i] : 0;
-        ii[q] = ok ? idx_in[i] : 0;
-        const uint32_t d = (uint32_t)(yy[q] >> shift) & (SORT_BINS - 1);
+        dd[q] = ok ? (uint32_t)(dig[i] >> shift) & (SORT_BINS - 1) : 0;
+        const uint32_t d = dd[q];
         const unsigned act = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const unsigned peers = __match_any_sync(act, d);
@@ -854,14 +947,15 @@ __global__ void __launch_bounds__(TILE) sort_scatter_kernel(const uint64_t *__re
     for (int q = 0; q < SORT_ITEMS; ++q) {
         const int64_t i = wbase + q * 32 + lane;
         const bool ok = i < n;
-        const uint32_t d = (uint32_t)(yy[q] >> shift) & (SORT_BINS - 1);
+        const uint32_t d = dd[q];
         const unsigned act = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const unsigned peers = __match_any_sync(act, d);
             const uint32_t rank = __popc(peers & ((1u << lane) - 1));
             const uint32_t pos = whist[w][d] + rank;
-            y_out[pos] = yy[q];
-            idx_out[pos] = ii[q];
+            y_out[pos] = y_in[i];
+            idx_out[pos] = idx_in[i];
+            if (WIDE) { klo_out[pos] = klo_in[i]; khi_out[pos] = khi_in[i]; }
             __syncwarp(peers);
             if (lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += __popc(peers);
         }
@@ -891,7 +985,7 @@ __global__ void __launch_bounds__(TILE) pack_rec_kernel(const spl_key *__restric
                                                         int64_t n, Rec *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
     if (i < n) {
-        Rec r{keys[i].lo, keys[i].hi & HI_KEY_MASK, aux[i], ~0ull};
+        Rec r{keys[i].lo, keys[i].hi & HI_KEY_MASK, aux ? aux[i] : 0ull, ~0ull};
         st_rec(out + i, r);
     }
 }

@@ -74,7 +74,7 @@ struct spl_ctx {
     uint32_t *d_hist = nullptr;
     DevBuf status[3];
     // scratch
-    DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], matrix, matrix2;
+    DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2;
     DevBuf pool_front, pool_uniq;      // frontier buffers lent to the active solver
     std::vector<DevBuf *> pool_links;  // link columns of finished solves, reused by the next one
     cudaEvent_t ev[8]{};
@@ -276,6 +276,7 @@ static int zero_ctr(spl_ctx *c, cudaStream_t st) {
     memset(&z, 0, sizeof z);
     z.sk_min = ~0ull;
     z.goal_rank = 0x7fffffffffffffffll;
+    z.key_and[0] = z.key_and[1] = ~0ull;
     *c->h_ctr = z;
     CK(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, st));
     c->h2d_bytes += sizeof z;
@@ -343,76 +344,130 @@ static int run_count(spl_ctx *c, const Rec *front, int64_t n, cudaStream_t st) {
     return read_ctr(c, st);
 }
 
-// radix select of the k-th largest score key; leaves threshold/quota in d_sel (x-space) and h_sel
-static int run_select(spl_ctx *c, const uint64_t *sk, int64_t n, int64_t k, uint64_t sk_min, uint64_t sk_max,
-                      cudaStream_t st) {
+// radix select of the k-th largest element under (score desc[, key desc]); leaves the thresholds and
+// the tie quota in d_sel / h_sel (score in x = sk - sk_min space).
+static int run_select(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t k, uint64_t sk_min,
+                      uint64_t sk_max, int det, cudaStream_t st) {
     const int nbits = bitlen(sk_max - sk_min);
     const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
-    int top = nbits, first = 1;
-    if (nbits == 0) {  // every score equal: threshold x = 0, quota k
-        c->h_sel->prefix = 0; c->h_sel->k_rem = (unsigned long long)k; c->h_sel->c_gt = 0; c->h_sel->pad = 0;
-        CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
-        CK(c, cudaStreamSynchronize(st));
-        return SPL_OK;
-    }
+    memset(c->h_sel, 0, sizeof(SelState));
+    c->h_sel->k_rem = (unsigned long long)k;
+    c->h_sel->tie_count = (unsigned long long)n;  // nbits == 0: every score equal
+    CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
+    int top = nbits, first = 1, init_k = 1;
     while (top > 0) {
         const int bits = std::min(SEL_BITS, top), shift = top - bits;
-        sel_hist_kernel<<<grid, TILE, 0, st>>>(sk, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
-        sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, shift, first, (uint64_t)k, c->d_sel);
+        sel_hist_kernel<0><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+        sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, 0, shift, first, init_k, (uint64_t)k, c->d_sel);
         c->launches += 2;
-        first = 0;
+        first = init_k = 0;
         top = shift;
     }
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     c->d2h_bytes += sizeof(SelState);
+    if (det && c->h_sel->k_rem < c->h_sel->tie_count) {  // split the score ties by key, larger first
+        for (int word = 1; word <= 2; ++word) {
+            top = word == 1 ? 41 : 64;
+            first = 1;
+            while (top > 0) {
+                const int bits = std::min(SEL_BITS, top), shift = top - bits;
+                if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+                else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+                sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, 0, (uint64_t)k, c->d_sel);
+                c->launches += 2;
+                first = 0;
+                top = shift;
+            }
+        }
+        CK(c, cudaGetLastError());
+        c->h_sel->tie_count = ~0ull;  // marks "threshold key valid"
+    }
     return SPL_OK;
 }
 
-// arrival-order cut + stable descending rank sort.  On return idx[*which] holds the kept source
-// indices in rank order (kept = min(k, n)).
-static int run_cut_sort(spl_ctx *c, const uint64_t *sk, int64_t n, int64_t k, uint64_t sk_min, uint64_t sk_max,
-                        int *which, int64_t *kept_out, cudaStream_t st) {
+// one stable LSD pass over `kept` elements: digit = (dig >> shift) & 255
+static int sort_pass(spl_ctx *c, int wide, int cur, const uint64_t *dig, int64_t kept, int shift, unsigned nt,
+                     size_t msz, cudaStream_t st) {
+    const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
+    sort_hist_kernel<<<nt, TILE, 0, st>>>(dig, kept, shift, c->matrix.as<uint32_t>(), nt);
+    CKS(c, prep_status(c, 1, st_tiles, st));
+    CKS(c, reset_ticket(c, 2, st));
+    scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
+                                                c->status[1].as<uint64_t>(), c->d_ctr, 2);
+    if (wide)
+        sort_scatter_kernel<true><<<nt, TILE, 0, st>>>(dig, c->y[cur].as<uint64_t>(), c->idx[cur].as<uint32_t>(), kept, shift,
+                                                        c->matrix2.as<uint32_t>(), nt, c->y[cur ^ 1].as<uint64_t>(),
+                                                        c->idx[cur ^ 1].as<uint32_t>(), c->kl[cur].as<uint64_t>(),
+                                                        c->kh[cur].as<uint64_t>(), c->kl[cur ^ 1].as<uint64_t>(),
+                                                        c->kh[cur ^ 1].as<uint64_t>());
+    else
+        sort_scatter_kernel<false><<<nt, TILE, 0, st>>>(dig, c->y[cur].as<uint64_t>(), c->idx[cur].as<uint32_t>(), kept, shift,
+                                                         c->matrix2.as<uint32_t>(), nt, c->y[cur ^ 1].as<uint64_t>(),
+                                                         c->idx[cur ^ 1].as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
+    c->launches += 3;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+// beam cut + rank sort.  stable: arrival-order cut, stable descending sort by score.  det: cut and sort
+// by (score desc, key desc).  On return idx[*which] holds the kept source indices in rank order.
+static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t k, uint64_t sk_min,
+                        uint64_t sk_max, int det, int *which, int64_t *kept_out, cudaStream_t st) {
     const int64_t kept = std::min(n, k);
     const int keep_all = n <= k;
-    if (!keep_all) CKS(c, run_select(c, sk, n, k, sk_min, sk_max, st));
+    if (!keep_all) CKS(c, run_select(c, sk, recs, n, k, sk_min, sk_max, det, st));
     const uint64_t T = keep_all ? 0 : c->h_sel->prefix;
     for (int b = 0; b < 2; ++b) {
         CK(c, c->y[b].ensure((size_t)kept * 8 + 8, 0, st));
         CK(c, c->idx[b].ensure((size_t)kept * 4 + 4, 0, st));
+        if (det) {
+            CK(c, c->kl[b].ensure((size_t)kept * 8 + 8, 0, st));
+            CK(c, c->kh[b].ensure((size_t)kept * 8 + 8, 0, st));
+        }
     }
     const unsigned ct = nblk(n, TILE * CUT_ITEMS);
     CKS(c, prep_status(c, 1, ct, st));
     CKS(c, prep_status(c, 2, ct, st));
     CKS(c, reset_ticket(c, 1, st));
-    cut_kernel<<<ct, TILE, 0, st>>>(sk, n, sk_min, sk_max, keep_all, c->d_sel, c->y[0].as<uint64_t>(),
-                                     c->idx[0].as<uint32_t>(), c->status[1].as<uint64_t>(),
-                                     c->status[2].as<uint64_t>(), c->d_ctr, 1);
-    ++c->launches;
-    CK(c, cudaGetLastError());
+    uint64_t vary_lo = 0, vary_hi = 0;
+    if (det) {
+        const int all_ties = keep_all || c->h_sel->tie_count != ~0ull;
+        CKS(c, zero_ctr(c, st));
+        cut_det_kernel<<<ct, TILE, 0, st>>>(sk, recs, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->y[0].as<uint64_t>(),
+                                             c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(), c->idx[0].as<uint32_t>(),
+                                             c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CKS(c, read_ctr(c, st));
+        vary_lo = c->h_ctr->key_or[0] ^ c->h_ctr->key_and[0];
+        vary_hi = (c->h_ctr->key_or[1] ^ c->h_ctr->key_and[1]) & HI_KEY_MASK;
+    } else {
+        cut_kernel<<<ct, TILE, 0, st>>>(sk, n, sk_min, sk_max, keep_all, c->d_sel, c->y[0].as<uint64_t>(),
+                                         c->idx[0].as<uint32_t>(), c->status[1].as<uint64_t>(),
+                                         c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+    }
     // y = sk_max - sk in [0, sk_max - sk_min - T]
     const int nbits = bitlen((sk_max - sk_min) - T);
     int cur = 0;
     const unsigned nt = nblk(kept, SORT_TILE);
-    if (nbits > 0 && kept > 1) {
+    if (kept > 1 && (nbits > 0 || vary_lo || vary_hi)) {
         const size_t msz = (size_t)SORT_BINS * nt;
         CK(c, c->matrix.ensure(msz * 4, 0, st));
         CK(c, c->matrix2.ensure(msz * 4, 0, st));
-        const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
+        if (det) {  // least significant first: key.lo, key.hi, then the score
+            for (int shift = 0; shift < 64; shift += SORT_BITS)
+                if ((vary_lo >> shift) & 0xff) { CKS(c, sort_pass(c, 1, cur, c->kl[cur].as<uint64_t>(), kept, shift, nt, msz, st)); cur ^= 1; }
+            for (int shift = 0; shift < 41; shift += SORT_BITS)
+                if ((vary_hi >> shift) & 0xff) { CKS(c, sort_pass(c, 1, cur, c->kh[cur].as<uint64_t>(), kept, shift, nt, msz, st)); cur ^= 1; }
+        }
         for (int shift = 0; shift < nbits; shift += SORT_BITS) {
-            sort_hist_kernel<<<nt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), kept, shift, c->matrix.as<uint32_t>(), nt);
-            CKS(c, prep_status(c, 1, st_tiles, st));
-            CKS(c, reset_ticket(c, 2, st));
-            scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
-                                                        c->status[1].as<uint64_t>(), c->d_ctr, 2);
-            sort_scatter_kernel<<<nt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), c->idx[cur].as<uint32_t>(), kept, shift,
-                                                      c->matrix2.as<uint32_t>(), nt, c->y[cur ^ 1].as<uint64_t>(),
-                                                      c->idx[cur ^ 1].as<uint32_t>());
-            c->launches += 3;
+            CKS(c, sort_pass(c, det, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
             cur ^= 1;
         }
-        CK(c, cudaGetLastError());
     }
     *which = cur;
     *kept_out = kept;
@@ -497,9 +552,9 @@ int32_t spl_score(spl_ctx *c, int32_t heuristic, int32_t noise, const spl_key *k
 
 int32_t spl_topk(spl_ctx *c, const double *scores, const spl_key *keys, int64_t n, int64_t k, int32_t tie_policy,
                  int64_t *out_idx, int64_t *n_out, void *stream) {
-    (void)keys;
     if (!c || !n_out || n < 0 || n >= (1ll << 32) || k < 0) return fail(c, SPL_E_INVALID, "spl_topk: bad arguments");
-    if (tie_policy != SPL_TIE_STABLE) return fail(c, SPL_E_INVALID, "spl_topk: tie policy %d not available yet", tie_policy);
+    if (tie_policy != SPL_TIE_STABLE && tie_policy != SPL_TIE_KEY) return fail(c, SPL_E_INVALID, "spl_topk: unknown tie policy %d", tie_policy);
+    if (tie_policy == SPL_TIE_KEY && !keys) return fail(c, SPL_E_INVALID, "spl_topk: SPL_TIE_KEY needs keys");
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
     *n_out = 0;
@@ -511,7 +566,15 @@ int32_t spl_topk(spl_ctx *c, const double *scores, const spl_key *keys, int64_t 
     CKS(c, read_ctr(c, st));
     int which = 0;
     int64_t kept = 0;
-    CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), n, k, c->h_ctr->sk_min, c->h_ctr->sk_max, &which, &kept, st));
+    const uint64_t smin = c->h_ctr->sk_min, smax = c->h_ctr->sk_max;
+    const Rec *recs = nullptr;
+    if (tie_policy == SPL_TIE_KEY) {
+        CK(c, c->tmp_rec.ensure((size_t)n * 32, 0, st));
+        pack_rec_kernel<<<nblk(n), TILE, 0, st>>>(keys, nullptr, n, c->tmp_rec.as<Rec>());
+        ++c->launches;
+        recs = c->tmp_rec.as<Rec>();
+    }
+    CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), recs, n, k, smin, smax, tie_policy == SPL_TIE_KEY, &which, &kept, st));
     idx_widen_kernel<<<nblk(kept), TILE, 0, st>>>(c->idx[which].as<uint32_t>(), kept, out_idx);
     ++c->launches;
     CK(c, cudaGetLastError());
@@ -563,7 +626,7 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
                           spl_solver **out) {
     if (!c || !root_key || !out) return fail(c, SPL_E_INVALID, "spl_solver_create: null argument");
     if (use_h && beam < 1) return fail(c, SPL_E_INVALID, "spl_solver_create: beam_width must be >= 1");
-    if (use_h && tie != SPL_TIE_STABLE) return fail(c, SPL_E_INVALID, "spl_solver_create: tie policy %d not available yet", tie);
+    if (use_h && tie != SPL_TIE_STABLE && tie != SPL_TIE_KEY) return fail(c, SPL_E_INVALID, "spl_solver_create: unknown tie policy %d", tie);
     CK(c, cudaSetDevice(c->device));
     cudaStream_t st = 0;
     spl_solver *s = new spl_solver();
@@ -710,7 +773,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     if (s->use_h && n_uniq > 0) {
         int which = 0;
         CK(c, cudaEventRecord(c->ev[4], st));
-        CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), n_uniq, s->beam, sk_min, sk_max, &which, &kept, st));
+        CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), s->uniq.as<Rec>(), n_uniq, s->beam, sk_min, sk_max, s->tie == SPL_TIE_KEY, &which, &kept, st));
         CK(c, cudaEventRecord(c->ev[5], st));
         CK(c, s->front.ensure((size_t)kept * 32, 0, st));
         gather_rec_kernel<<<nblk(kept), TILE, 0, st>>>(s->uniq.as<Rec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<Rec>());

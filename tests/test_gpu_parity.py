@@ -181,6 +181,24 @@ def test_topk_stable(eng, n, k):
     assert (got == want).all()
 
 
+@pytest.mark.parametrize('n,k', [(1000, 1), (1000, 999), (5000, 9000), (300_001, 100_000), (1_000_000, 300_000)])
+def test_topk_det(eng, n, k):
+    """tie policy `det`: sorted(range(n), key=lambda i: (score[i], key[i]), reverse=True)[:k]."""
+    rng = np.random.default_rng(n * 7 + k)
+    vals = np.concatenate([rng.normal(size=11) * 1e3, [0.0, 0.5, -2.0]])
+    sc = vals[rng.integers(0, len(vals), size=n)]
+    lo = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    hi = rng.integers(0, 2 ** 41, size=n, dtype=np.uint64)
+    lo[: n // 3] = lo[0]  # equal low words: order decided by the high word, and vice versa
+    hi[n // 2:] = hi[-1]
+    dup = (lo == lo[0]) & (hi == hi[-1])
+    lo[dup] = np.arange(dup.sum(), dtype=np.uint64)  # keys must stay unique
+    keys, _ = eng.to_device(np.stack([lo, hi], 1), np.zeros(n, np.uint64))
+    got = eng.topk(torch.from_numpy(sc).to(eng.tdev), keys, k, 'det').cpu().numpy()
+    want = np.lexsort((lo, hi, sc))[::-1][:k]
+    assert (got == want).all()
+
+
 def test_topk_all_equal_and_distinct(eng):
     n = 100_000
     keys = torch.zeros((n, 2), dtype=torch.int64, device=eng.tdev)
@@ -238,7 +256,7 @@ def test_bfs_chunked_equals_unchunked(golden):
 
 
 def _stable_runs(golden):
-    return [r for r in golden['beam_runs'] if r['policy'] == 'stable']
+    return golden['beam_runs']  # both tie policies (stable = arrival order, det = key descending)
 
 
 def test_beam_runs_vs_reference(eng, golden):
@@ -263,12 +281,15 @@ def test_beam_runs_vs_reference(eng, golden):
         assert [(s.saved, s.pts, list(s.bonus)) for s in path] == [(p['saved'], p['pts'], p['bonus']) for p in run['path']], what
 
 
-@pytest.mark.parametrize('hname,beam', [('aggressive', 300_000), ('simple', 100_000)])
-def test_beam_vs_oracle_large(eng, hname, beam):
-    """Config 1/3 at the reference's default width (beam 300 000): full arrays vs the oracle."""
+@pytest.mark.parametrize('hname,beam,policy,noise', [('aggressive', 300_000, 'stable', 'const'),
+                                                     ('simple', 100_000, 'stable', 'const'),
+                                                     ('balanced', 100_000, 'det', 'const'),
+                                                     ('efficiency', 50_000, 'det', 'hash')])
+def test_beam_vs_oracle_large(eng, hname, beam, policy, noise):
+    """Config 1/3/4 at the reference's default width (beam 300 000) and both tie policies: full arrays vs the oracle."""
     k, a = S.State.newgame().record()
-    sol = eng.solver(k, a, 15, True, hname, beam, 'stable', 'const')
-    orc = oracle.Solver(15, use_heuristic=True, heuristic_name=hname, beam_width=beam, policy='stable', noise='const')
+    sol = eng.solver(k, a, 15, True, hname, beam, policy, noise)
+    orc = oracle.Solver(15, use_heuristic=True, heuristic_name=hname, beam_width=beam, policy=policy, noise=noise)
     while True:
         gi, oi = sol.step(), orc.step()
         _check_level(sol, orc, gi, oi, None, f'{hname} beam {beam} level {gi["level"]}')
