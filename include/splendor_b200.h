@@ -146,6 +146,36 @@ int32_t spl_score(spl_ctx *ctx, int32_t heuristic, int32_t noise, const spl_key 
 int32_t spl_topk(spl_ctx *ctx, const double *scores_dev, const spl_key *keys_dev, int64_t n, int64_t k,
                  int32_t tie_policy, int64_t *out_idx_dev, int64_t *n_out_host, void *stream);
 
+/* ---- multi-GPU building blocks (one process per GPU; the collectives themselves are issued by the
+ * host through torch.distributed/NCCL between these calls) -------------------------------------
+ * The reference has no distributed path; these exist so that a frontier sharded by key hash
+ * across ranks produces bit-identical levels to the single-GPU solver. */
+
+/* stable partition of a candidate list by owner rank = f(key) mod n_ranks: perm_dev[j] = index of the
+ * j-th candidate in (owner, arrival) order; counts_host[g] = candidates owned by rank g. */
+int32_t spl_owner_partition(spl_ctx *ctx, const spl_key *keys_dev, int64_t n, int32_t n_ranks, int64_t *perm_dev,
+                            int64_t *counts_host, void *stream);
+
+/* distributed beam cut: the radix select of spl_topk, one pass at a time, so that the host can
+ * all-reduce the 2048-bin histogram (*hist_dev_out, uint32) between spl_dtopk_hist and spl_dtopk_pick.
+ * word 0 = score passes, word 1/2 = key.hi / key.lo passes among score ties (det policy). */
+int32_t spl_dtopk_begin(spl_ctx *ctx, const double *scores_dev, const spl_key *keys_dev_or_null, int64_t n,
+                        uint64_t *sk_min_host, uint64_t *sk_max_host, void *stream);
+int32_t spl_dtopk_hist(spl_ctx *ctx, int32_t word, int32_t shift, int32_t bits, int32_t first, uint64_t sk_min_global,
+                       uint32_t **hist_dev_out, void *stream);
+int32_t spl_dtopk_pick(spl_ctx *ctx, int32_t word, int32_t shift, int32_t first, int32_t init_k, int64_t k, void *stream);
+/* select state = {score threshold (x space), tie quota, count above, tie bucket size, key.hi, key.lo threshold} */
+int32_t spl_dtopk_get(spl_ctx *ctx, uint64_t state_host[6], void *stream);
+int32_t spl_dtopk_set(spl_ctx *ctx, const uint64_t state_host[6], void *stream);
+/* local cut by the state set above + local rank sort; outputs the survivors' indices and sort words */
+int32_t spl_dtopk_cut(spl_ctx *ctx, int32_t tie_policy, int32_t keep_all, int32_t all_ties, uint64_t sk_min_global,
+                      uint64_t sk_max_global, int64_t *out_idx_dev, uint64_t *out_y_dev, uint64_t *out_klo_dev,
+                      uint64_t *out_khi_dev, int64_t *kept_host, void *stream);
+/* out[i] (+)= #{ j : b[j] < a[i] } (or <= when inclusive) for ascending-sorted composite b; words = 1 | 3 */
+int32_t spl_count_less(spl_ctx *ctx, int32_t words, int32_t inclusive, const uint64_t *ay_dev, const uint64_t *akl_dev,
+                       const uint64_t *akh_dev, int64_t na, const uint64_t *by_dev, const uint64_t *bkl_dev,
+                       const uint64_t *bkh_dev, int64_t nb, int64_t *out_dev, int32_t accumulate, void *stream);
+
 /* ---- fused level-synchronous solver: State.solve (src/solver.py:390-464) ------------------- */
 
 /* root_host: one packed state (key + aux) in HOST memory -- the `self` of solve().

@@ -63,6 +63,14 @@ def _load():
         'spl_dedup': (i32, [vp, vp, vp, i64, vp, vp, vp, C.POINTER(i64), vp]),
         'spl_score': (i32, [vp, i32, i32, vp, vp, i64, vp, vp]),
         'spl_topk': (i32, [vp, vp, vp, i64, i64, i32, vp, C.POINTER(i64), vp]),
+        'spl_owner_partition': (i32, [vp, vp, i64, i32, vp, vp, vp]),
+        'spl_dtopk_begin': (i32, [vp, vp, vp, i64, C.POINTER(u64), C.POINTER(u64), vp]),
+        'spl_dtopk_hist': (i32, [vp, i32, i32, i32, i32, u64, C.POINTER(vp), vp]),
+        'spl_dtopk_pick': (i32, [vp, i32, i32, i32, i32, i64, vp]),
+        'spl_dtopk_get': (i32, [vp, vp, vp]),
+        'spl_dtopk_set': (i32, [vp, vp, vp]),
+        'spl_dtopk_cut': (i32, [vp, i32, i32, i32, u64, u64, vp, vp, vp, vp, C.POINTER(i64), vp]),
+        'spl_count_less': (i32, [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, i64, vp, i32, vp]),
         'spl_solver_create': (i32, [vp, C.POINTER(Key), u64, i32, i32, i32, i64, i32, i32, i32, C.POINTER(vp)]),
         'spl_solver_destroy': (i32, [vp]),
         'spl_solver_step': (i32, [vp, C.POINTER(LevelInfo), vp]),

@@ -1020,6 +1020,51 @@ __global__ void __launch_bounds__(TILE) flip_scores_kernel(const double *__restr
     }
 }
 
+// ------------------------------------------------------------------ multi-GPU building blocks
+// owner rank of a key: a second, independent mix of the key so that ownership and the slot index
+// inside the owner's table are uncorrelated
+__device__ __host__ __forceinline__ uint32_t owner_of_key(uint64_t lo, uint64_t hi, uint32_t n_ranks) {
+    uint64_t x = (lo * 0xC2B2AE3D27D4EB4Full) ^ (hi * 0x165667B19E3779F9ull);
+    x ^= x >> 29;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 32;
+    return (uint32_t)(((x & 0xffffffffull) * n_ranks) >> 32);
+}
+__global__ void __launch_bounds__(TILE) owner_kernel(const spl_key *__restrict__ keys, int64_t n, uint32_t n_ranks,
+                                                     uint64_t *__restrict__ y, uint32_t *__restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) {
+        y[i] = owner_of_key(keys[i].lo, keys[i].hi & HI_KEY_MASK, n_ranks);
+        idx[i] = (uint32_t)i;
+    }
+}
+// for every a[i] (sorted or not): number of elements of the ascending-sorted composite list b that
+// are < a[i] (inclusive = 0) or <= a[i] (inclusive = 1); composite = (y, klo, khi) when words == 3
+__global__ void __launch_bounds__(TILE) count_less_kernel(int words, int inclusive, const uint64_t *__restrict__ ay,
+                                                          const uint64_t *__restrict__ akl, const uint64_t *__restrict__ akh,
+                                                          int64_t na, const uint64_t *__restrict__ by,
+                                                          const uint64_t *__restrict__ bkl, const uint64_t *__restrict__ bkh,
+                                                          int64_t nb, int64_t *__restrict__ out, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i >= na) return;
+    const uint64_t y = ay[i], kl = words == 3 ? akl[i] : 0, kh = words == 3 ? akh[i] : 0;
+    int64_t lo = 0, hi = nb;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const uint64_t my = by[mid];
+        bool less;  // b[mid] < a (or <= a)
+        if (my != y) less = my < y;
+        else if (words == 3) {
+            const uint64_t mh = bkh[mid], ml = bkl[mid];
+            if (mh != kh) less = mh < kh;
+            else if (ml != kl) less = ml < kl;
+            else less = inclusive;
+        } else less = inclusive;
+        if (less) lo = mid + 1; else hi = mid;
+    }
+    out[i] = (accumulate ? out[i] : 0) + lo;
+}
+
 // move every occupied slot of an old table into a larger one (tags preserved)
 __global__ void __launch_bounds__(TILE) rehash_kernel(const uint64_t *__restrict__ old_table, uint64_t old_cap,
                                                       uint64_t *__restrict__ table, uint64_t cap, Counters *ctr) {

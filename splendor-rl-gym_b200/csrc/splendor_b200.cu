@@ -79,6 +79,8 @@ struct spl_ctx {
     std::vector<DevBuf *> pool_links;  // link columns of finished solves, reused by the next one
     cudaEvent_t ev[8]{};
     long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    int64_t dtopk_n = 0;       // distributed top-k: elements staged by spl_dtopk_begin
+    bool dtopk_recs = false;
 };
 
 static int fail(spl_ctx *c, int code, const char *fmt, ...) {
@@ -413,11 +415,27 @@ static int sort_pass(spl_ctx *c, int wide, int cur, const uint64_t *dig, int64_t
 
 // beam cut + rank sort.  stable: arrival-order cut, stable descending sort by score.  det: cut and sort
 // by (score desc, key desc).  On return idx[*which] holds the kept source indices in rank order.
+static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t cap_kept, int keep_all,
+                       int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int *which, int64_t *kept_out,
+                       cudaStream_t st);
+
 static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t k, uint64_t sk_min,
                         uint64_t sk_max, int det, int *which, int64_t *kept_out, cudaStream_t st) {
-    const int64_t kept = std::min(n, k);
     const int keep_all = n <= k;
     if (!keep_all) CKS(c, run_select(c, sk, recs, n, k, sk_min, sk_max, det, st));
+    const int all_ties = keep_all || c->h_sel->tie_count != ~0ull;
+    CKS(c, do_cut_sort(c, sk, recs, n, std::min(n, k), keep_all, all_ties, sk_min, sk_max, det, which, kept_out, st));
+    if (*kept_out != std::min(n, k))
+        return fail(c, SPL_E_CUDA, "internal: cut kept %lld states, expected %lld", (long long)*kept_out, (long long)std::min(n, k));
+    return SPL_OK;
+}
+
+// cut by the thresholds currently in d_sel / h_sel (x-space score threshold `prefix`, arrival quota
+// `k_rem` for the stable policy, key threshold khi/klo for det), then rank-sort the survivors.
+static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t cap_kept, int keep_all,
+                       int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int *which, int64_t *kept_out,
+                       cudaStream_t st) {
+    int64_t kept = cap_kept;
     const uint64_t T = keep_all ? 0 : c->h_sel->prefix;
     for (int b = 0; b < 2; ++b) {
         CK(c, c->y[b].ensure((size_t)kept * 8 + 8, 0, st));
@@ -433,7 +451,6 @@ static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t
     CKS(c, reset_ticket(c, 1, st));
     uint64_t vary_lo = 0, vary_hi = 0;
     if (det) {
-        const int all_ties = keep_all || c->h_sel->tie_count != ~0ull;
         CKS(c, zero_ctr(c, st));
         cut_det_kernel<<<ct, TILE, 0, st>>>(sk, recs, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->y[0].as<uint64_t>(),
                                              c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(), c->idx[0].as<uint32_t>(),
@@ -449,6 +466,14 @@ static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t
                                          c->status[2].as<uint64_t>(), c->d_ctr, 1);
         ++c->launches;
         CK(c, cudaGetLastError());
+    }
+    {   // survivors actually written = inclusive prefix published by the last cut tile
+        uint64_t last = 0;
+        CK(c, cudaMemcpyAsync(&last, c->status[2].as<uint64_t>() + (ct - 1), 8, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        c->d2h_bytes += 8;
+        kept = (int64_t)(last & ((1ull << 62) - 1));
+        if (kept > cap_kept) return fail(c, SPL_E_CUDA, "internal: cut kept %lld > capacity %lld", (long long)kept, (long long)cap_kept);
     }
     // y = sk_max - sk in [0, sk_max - sk_min - T]
     const int nbits = bitlen((sk_max - sk_min) - T);
@@ -580,6 +605,157 @@ int32_t spl_topk(spl_ctx *c, const double *scores, const spl_key *keys, int64_t 
     CK(c, cudaGetLastError());
     CK(c, cudaStreamSynchronize(st));
     *n_out = kept;
+    return SPL_OK;
+}
+
+// ---- multi-GPU building blocks ----------------------------------------------------------------
+int32_t spl_owner_partition(spl_ctx *c, const spl_key *keys, int64_t n, int32_t n_ranks, int64_t *perm, int64_t *counts_host,
+                            void *stream) {
+    if (!c || !counts_host || n < 0 || n >= (1ll << 32) || n_ranks < 1 || n_ranks > 256)
+        return fail(c, SPL_E_INVALID, "spl_owner_partition: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    for (int g = 0; g < n_ranks; ++g) counts_host[g] = 0;
+    if (n == 0) return SPL_OK;
+    for (int b = 0; b < 2; ++b) {
+        CK(c, c->y[b].ensure((size_t)n * 8 + 8, 0, st));
+        CK(c, c->idx[b].ensure((size_t)n * 4 + 4, 0, st));
+    }
+    owner_kernel<<<nblk(n), TILE, 0, st>>>(keys, n, (uint32_t)n_ranks, c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>());
+    ++c->launches;
+    const unsigned nt = nblk(n, SORT_TILE);
+    const size_t msz = (size_t)SORT_BINS * nt;
+    CK(c, c->matrix.ensure(msz * 4, 0, st));
+    CK(c, c->matrix2.ensure(msz * 4, 0, st));
+    CKS(c, sort_pass(c, 0, 0, c->y[0].as<uint64_t>(), n, 0, nt, msz, st));  // one stable pass: digit = owner
+    idx_widen_kernel<<<nblk(n), TILE, 0, st>>>(c->idx[1].as<uint32_t>(), n, perm);
+    ++c->launches;
+    // per-owner counts = differences of the digit-major scanned histogram at tile 0
+    std::vector<uint32_t> base(n_ranks + 1);
+    for (int g = 0; g <= n_ranks; ++g)
+        CK(c, cudaMemcpyAsync(&base[g], c->matrix2.as<uint32_t>() + (size_t)g * nt, 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += 4 * (n_ranks + 1);
+    for (int g = 0; g < n_ranks; ++g) counts_host[g] = (g + 1 < SORT_BINS ? base[g + 1] : (uint32_t)n) - base[g];
+    return SPL_OK;
+}
+
+int32_t spl_dtopk_begin(spl_ctx *c, const double *scores, const spl_key *keys, int64_t n, uint64_t *sk_min_host,
+                        uint64_t *sk_max_host, void *stream) {
+    if (!c || !sk_min_host || !sk_max_host || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dtopk_begin: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    c->dtopk_n = n;
+    c->dtopk_recs = false;
+    *sk_min_host = ~0ull;
+    *sk_max_host = 0;
+    if (n == 0) return SPL_OK;
+    CKS(c, zero_ctr(c, st));
+    CK(c, c->sk.ensure((size_t)n * 8, 0, st));
+    flip_scores_kernel<<<nblk(n), TILE, 0, st>>>(scores, n, c->sk.as<uint64_t>(), c->d_ctr);
+    ++c->launches;
+    if (keys) {
+        CK(c, c->tmp_rec.ensure((size_t)n * 32, 0, st));
+        pack_rec_kernel<<<nblk(n), TILE, 0, st>>>(keys, nullptr, n, c->tmp_rec.as<Rec>());
+        ++c->launches;
+        c->dtopk_recs = true;
+    }
+    CKS(c, read_ctr(c, st));
+    *sk_min_host = c->h_ctr->sk_min;
+    *sk_max_host = c->h_ctr->sk_max;
+    return SPL_OK;
+}
+
+int32_t spl_dtopk_hist(spl_ctx *c, int32_t word, int32_t shift, int32_t bits, int32_t first, uint64_t sk_min_global,
+                       uint32_t **hist_dev_out, void *stream) {
+    if (!c || !hist_dev_out || word < 0 || word > 2 || bits < 1 || bits > SEL_BITS) return fail(c, SPL_E_INVALID, "spl_dtopk_hist: bad arguments");
+    if (word > 0 && !c->dtopk_recs && c->dtopk_n) return fail(c, SPL_E_STATE, "spl_dtopk_hist: key passes need keys in spl_dtopk_begin");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    const int64_t n = c->dtopk_n;
+    *hist_dev_out = c->d_hist;
+    if (n == 0) return SPL_OK;
+    const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
+    const uint64_t *sk = c->sk.as<uint64_t>();
+    const Rec *recs = c->tmp_rec.as<Rec>();
+    if (word == 0) sel_hist_kernel<0><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
+    else if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
+    else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+int32_t spl_dtopk_pick(spl_ctx *c, int32_t word, int32_t shift, int32_t first, int32_t init_k, int64_t k, void *stream) {
+    if (!c) return SPL_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, init_k, (uint64_t)k, c->d_sel);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+int32_t spl_dtopk_get(spl_ctx *c, uint64_t state_host[6], void *stream) {
+    if (!c || !state_host) return SPL_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += sizeof(SelState);
+    memcpy(state_host, c->h_sel, sizeof(SelState));
+    return SPL_OK;
+}
+
+int32_t spl_dtopk_set(spl_ctx *c, const uint64_t state_host[6], void *stream) {
+    if (!c || !state_host) return SPL_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    memcpy(c->h_sel, state_host, sizeof(SelState));
+    CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->h2d_bytes += sizeof(SelState);
+    return SPL_OK;
+}
+
+int32_t spl_dtopk_cut(spl_ctx *c, int32_t tie_policy, int32_t keep_all, int32_t all_ties, uint64_t sk_min_global,
+                      uint64_t sk_max_global, int64_t *out_idx, uint64_t *out_y, uint64_t *out_klo, uint64_t *out_khi,
+                      int64_t *kept_host, void *stream) {
+    if (!c || !kept_host) return SPL_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    const int64_t n = c->dtopk_n;
+    *kept_host = 0;
+    if (n == 0) return SPL_OK;
+    const int det = tie_policy == SPL_TIE_KEY;
+    if (det && !c->dtopk_recs) return fail(c, SPL_E_STATE, "spl_dtopk_cut: det policy needs keys in spl_dtopk_begin");
+    int which = 0;
+    int64_t kept = 0;
+    CKS(c, do_cut_sort(c, c->sk.as<uint64_t>(), c->tmp_rec.as<Rec>(), n, n, keep_all, all_ties, sk_min_global, sk_max_global,
+                       det, &which, &kept, st));
+    if (kept) {
+        idx_widen_kernel<<<nblk(kept), TILE, 0, st>>>(c->idx[which].as<uint32_t>(), kept, out_idx);
+        ++c->launches;
+        if (out_y) CK(c, cudaMemcpyAsync(out_y, c->y[which].p, (size_t)kept * 8, cudaMemcpyDeviceToDevice, st));
+        if (det && out_klo) CK(c, cudaMemcpyAsync(out_klo, c->kl[which].p, (size_t)kept * 8, cudaMemcpyDeviceToDevice, st));
+        if (det && out_khi) CK(c, cudaMemcpyAsync(out_khi, c->kh[which].p, (size_t)kept * 8, cudaMemcpyDeviceToDevice, st));
+        CK(c, cudaGetLastError());
+        CK(c, cudaStreamSynchronize(st));
+    }
+    *kept_host = kept;
+    return SPL_OK;
+}
+
+int32_t spl_count_less(spl_ctx *c, int32_t words, int32_t inclusive, const uint64_t *ay, const uint64_t *akl,
+                       const uint64_t *akh, int64_t na, const uint64_t *by, const uint64_t *bkl, const uint64_t *bkh,
+                       int64_t nb, int64_t *out, int32_t accumulate, void *stream) {
+    if (!c || (words != 1 && words != 3) || na < 0 || nb < 0) return fail(c, SPL_E_INVALID, "spl_count_less: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (na == 0) return SPL_OK;
+    count_less_kernel<<<nblk(na), TILE, 0, st>>>(words, inclusive, ay, akl, akh, na, by, bkl, bkh, nb, out, accumulate);
+    ++c->launches;
+    CK(c, cudaGetLastError());
     return SPL_OK;
 }
 

@@ -308,3 +308,60 @@ def test_verbose_output_matches_reference_format(capsys):
     assert 'SPEEDRUN MODE SOLVER' in out and 'Heuristic: None (pure BFS)' in out
     assert 'turn=0          (0, 0, 0, 0, 0)' in out
     assert 'max_pts=3       (0, 0, 2, 2, 0) 3K6' in out
+
+
+# ------------------------------------------------------------------ multi-GPU building blocks on one GPU
+@pytest.mark.parametrize('cfg', [(255, False, 'simple', 0, 'stable', 'const', 7), (15, True, 'aggressive', 20_000, 'stable', 'const', None),
+                                 (15, True, 'balanced', 20_000, 'det', 'hash', None)])
+def test_sharded_solver_world1_vs_oracle(eng, cfg):
+    """The sharded driver (routing, winner bytes, pass-wise select, global ranks) on a single rank, with the
+    real CUDA backend, must reproduce the oracle level by level (the 2-rank logic is covered on gloo)."""
+    from splendor_rl_gym_b200.sharded import Comm, CudaBackend, ShardedSolver
+    goal, use_h, hname, beam, tie, noise, max_levels = cfg
+    sol = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), 0, 0, goal, use_h, hname, beam, tie, noise)
+    orc = oracle.Solver(goal, use_heuristic=use_h, heuristic_name=hname, beam_width=beam, policy=tie, noise=noise)
+    while True:
+        gi, oi = sol.step(), orc.step()
+        fields = ('frontier', 'goal_rank') if gi['ended'] else ('frontier', 'generated', 'unique', 'kept', 'goal_rank', 'visited')
+        for f in fields:
+            assert gi[f] == oi[f], (f, gi, oi)
+        if gi['ended']:
+            break
+        fr = sol.gather_frontier().cpu().numpy().view(np.uint64)
+        st, lk = orc.level(oi['level'] + 1)
+        assert (fr[:, 0] == st['lo']).all() and (fr[:, 1] == st['hi']).all() and (fr[:, 2] == st['aux']).all()
+        assert (fr[:, 3] == lk).all()
+        if max_levels and len(sol.infos) >= max_levels:
+            break
+    if gi['ended']:
+        assert len(sol.path()[1]) == orc.nlevels - 1
+    eng.reset_visited()
+
+
+def test_owner_partition_and_count_less(eng):
+    import ctypes as C
+    from splendor_rl_gym_b200.sharded import CudaBackend
+    b = CudaBackend(eng)
+    rng = np.random.default_rng(5)
+    n = 300_000
+    keys = torch.from_numpy(rng.integers(0, 2 ** 62, size=(n, 2), dtype=np.int64)).to(eng.tdev)
+    keys[:, 1] &= (1 << 41) - 1
+    for world in (1, 2, 3, 8):
+        perm, counts = b.owner_partition(keys, world)
+        assert counts.sum() == n and sorted(perm.cpu().tolist()) == list(range(n))
+        # stable: within each owner segment the original order is preserved
+        p = perm.cpu().numpy()
+        off = 0
+        for g in range(world):
+            seg = p[off:off + counts[g]]
+            assert (np.diff(seg) > 0).all()
+            off += counts[g]
+        assert counts.min() > 0.8 * n / world  # ownership is balanced
+    a = torch.sort(torch.from_numpy(rng.integers(0, 1000, size=5000, dtype=np.int64)).to(eng.tdev)).values
+    bb = torch.sort(torch.from_numpy(rng.integers(0, 1000, size=7000, dtype=np.int64)).to(eng.tdev)).values
+    out = torch.zeros(5000, dtype=torch.int64, device=eng.tdev)
+    b.count_less(1, False, (a, None, None), (bb, None, None), out, False)
+    assert (out.cpu().numpy() == np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='left')).all()
+    b.count_less(1, True, (a, None, None), (bb, None, None), out, True)
+    want = np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='left') + np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='right')
+    assert (out.cpu().numpy() == want).all()

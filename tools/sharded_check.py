@@ -1,0 +1,67 @@
+"""Multi-GPU parity + timing check, run under torchrun on the GPU box:
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/sharded_check.py --beam 100000
+Every rank runs the sharded solver; rank 0 also runs the CPU oracle and compares every level."""
+import argparse
+import os
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import splendor_rl_gym_b200 as S
+from splendor_rl_gym_b200.sharded import Comm, CudaBackend, ShardedSolver
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--goal', type=int, default=15)
+ap.add_argument('--beam', type=int, default=100_000)
+ap.add_argument('--heuristic', default='aggressive')
+ap.add_argument('--tie', default='stable')
+ap.add_argument('--noise', default='const')
+ap.add_argument('--bfs', type=int, default=0)
+ap.add_argument('--no-oracle', action='store_true')
+ap.add_argument('--reps', type=int, default=1)
+a = ap.parse_args()
+
+local = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+eng = S.Engine(local, table_slots=max(1 << 22, int(a.beam * 110 / 0.6 / max(1, int(os.environ.get('WORLD_SIZE', '1'))))))
+comm = Comm(eng.tdev)
+use_h = a.bfs == 0
+check = comm.rank == 0 and not a.no_oracle
+for rep in range(a.reps):
+    if check and rep == 0:
+        import oracle
+        orc = oracle.Solver(255 if a.bfs else a.goal, use_heuristic=use_h, heuristic_name=a.heuristic, beam_width=a.beam,
+                            policy=a.tie, noise=a.noise)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    sol = ShardedSolver(CudaBackend(eng), comm, 0, 0, 255 if a.bfs else a.goal, use_h, a.heuristic, a.beam, a.tie, a.noise)
+    while True:
+        gi = sol.step()
+        if rep == 0 and not a.no_oracle:
+            fr = sol.gather_frontier() if not gi['ended'] else None
+            if check:
+                oi = orc.step()
+                fields = ('frontier', 'goal_rank') if gi['ended'] else ('frontier', 'generated', 'unique', 'kept', 'goal_rank', 'visited')
+                for f in fields:
+                    assert gi[f] == oi[f], (f, gi, oi)
+                if not gi['ended']:
+                    h = fr.cpu().numpy().view(np.uint64)
+                    st, lk = orc.level(oi['level'] + 1)
+                    assert (h[:, 0] == st['lo']).all() and (h[:, 1] == st['hi']).all() and (h[:, 2] == st['aux']).all() and (h[:, 3] == lk).all()
+        if gi['ended'] or (a.bfs and len(sol.infos) >= a.bfs):
+            break
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    if comm.rank == 0:
+        exp = sum(i['expanded'] for i in sol.infos)
+        print(f'world={comm.world} rep={rep} levels={len(sol.infos)} expanded={exp} wall={dt:.3f}s -> {exp / dt / 1e6:.2f} M expanded/s'
+              + (' PARITY OK vs oracle' if check and rep == 0 else ''), flush=True)
+if comm.on:
+    dist.destroy_process_group()
