@@ -127,28 +127,39 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------ GPU arm
+SHARDED_BEAM_PER_GPU = 4_000_000  # the sharded path materialises a level's candidates: per-rank queue bound
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
 
     import splendor_rl_gym_b200 as S
+    from splendor_rl_gym_b200.sharded import Comm, CudaBackend, ShardedSolver
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    torch.cuda.set_device(local)
+        if a.beam == 30_000_000:  # default: keep the per-GPU queue fixed (weak scaling)
+            a.beam = min(30_000_000, SHARDED_BEAM_PER_GPU * world)
     # visited table sized for the whole search up front (about 85 visited states per beam slot at
     # goal 15) so the timed region never rehashes; capped by the 32-bit slot index.
-    slots = int(min(0xFFFFFFF0, max(1 << 22, a.beam * 72 / 0.62)))
+    slots = int(min(0xFFFFFFF0, max(1 << 22, a.beam * 72 / 0.62 / world)))
     eng = S.Engine(local, table_slots=slots, max_table_bytes=int(150e9))
     k, aux = S.State.newgame().record()
+    comm = Comm(eng.tdev)
 
     def solve_device():
-        sol = eng.solver(k, aux, a.goal, True, a.heuristic, a.beam, a.tie, a.noise)
-        infos = sol.run()
-        sol.close()
+        if world == 1:
+            sol = eng.solver(k, aux, a.goal, True, a.heuristic, a.beam, a.tie, a.noise)
+            infos = sol.run()
+            sol.close()
+        else:  # frontier sharded by key hash over the ranks; every level bit-identical to world == 1
+            sol = ShardedSolver(CudaBackend(eng), comm, k, aux, a.goal, True, a.heuristic, a.beam, a.tie, a.noise)
+            infos = sol.run()
         return infos
 
     for _ in range(a.warmup):
@@ -174,18 +185,23 @@ def run_b200(a):
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - l0
     tm = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    # per-level counters of the sharded solver are already global; count them once
     expanded = torch.tensor([float(sum(i['expanded'] for inf in all_infos for i in inf))], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(expanded, op=dist.ReduceOp.SUM)
+        lt = torch.tensor([float(launches)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
     ms = float(tm.item())
     value = float(expanded.item()) / (ms * 1e-3)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
     # ---- end to end through the public API (host inputs / outputs inside the timed region)
-    import splendor_rl_gym_b200.solver as solver_mod
     h0, d0 = eng.transfer_bytes()
     st = []
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     te0 = time.perf_counter()
     for _ in range(a.steps):
         path = S.State.newgame().solve(goal_pts=a.goal, use_heuristic=True, heuristic_name=a.heuristic,
@@ -194,21 +210,18 @@ def run_b200(a):
     torch.cuda.synchronize()
     te = time.perf_counter() - te0
     h1, d1 = eng.transfer_bytes()
-    e2e_exp = sum(i['expanded'] for i in st)
     e2e_t = torch.tensor([te], dtype=torch.float64, device='cuda')
-    e2e_e = torch.tensor([float(e2e_exp)], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_e, op=dist.ReduceOp.SUM)
-    # path replay goes through spl_expand on 1-state batches: 32 B up, <= 190 * 40 B down per move
-    replay_h2d = (len(path) - 1) * 24
-    replay_d2h = sum(len(list(p)) for p in path[:1]) * 0  # measured below from the records actually copied
-    e2e = {'value': float(e2e_e.item()) / float(e2e_t.item()), 'unit': 'expanded states/s',
-           'h2d_bytes_per_step': (h1 - h0) // a.steps + replay_h2d,
-           'd2h_bytes_per_step': (d1 - d0) // a.steps + (len(path) - 1) * 40 * 32 + replay_d2h,
-           'moves': len(path) - 1, 'final': repr(path[-1]), 'final_pts': path[-1].pts,
+    e2e_exp = sum(i['expanded'] for i in st)
+    # bytes that crossed PCIe per solve: root record + per-launch scalars up; counters, select state,
+    # parent links and the replayed successor lists of the winning line (<= 190 * 40 B per move) down
+    moves = len(path) - 1
+    e2e = {'value': float(e2e_exp) / float(e2e_t.item()), 'unit': 'expanded states/s',
+           'h2d_bytes_per_step': (h1 - h0) // a.steps + moves * 24,
+           'd2h_bytes_per_step': (d1 - d0) // a.steps + moves * 190 * 40,
+           'moves': moves, 'final': repr(path[-1]), 'final_pts': path[-1].pts,
            'seconds_per_solve': float(e2e_t.item()) / a.steps}
-    del solver_mod
 
     if rank != 0:
         if world > 1:
@@ -218,6 +231,26 @@ def run_b200(a):
     # ---- roofline of the dominant kernel, from the last timed solve's per-level CUDA-event times
     infos = all_infos[-1]
     lv = [i for i in infos if i['expanded'] and i['generated']]
+    if world > 1:
+        line = {
+            'metric': 'expanded states/sec (gen+dedup+score+top-k)', 'value': value, 'unit': 'expanded states/s',
+            'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u64 keys / f64 scores',
+            'data': 'synthetic',
+            'config': {'workload': f'C3 (BASELINE configs[2]): speedrun goal {a.goal} -u -H {a.heuristic}, beam {a.beam} '
+                                   f'(= {a.beam // world} per GPU), noise={a.noise}, ties={a.tie}; frontier sharded by key hash, '
+                                   f'NCCL all-to-all routing; one step = one full solve',
+                       'l2': 'working set (visited table %.1f GB per GPU) >> 126 MB L2; no flush needed' % (slots * 32 / 1e9),
+                       'beam': a.beam, 'goal': a.goal, 'heuristic': a.heuristic, 'parallelism': f'hash-sharded x{world}'},
+            'time_to_solve_goal15_s': ms / a.steps * 1e-3, 'levels': len(infos),
+            'expanded_per_step': sum(i['expanded'] for i in lv), 'generated_per_step': sum(i['generated'] for i in lv),
+            'unique_per_step': sum(i['unique'] for i in lv), 'visited': infos[-2]['visited'] if len(infos) > 1 else None,
+            'roofline': None, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'note': 'roofline / cpu_baseline are reported by the N=1 line (same kernels); this line is the sharded driver',
+        }
+        print(json.dumps(line))
+        dist.destroy_process_group()
+        return
     ms_stage = {s: sum(i['ms_' + s] for i in lv) for s in ('count', 'expand', 'resolve', 'select', 'sort')}
     n = sum(i['expanded'] for i in lv)
     gen = sum(i['generated'] for i in lv)

@@ -177,6 +177,21 @@ class State:
             print('=' * 60)
             print()
         k, a = self.record()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # one process per GPU (torchrun): every rank calls solve() collectively; the frontier is
+            # sharded by key hash and each level is bit-identical to the single-GPU search
+            from .sharded import Comm, CudaBackend, ShardedSolver
+            sh = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), k, a, goal_pts, use_heuristic, heuristic_name,
+                               beam_width, tie_policy, noise)
+            for info in sh.run():
+                if stats is not None:
+                    stats.append(info)
+            _, ordinals = sh.path()
+            path = [self]
+            for o in ordinals:
+                path.append(list(path[-1])[o])
+            return path
         sol = eng.solver(k, a, goal_pts, use_heuristic, heuristic_name, beam_width, tie_policy, noise)
         try:
             turn = 0
