@@ -247,6 +247,7 @@ int32_t spl_destroy(spl_ctx *c) {
 
 int32_t spl_reset_visited(spl_ctx *c, void *stream) {
     if (!c) return SPL_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
     CK(c, cudaMemsetAsync(c->table, 0, c->cap * 32, (cudaStream_t)stream));
     c->occupied = 0;
     c->epoch = 0;

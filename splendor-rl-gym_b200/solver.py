@@ -131,15 +131,16 @@ class State:
     def __iter__(self):
         """Successors in reference order -- buys (ascending card index) then gem takes
         (src/solver.py:357-388) -- produced by the expand kernel."""
-        eng = _engine()
+        yield from self._successors(_engine())
+
+    def _successors(self, eng: Engine):
         k, a = self.record()
         keys = torch.tensor([[_i64(k), _i64(k >> 64)]], dtype=torch.int64, device=eng.tdev)
         aux = torch.tensor([_i64(a)], dtype=torch.int64, device=eng.tdev)
         ck, ca, _ = eng.expand(keys, aux)
         ck = ck.cpu().numpy().view(np.uint64)
         ca = ca.cpu().numpy().view(np.uint64)
-        for i in range(len(ca)):
-            yield State.from_record(int(ck[i, 0]), int(ck[i, 1]), int(ca[i]))
+        return [State.from_record(int(ck[i, 0]), int(ck[i, 1]), int(ca[i])) for i in range(len(ca))]
 
     def solve(
         self,
@@ -190,7 +191,7 @@ class State:
             _, ordinals = sh.path()
             path = [self]
             for o in ordinals:
-                path.append(list(path[-1])[o])
+                path.append(path[-1]._successors(eng)[o])
             return path
         sol = eng.solver(k, a, goal_pts, use_heuristic, heuristic_name, beam_width, tie_policy, noise)
         try:
@@ -211,7 +212,7 @@ class State:
         # replay the winning line through __iter__ so every field (saved, bonus, pts) is exact
         path = [self]
         for o in ordinals:
-            path.append(list(path[-1])[o])
+            path.append(path[-1]._successors(eng)[o])
         return path
 
 
