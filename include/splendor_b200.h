@@ -194,6 +194,35 @@ int32_t spl_solver_frontier(spl_solver *s, const spl_key **keys_dev, const uint6
 int32_t spl_solver_path(spl_solver *s, int64_t *ranks_host, int32_t *ordinals_host, int32_t cap,
                         int32_t *n_moves_host);
 
+/* ---- realistic multi-player mode: MultiPlayerState (src/solver.py:471-860) ---------------------
+ * State record = 96 bytes:
+ *   struct { uint64 mlo; uint32 mhi; uint16 gems; uint16 saved; } p[4];   card mask / gems (3 b per colour) / saved
+ *   uint8 vis[12];  visible card per market slot in slot order, tier-major (255 = empty)
+ *   uint8 cur; uint8 pad[3]; uint64 link; uint64 spare;
+ * bonus, pts, gem pool, deck position and final-round state are derived (see csrc/spl_realistic.cuh).
+ * The market order is an INPUT: deck[t] = full sequence of tier t (visible cards first), as built by
+ * CardMarket.from_full_deck(shuffle, seed) (src/solver.py:94-119) on the host. */
+typedef struct {
+    int32_t num_players;     /* 2..4  (GameConfig.num_players, src/solver.py:29) */
+    int32_t target_points;   /* GameConfig.target_points */
+    int32_t gems_per_color;  /* GameConfig.gems_per_color: 4 / 5 / 7 */
+    int32_t noise;           /* SPL_NOISE_* for the randint term at :810 */
+    int32_t deck_len[3];
+    uint8_t deck[3][40];
+} spl_rconfig;
+
+/* MultiPlayerState.__iter__ (:568-748) for a batch of records: successors in reference order
+ * (buys in market slot order, colour triples in combinations() order, double takes). */
+int32_t spl_rexpand(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, int64_t n, void *out_recs_dev,
+                    int64_t cap, int64_t *n_out_host, void *stream);
+/* multi_competitive_heuristic (:778-812), bit-exact doubles */
+int32_t spl_rscore(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, int64_t n, double *scores_dev, void *stream);
+/* MultiPlayerState.solve (:750-860): beam always applied, ties by arrival order, game over when play
+ * returns to the player who triggered the final round.  Steps / path / destroy via spl_solver_*. */
+int32_t spl_rsolver_create(spl_ctx *ctx, const spl_rconfig *cfg, const void *root_rec_host, int64_t beam_width,
+                           int32_t keep_links, spl_solver **out);
+int32_t spl_rsolver_frontier(spl_solver *s, const void **recs_dev, int64_t *n_host);
+
 #ifdef __cplusplus
 }
 #endif

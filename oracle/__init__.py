@@ -193,3 +193,130 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+# ================================================================ realistic mode (MultiPlayerState)
+RPLAYER_DTYPE = np.dtype([('mlo', '<u8'), ('mhi', '<u4'), ('gems', '<u2'), ('saved', '<u2')])
+RREC_DTYPE = np.dtype([('p', RPLAYER_DTYPE, (4,)), ('vis', 'u1', (12,)), ('cur', 'u1'), ('pad', 'u1', (3,)),
+                       ('link', '<u8'), ('spare', '<u8')])
+assert RREC_DTYPE.itemsize == 96
+
+
+class RConfig(C.Structure):
+    _fields_ = [('num_players', C.c_int32), ('target_points', C.c_int32), ('gems_per_color', C.c_int32),
+                ('noise_mode', C.c_int32), ('deck_len', C.c_int32 * 3), ('deck', (C.c_uint8 * 40) * 3)]
+
+
+def make_rconfig(num_players, target_points, gems_per_color, tiers, noise='const') -> RConfig:
+    """tiers = three full card sequences (visible cards first), as CardMarket.from_full_deck builds them."""
+    cfg = RConfig(num_players, target_points, gems_per_color, NOISE_IDS[noise])
+    for t, seq in enumerate(tiers):
+        cfg.deck_len[t] = len(seq)
+        for i, c in enumerate(seq):
+            cfg.deck[t][i] = c
+    return cfg
+
+
+def rident_bytes(rec, num_players) -> bytes:
+    """canonical identity bytes of one record (what tests/golden/make_golden.py::rrec_bytes hashes)"""
+    return rec['p'][:num_players].tobytes() + rec['vis'].tobytes() + bytes([int(rec['cur'])])
+
+
+def _rlib():
+    L = lib()
+    if not getattr(L, '_r_ready', False):
+        L.orc_r_root.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_r_expand.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_r_score.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_r_score.restype = C.c_double
+        L.orc_r_pts.argtypes = [C.c_void_p, C.c_int]
+        L.orc_rsolver_new.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_rsolver_new.restype = C.c_void_p
+        L.orc_rsolver_free.argtypes = [C.c_void_p]
+        L.orc_rsolver_step.argtypes = [C.c_void_p, C.POINTER(LevelInfo)]
+        L.orc_rsolver_nlevels.argtypes = [C.c_void_p]
+        L.orc_rsolver_level_size.argtypes = [C.c_void_p, C.c_int]
+        L.orc_rsolver_level_size.restype = C.c_int64
+        L.orc_rsolver_level_states.argtypes = [C.c_void_p, C.c_int]
+        L.orc_rsolver_level_states.restype = C.c_void_p
+        L.orc_rsolver_goal_rank.argtypes = [C.c_void_p]
+        L.orc_rsolver_goal_rank.restype = C.c_int64
+        L.orc_rsolver_smin.argtypes = [C.c_void_p]
+        L.orc_rsolver_smin.restype = C.c_double
+        L.orc_rsolver_smax.argtypes = [C.c_void_p]
+        L.orc_rsolver_smax.restype = C.c_double
+        L.orc_rsolver_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L._r_ready = True
+    return L
+
+
+def r_root(cfg: RConfig) -> np.ndarray:
+    out = np.zeros(1, RREC_DTYPE)
+    _rlib().orc_r_root(C.byref(cfg), out.ctypes.data)
+    return out
+
+
+def r_expand(cfg: RConfig, rec: np.ndarray) -> np.ndarray:
+    out = np.zeros(32, RREC_DTYPE)
+    s = np.ascontiguousarray(rec).reshape(1)
+    n = _rlib().orc_r_expand(C.byref(cfg), s.ctypes.data, out.ctypes.data)
+    return out[:n].copy()
+
+
+def r_score(cfg: RConfig, recs: np.ndarray) -> np.ndarray:
+    recs = np.ascontiguousarray(recs)
+    L = _rlib()
+    return np.array([L.orc_r_score(C.byref(cfg), recs.ctypes.data + i * 96) for i in range(len(recs))], np.float64)
+
+
+def r_pts(rec, player) -> int:
+    s = np.ascontiguousarray(rec).reshape(1)
+    return _rlib().orc_r_pts(s.ctypes.data, player)
+
+
+class RSolver:
+    """Level stepper over the oracle's restatement of MultiPlayerState.solve (src/solver.py:750-860)."""
+
+    def __init__(self, cfg: RConfig, beam_width=20_000):
+        self.cfg = cfg
+        self._h = _rlib().orc_rsolver_new(C.byref(cfg), beam_width)
+        self.infos, self.done = [], False
+
+    def step(self):
+        li = LevelInfo()
+        self.done = bool(_rlib().orc_rsolver_step(self._h, C.byref(li)))
+        self.infos.append(li.as_dict())
+        return self.infos[-1]
+
+    def run(self):
+        while not self.done:
+            self.step()
+        return self.infos
+
+    @property
+    def nlevels(self):
+        return _rlib().orc_rsolver_nlevels(self._h)
+
+    def level(self, i):
+        n = _rlib().orc_rsolver_level_size(self._h, i)
+        sp = _rlib().orc_rsolver_level_states(self._h, i)
+        return np.frombuffer((C.c_char * (n * 96)).from_address(sp), RREC_DTYPE).copy()
+
+    def path(self):
+        out = np.zeros(self.nlevels, RREC_DTYPE)
+        n = _rlib().orc_rsolver_path(self._h, out.ctypes.data, len(out))
+        return out[:n]
+
+    def score_range(self):
+        return _rlib().orc_rsolver_smin(self._h), _rlib().orc_rsolver_smax(self._h)
+
+    def close(self):
+        if self._h:
+            _rlib().orc_rsolver_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(TILE) resolve_kernel(const Rec *__restrict__ f
                 const uint64_t t = (uint64_t)c0 + i;
                 r.lo = list_keys[t].lo;
                 r.hi = list_keys[t].hi & HI_KEY_MASK;
-                r.aux = list_aux[t];
+                r.aux = list_aux ? list_aux[t] : 0;
                 r.link = t;
                 if (out_src) out_src[pos] = (int64_t)t;
             }

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "spl_kernels.cuh"
+#include "spl_realistic.cuh"
 #include "spl_tables.cuh"
 
 using namespace spl;
@@ -76,6 +77,7 @@ struct spl_ctx {
     // scratch
     DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2;
     DevBuf pool_front, pool_uniq;      // frontier buffers lent to the active solver
+    DevBuf rcfg, rcand, rkeys, rvmask, ridx64, rtmp;  // realistic mode scratch
     std::vector<DevBuf *> pool_links;  // link columns of finished solves, reused by the next one
     cudaEvent_t ev[8]{};
     long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -766,6 +768,8 @@ int32_t spl_count_less(spl_ctx *c, int32_t words, int32_t inclusive, const uint6
 struct spl_solver {
     spl_ctx *c = nullptr;
     int goal = 15, use_h = 0, heuristic = 0, tie = 0, noise = 0, keep_links = 1;
+    bool realistic = false;
+    spl_rconfig rcfg{};
     int64_t beam = 300000;
     DevBuf front, uniq;
     int64_t n_front = 0;
@@ -790,9 +794,165 @@ static int save_links(spl_solver *s, cudaStream_t st) {
     s->level_n.push_back(s->n_front);
     if (!s->keep_links || s->n_front == 0) return SPL_OK;
     CK(c, b->ensure((size_t)s->n_front * 8, 0, st));
-    unpack_rec_kernel<<<nblk(s->n_front), TILE, 0, st>>>(s->front.as<Rec>(), s->n_front, nullptr, nullptr, b->as<uint64_t>());
+    if (s->realistic)
+        r_links_kernel<<<nblk(s->n_front), TILE, 0, st>>>(s->front.as<RRec>(), s->n_front, b->as<uint64_t>());
+    else
+        unpack_rec_kernel<<<nblk(s->n_front), TILE, 0, st>>>(s->front.as<Rec>(), s->n_front, nullptr, nullptr, b->as<uint64_t>());
     ++c->launches;
     CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+// ------------------------------------------------------------------ realistic mode host side
+static int upload_rconfig(spl_ctx *c, const spl_rconfig *cfg, cudaStream_t st) {
+    if (!cfg || cfg->num_players < 2 || cfg->num_players > 4 || cfg->gems_per_color < 1 || cfg->gems_per_color > 7)
+        return fail(c, SPL_E_INVALID, "realistic config: num_players must be 2..4 and gems_per_color 1..7");
+    const HostTables &T = host_tables();
+    RConfigDev h;
+    memset(&h, 0, sizeof h);
+    h.P = cfg->num_players; h.target = cfg->target_points; h.gpc = cfg->gems_per_color; h.noise = cfg->noise;
+    for (int t = 0; t < 3; ++t) {
+        if (cfg->deck_len[t] < 0 || cfg->deck_len[t] > 40) return fail(c, SPL_E_INVALID, "realistic config: bad deck length");
+        h.deck_len[t] = cfg->deck_len[t];
+        memcpy(h.deck[t], cfg->deck[t], 40);
+    }
+    for (int i = 0; i < SPL_NUM_CARDS; ++i) {
+        const int t = T.card_pt[i] == 0 ? 0 : T.card_pt[i] <= 2 ? 1 : 2;  // tiers by points, src/solver.py:102-104
+        if (i < 64) { h.col_lo[T.card_bonus[i]] |= 1ull << i; h.pt_lo[T.card_pt[i]] |= 1ull << i; h.tier_lo[t] |= 1ull << i; }
+        else { h.col_hi[T.card_bonus[i]] |= 1u << (i - 64); h.pt_hi[T.card_pt[i]] |= 1u << (i - 64); h.tier_hi[t] |= 1u << (i - 64); }
+        h.card[i] = T.dev.card[i];
+    }
+    CK(c, c->rcfg.ensure(sizeof h, 0, st));
+    CK(c, cudaMemcpyAsync(c->rcfg.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    CK(c, cudaStreamSynchronize(st));  // h is a stack object
+    c->h2d_bytes += sizeof h;
+    return SPL_OK;
+}
+
+// count + materialise the successors of front[0..n) into c->rcand (+ fingerprints in c->rkeys)
+static int r_expand_all(spl_ctx *c, const RRec *front, int64_t n, int64_t rank_base, bool keys, int64_t *total_out,
+                        cudaStream_t st) {
+    const unsigned nt = nblk(n);
+    CK(c, c->off.ensure((size_t)n * 4 + 4, 0, st));
+    CK(c, c->rvmask.ensure((size_t)n * 4 + 4, 0, st));
+    CKS(c, zero_ctr(c, st));
+    CKS(c, prep_status(c, 0, nt, st));
+    r_count_scan_kernel<<<nt, TILE, 0, st>>>(front, n, c->rcfg.as<RConfigDev>(), c->off.as<uint32_t>(), c->rvmask.as<uint32_t>(),
+                                              c->status[0].as<uint64_t>(), c->d_ctr, 0);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    const int64_t total = (int64_t)c->h_ctr->total_cands;
+    *total_out = total;
+    if (total == 0) return SPL_OK;
+    CK(c, c->rcand.ensure((size_t)total * 96, 0, st));
+    if (keys) CK(c, c->rkeys.ensure((size_t)total * 16, 0, st));
+    r_expand_kernel<<<nt, TILE, 0, st>>>(front, n, c->rcfg.as<RConfigDev>(), c->off.as<uint32_t>(), c->rvmask.as<uint32_t>(),
+                                          rank_base, c->rcand.as<RRec>(), keys ? c->rkeys.as<spl_key>() : nullptr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
+    spl_ctx *c = s->c;
+    memset(info, 0, sizeof *info);
+    info->level = s->level;
+    info->frontier = s->n_front;
+    info->goal_rank = -1;
+    const int64_t n = s->n_front;
+    const RRec *front = s->front.as<RRec>();
+    // game over on dequeue (src/solver.py:827-829)
+    CKS(c, zero_ctr(c, st));
+    r_goal_kernel<<<nblk(n), TILE, 0, st>>>(front, n, c->rcfg.as<RConfigDev>(), c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    if (c->h_ctr->goal_rank != 0x7fffffffffffffffll || s->level > 1000) {  // turn limit, :849-852
+        s->ended = true;
+        s->goal_rank = c->h_ctr->goal_rank != 0x7fffffffffffffffll ? c->h_ctr->goal_rank : n - 1;
+        info->ended = 1;
+        info->goal_rank = c->h_ctr->goal_rank != 0x7fffffffffffffffll ? s->goal_rank : -1;
+        info->visited = (int64_t)c->occupied;
+        info->table_slots = c->cap;
+        return SPL_OK;
+    }
+    int64_t total = 0, n_new = 0, kept = 0;
+    CK(c, cudaEventRecord(c->ev[0], st));
+    CKS(c, r_expand_all(c, front, n, 0, true, &total, st));
+    CK(c, cudaEventRecord(c->ev[1], st));
+    info->expanded = n;
+    info->generated = total;
+    if (total >= 0xFFFFFFFFll) return fail(c, SPL_E_INVALID, "level produced %lld candidates (>= 2^32)", (long long)total);
+    if (total) {  // first-arrival dedup on the identity fingerprint (:840-843)
+        CKS(c, ensure_table(c, (uint64_t)total, st));
+        uint64_t tag;
+        CKS(c, next_epoch(c, tag));
+        CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
+        CKS(c, zero_ctr(c, st));
+        probe_list_kernel<<<nblk(total), TILE, 0, st>>>(c->rkeys.as<spl_key>(), total, c->table, c->cap, tag,
+                                                        c->cand_slot.as<uint32_t>(), c->d_ctr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CKS(c, read_ctr(c, st));
+        if (c->h_ctr->error) return fail(c, SPL_E_TABLE_FULL, "visited table full during level %d", s->level);
+        n_new = (int64_t)c->h_ctr->n_new;
+        c->occupied += n_new;
+    }
+    info->unique = n_new;
+    if (n_new) {
+        CK(c, c->rtmp.ensure((size_t)n_new * 32, 0, st));
+        CK(c, c->ridx64.ensure((size_t)n_new * 8, 0, st));
+        const unsigned nt = nblk(total, TILE * 32);
+        CKS(c, prep_status(c, 0, nt, st));
+        CKS(c, reset_ticket(c, 0, st));
+        resolve_kernel<SRC_LIST, false><<<nt, TILE, sizeof(ResolveSmem), st>>>(
+            nullptr, 0, c->d_tabs, c->d_takes_idx, c->d_takes_edges, nullptr, (uint32_t)total, c->table,
+            c->cand_slot.as<uint32_t>(), c->rkeys.as<spl_key>(), nullptr, 0, 0, c->rtmp.as<Rec>(), nullptr,
+            c->ridx64.as<int64_t>(), 0, 0, c->luts, c->status[0].as<uint64_t>(), c->d_ctr, 0);
+        CK(c, s->uniq.ensure((size_t)n_new * 96, 0, st));
+        r_gather_kernel<int64_t><<<nblk(n_new), TILE, 0, st>>>(c->rcand.as<RRec>(), c->ridx64.as<int64_t>(), n_new, s->uniq.as<RRec>());
+        c->launches += 2;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev[2], st));
+        // score + beam cut, ties by arrival order (:846)
+        CKS(c, zero_ctr(c, st));
+        CK(c, c->sk.ensure((size_t)n_new * 8, 0, st));
+        r_score_kernel<<<nblk(n_new), TILE, 0, st>>>(s->uniq.as<RRec>(), n_new, c->rcfg.as<RConfigDev>(), c->luts,
+                                                      c->sk.as<uint64_t>(), nullptr, c->d_ctr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CKS(c, read_ctr(c, st));
+        const uint64_t smin = c->h_ctr->sk_min, smax = c->h_ctr->sk_max;
+        int which = 0;
+        CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), nullptr, n_new, s->beam, smin, smax, 0, &which, &kept, st));
+        CK(c, s->front.ensure((size_t)kept * 96, 0, st));
+        r_gather_kernel<uint32_t><<<nblk(kept), TILE, 0, st>>>(s->uniq.as<RRec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<RRec>());
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev[3], st));
+        CK(c, cudaStreamSynchronize(st));
+        float t;
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
+        info->ms_expand = t;
+        cudaEventElapsedTime(&t, c->ev[1], c->ev[2]);
+        info->ms_resolve = t;
+        cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
+        info->ms_select = t;
+    }
+    info->kept = kept;
+    info->visited = (int64_t)c->occupied;
+    info->table_slots = c->cap;
+    if (kept == 0) {  // queue exhausted: `puzzle` is the last dequeued state
+        s->ended = true;
+        s->goal_rank = n - 1;
+        info->ended = 1;
+        return SPL_OK;
+    }
+    s->n_front = kept;
+    s->level += 1;
+    CKS(c, save_links(s, st));
+    CK(c, cudaStreamSynchronize(st));
     return SPL_OK;
 }
 
@@ -854,6 +1014,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     if (s->ended) return fail(c, SPL_E_STATE, "spl_solver_step: the search has already ended");
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
+    if (s->realistic) return rsolver_step(s, info, st);
     memset(info, 0, sizeof *info);
     info->level = s->level;
     info->frontier = s->n_front;
@@ -982,6 +1143,89 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     }
     CKS(c, save_links(s, st));
     CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+int32_t spl_rexpand(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, void *out_recs, int64_t cap,
+                    int64_t *n_out, void *stream) {
+    if (!c || !n_out || n < 0 || n > (16ll << 20)) return fail(c, SPL_E_INVALID, "spl_rexpand: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0) return SPL_OK;
+    CKS(c, upload_rconfig(c, cfg, st));
+    int64_t total = 0;
+    CKS(c, r_expand_all(c, reinterpret_cast<const RRec *>(recs), n, 0, false, &total, st));
+    *n_out = total;
+    if (total > cap) return fail(c, SPL_E_CAPACITY, "spl_rexpand: %lld successors, capacity %lld", (long long)total, (long long)cap);
+    if (total) CK(c, cudaMemcpyAsync(out_recs, c->rcand.p, (size_t)total * 96, cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+int32_t spl_rscore(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, double *scores, void *stream) {
+    if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_rscore: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return SPL_OK;
+    CKS(c, upload_rconfig(c, cfg, st));
+    r_score_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const RRec *>(recs), n, c->rcfg.as<RConfigDev>(), c->luts,
+                                              nullptr, scores, c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_rec_host, int64_t beam, int32_t keep_links,
+                           spl_solver **out) {
+    if (!c || !cfg || !root_rec_host || !out) return fail(c, SPL_E_INVALID, "spl_rsolver_create: null argument");
+    if (beam < 1) return fail(c, SPL_E_INVALID, "spl_rsolver_create: beam_width must be >= 1");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = 0;
+    CKS(c, upload_rconfig(c, cfg, st));
+    spl_solver *s = new spl_solver();
+    s->c = c; s->realistic = true; s->rcfg = *cfg; s->use_h = 1; s->beam = beam; s->keep_links = keep_links;
+    s->goal = cfg->target_points;
+    s->front.swap(c->pool_front);
+    s->uniq.swap(c->pool_uniq);
+    int rc = spl_reset_visited(c, st);
+    if (rc == SPL_OK) {
+        cudaError_t e = s->front.ensure(96, 0, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->front.p, root_rec_host, 96, cudaMemcpyHostToDevice, st);
+        c->h2d_bytes += 96;
+        if (e != cudaSuccess) rc = fail(c, SPL_E_CUDA, "root upload: %s", cudaGetErrorString(e));
+    }
+    if (rc == SPL_OK) {  // trail = {self: None}: register the root's identity fingerprint
+        int64_t total = 0;
+        s->n_front = 1;
+        cudaError_t e = c->rkeys.ensure(16, 0, st);
+        if (e == cudaSuccess) e = c->rcand.ensure(96, 0, st);
+        if (e == cudaSuccess) e = c->cand_slot.ensure(4, 0, st);
+        if (e != cudaSuccess) rc = fail(c, SPL_E_NOMEM, "realistic scratch alloc");
+        (void)total;
+    }
+    if (rc == SPL_OK) rc = zero_ctr(c, st);
+    if (rc == SPL_OK) {
+        uint64_t tag;
+        rc = next_epoch(c, tag);
+        if (rc == SPL_OK) {
+            r_root_key_kernel<<<1, 1, 0, st>>>(s->front.as<RRec>(), c->rcfg.as<RConfigDev>(), c->rkeys.as<spl_key>());
+            probe_list_kernel<<<1, TILE, 0, st>>>(c->rkeys.as<spl_key>(), 1, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+            c->launches += 2;
+            c->occupied = 1;
+        }
+    }
+    if (rc == SPL_OK) rc = save_links(s, st);
+    if (rc == SPL_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(c, SPL_E_CUDA, "rsolver create sync failed");
+    if (rc != SPL_OK) { delete s; return rc; }
+    *out = s;
+    return SPL_OK;
+}
+
+int32_t spl_rsolver_frontier(spl_solver *s, const void **recs, int64_t *n) {
+    if (!s || !recs || !n || !s->realistic) return SPL_E_INVALID;
+    *recs = s->front.p;
+    *n = s->n_front;
     return SPL_OK;
 }
 

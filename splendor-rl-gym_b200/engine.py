@@ -171,6 +171,30 @@ class Engine:
                            C.byref(m), self._stream()), self._h)
         return out[:m.value]
 
+    # -------------------------------------------------------------- realistic mode (MultiPlayerState)
+    def rexpand(self, rcfg, recs_np: np.ndarray) -> np.ndarray:
+        """MultiPlayerState.__iter__ for a batch of 96-byte records (host numpy in, host numpy out)."""
+        recs_np = np.ascontiguousarray(recs_np).reshape(-1)
+        n = len(recs_np)
+        src = torch.from_numpy(recs_np.view(np.uint8).reshape(n, 96).copy()).to(self.tdev)
+        cap = max(64, n * 27)
+        out = torch.empty((cap, 96), dtype=torch.uint8, device=self.tdev)
+        m = C.c_int64()
+        check(lib.spl_rexpand(self._h, C.byref(rcfg), src.data_ptr(), n, out.data_ptr(), cap, C.byref(m), self._stream()),
+              self._h)
+        return out[:m.value].cpu().numpy().reshape(-1).view(recs_np.dtype).copy()
+
+    def rscore(self, rcfg, recs_np: np.ndarray) -> np.ndarray:
+        recs_np = np.ascontiguousarray(recs_np).reshape(-1)
+        n = len(recs_np)
+        src = torch.from_numpy(recs_np.view(np.uint8).reshape(n, 96).copy()).to(self.tdev)
+        out = torch.empty(n, dtype=torch.float64, device=self.tdev)
+        check(lib.spl_rscore(self._h, C.byref(rcfg), src.data_ptr(), n, out.data_ptr(), self._stream()), self._h)
+        return out.cpu().numpy()
+
+    def rsolver(self, rcfg, root_rec_np: np.ndarray, beam_width: int, keep_links: bool = True) -> 'RLevelSolver':
+        return RLevelSolver(self, rcfg, root_rec_np, beam_width, keep_links)
+
     # -------------------------------------------------------------- fused solver
     def solver(self, root_key: int, root_aux: int, goal_pts: int, use_heuristic: bool, heuristic: str, beam_width: int,
                tie: str = 'stable', noise: str = 'const', keep_links: bool = True) -> 'LevelSolver':
@@ -235,3 +259,31 @@ class LevelSolver:
             self.close()
         except Exception:
             pass
+
+
+class RLevelSolver(LevelSolver):
+    """spl_rsolver_create + spl_solver_step: one object per MultiPlayerState.solve()."""
+
+    def __init__(self, eng: Engine, rcfg, root_rec_np, beam_width, keep_links):
+        self.eng = eng
+        root = np.ascontiguousarray(root_rec_np).reshape(-1)[:1].copy()
+        h = C.c_void_p()
+        check(lib.spl_rsolver_create(eng._h, C.byref(rcfg), root.ctypes.data, beam_width, int(keep_links), C.byref(h)), eng._h)
+        self._h = h
+        self._dtype = root.dtype
+        self.infos = []
+        self.ended = False
+
+    def frontier_size(self) -> int:
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib.spl_rsolver_frontier(self._h, C.byref(p), C.byref(n)), self.eng._h)
+        return n.value
+
+    def frontier(self) -> np.ndarray:
+        """current queue as host records (96 B each)"""
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib.spl_rsolver_frontier(self._h, C.byref(p), C.byref(n)), self.eng._h)
+        if n.value == 0:
+            return np.zeros(0, self._dtype)
+        t = torch.as_tensor(_DevArray(p.value, (n.value, 96), '|u1'), device=self.eng.tdev)
+        return t.cpu().numpy().reshape(-1).view(self._dtype).copy()

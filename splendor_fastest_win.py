@@ -25,6 +25,10 @@ def cli():
     ap.add_argument('--tie', default='stable', choices=['stable', 'det'], help='score tie-break: arrival order | key')
     ap.add_argument('--noise', default='const', choices=['const', 'hash'], help='deterministic stand-in for randint noise')
     ap.add_argument('--device', type=int, default=None)
+    ap.add_argument('--realistic', action='store_true', help='realistic multi-player mode (gem pool, 12 visible cards)')
+    ap.add_argument('--players', type=int, default=2, help='number of players for realistic mode')
+    ap.add_argument('--shuffle', action='store_true', help='shuffle the card market in realistic mode')
+    ap.add_argument('--seed', type=int, default=None, help='market shuffle seed (the reference passes none)')
     if len(sys.argv) == 1:
         ap.print_help()
         ap.exit()
@@ -38,8 +42,23 @@ def cli():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from splendor_rl_gym_b200 import Color, State
+    from splendor_rl_gym_b200 import Color, GameConfig, MultiPlayerState, State
     rank0 = int(os.environ.get('RANK', '0')) == 0
+    if a.realistic:  # reference CLI lines 95-129
+        cfg = GameConfig(num_players=a.players, target_points=a.goal_pts,
+                         gems_per_color={2: 4, 3: 5, 4: 7}.get(a.players, 4), infinite_resources=False)
+        solution = MultiPlayerState.newgame(config=cfg, shuffle_market=a.shuffle, seed=a.seed).solve(
+            use_heuristic=True, heuristic_name='competitive',
+            beam_width=a.beam_width if a.beam_width != 300_000 else 20_000, verbose=not a.quiet, device=a.device)
+        last = solution[-1]
+        print(f'\n{"=" * 60}')
+        print(f'Game Over! Winner: Player {last.get_winner()}')
+        print('Final Scores:')
+        for p in last.players:
+            print(f'  Player {p.player_id}: {p.pts} points, {len(p.cards)} cards')
+        print(f'Total moves: {last.turn_number}')
+        print(f'{"=" * 60}\n')
+        return
     try:
         solution = State.newgame().solve(goal_pts=a.goal_pts, use_heuristic=a.use_heuristic, heuristic_name=a.heuristic,
                                          beam_width=a.beam_width, verbose=not a.quiet and rank0, tie_policy=a.tie,

@@ -37,7 +37,7 @@ ref_buys.BUYS_PATH = Path('/tmp/splendor_ref_buys.pickle')
 
 import src.solver as ref_solver  # noqa: E402
 from src.gems import get_takes, subtract_with_bonus, take_gems  # noqa: E402
-from src.solver import HEURISTICS, State, deck  # noqa: E402
+from src.solver import HEURISTICS, GameConfig, MultiPlayerState, State, deck  # noqa: E402
 
 M64 = (1 << 64) - 1
 
@@ -259,6 +259,152 @@ def gen_successors_and_scores(levels, per_level=24):
     return succ, scores
 
 
+# ---------------------------------------------------------------- realistic mode (src/solver.py:471-860)
+def rrec_bytes(s) -> bytes:
+    """Canonical identity bytes of a MultiPlayerState: per player (card mask u64+u32, gems u16, saved u16),
+    12 visible slots in slot order (255 = empty), current player."""
+    out = b''
+    for p in s.players:
+        m = 0
+        for c in p.cards:
+            m |= 1 << c
+        g = 0
+        for i, x in enumerate(p.gems):
+            g |= x << (3 * i)
+        out += struct.pack('<QIHH', m & M64, m >> 64, g, p.saved)
+    vis = []
+    for tier in (s.market.tier1_visible, s.market.tier2_visible, s.market.tier3_visible):
+        vis += list(tier) + [255] * (4 - len(tier))
+    out += bytes(vis) + bytes([s.current_player])
+    return out
+
+
+def rlevel_digest(states, links=None):
+    h = hashlib.sha256()
+    for s in states:
+        h.update(rrec_bytes(s))
+    d = dict(n=len(states), sha=h.hexdigest(),
+             sum_saved=sum(p.saved for s in states for p in s.players),
+             sum_pts=sum(p.pts for s in states for p in s.players),
+             sum_pool=sum(sum(s.gem_pool.available) for s in states))
+    if links is not None:
+        d['sum_parent_rank'] = sum(p for p, _ in links)
+        d['sum_ordinal'] = sum(o for _, o in links)
+    return d
+
+
+def rstepper(players, goal, seed, beam, gems_per_color=None):
+    """Mirror of MultiPlayerState.solve's loop (src/solver.py:820-852) recording per-level digests."""
+    gpc = gems_per_color or {2: 4, 3: 5, 4: 7}[players]
+    cfg = GameConfig(num_players=players, target_points=goal, gems_per_color=gpc, infinite_resources=False)
+    root = MultiPlayerState.newgame(cfg, shuffle_market=seed is not None, seed=seed)
+    # the reference's closure heuristic (src/solver.py:778-812) is not reachable from outside solve();
+    # obtain the identical code object by running solve() on a finished game and capturing `sorted`'s key
+    captured = {}
+    import builtins
+    real_sorted = builtins.sorted
+
+    def spy(it, key=None, reverse=False):
+        if key is not None and 'h' not in captured:
+            captured['h'] = key
+        return real_sorted(it, key=key, reverse=reverse)
+    ref_solver.sorted = spy
+    try:
+        tiny = MultiPlayerState.newgame(GameConfig(num_players=players, target_points=0, gems_per_color=gpc,
+                                                   infinite_resources=False))
+        # target 0 -> `any(p.pts >= 0)` ends the game at the first dequeue; sorted() is still called once
+        tiny.solve(beam_width=1, verbose=False)
+    finally:
+        del ref_solver.sorted
+    heuristic = captured['h']
+    queue = [root]
+    trail = {root: None}
+    levels = []
+    turn = 0
+    puzzle = root
+    smin, smax = None, None
+    expanded_total = generated_total = 0
+    t0 = time.time()
+    while queue:
+        next_queue, links = [], []
+        expanded = generated = 0
+        goal_rank = None
+        for rank, puzzle in enumerate(queue):
+            if puzzle.is_game_over():
+                next_queue.clear()
+                links.clear()
+                goal_rank = rank
+                break
+            expanded += 1
+            for ordinal, nxt in enumerate(puzzle):
+                generated += 1
+                if nxt in trail:
+                    continue
+                trail[nxt] = puzzle
+                next_queue.append(nxt)
+                links.append((rank, ordinal))
+        scores = [heuristic(s) for s in next_queue]
+        if scores:
+            smin = min(scores) if smin is None else min(smin, min(scores))
+            smax = max(scores) if smax is None else max(smax, max(scores))
+        sh = hashlib.sha256()
+        for v in scores:
+            sh.update(struct.pack('<d', v))
+        order = sorted(range(len(next_queue)), key=lambda i: scores[i], reverse=True)[:beam]
+        rec = dict(level=turn, frontier=len(queue), expanded=expanded, generated=generated, goal_rank=goal_rank,
+                   unique=rlevel_digest(next_queue, links), scores_sha=sh.hexdigest())
+        queue = [next_queue[i] for i in order]
+        rec['kept'] = rlevel_digest(queue, [links[i] for i in order])
+        levels.append(rec)
+        expanded_total += expanded
+        generated_total += generated
+        turn += 1
+        if turn > 1000:
+            break
+    sol = []
+    while puzzle:
+        sol.append(puzzle)
+        puzzle = trail.get(puzzle)
+    sol.reverse()
+    final = sol[-1]
+    root_market = dict(t1=list(root.market.tier1_visible) + list(root.market.tier1_deck),
+                       t2=list(root.market.tier2_visible) + list(root.market.tier2_deck),
+                       t3=list(root.market.tier3_visible) + list(root.market.tier3_deck))
+    out = dict(players=players, goal=goal, seed=seed, beam=beam, gems_per_color=gpc, plies=len(sol) - 1,
+               winner=final.get_winner(), expanded=expanded_total, generated=generated_total, visited=len(trail),
+               min_score=smin, max_score=smax, market=root_market, levels=levels, wall_s=round(time.time() - t0, 2),
+               final=[dict(pts=p.pts, cards=list(p.cards), saved=p.saved, gems=list(p.gems)) for p in final.players],
+               path_sha=[hashlib.sha256(rrec_bytes(s)).hexdigest()[:16] for s in sol])
+    # cross-check against the reference's own unmodified solve()
+    ref_sol = MultiPlayerState.newgame(cfg, shuffle_market=seed is not None, seed=seed).solve(beam_width=beam, verbose=False)
+    assert [rrec_bytes(s) for s in ref_sol] == [rrec_bytes(s) for s in sol], 'stepper != reference solve()'
+    return out
+
+
+def gen_realistic_successors(n_states=60):
+    import random
+    rng = random.Random(99)
+    out = []
+    for players, seed in ((2, 0), (3, 1), (2, None), (4, 5)):
+        gpc = {2: 4, 3: 5, 4: 7}[players]
+        cfg = GameConfig(num_players=players, target_points=15, gems_per_color=gpc, infinite_resources=False)
+        s = MultiPlayerState.newgame(cfg, shuffle_market=seed is not None, seed=seed)
+        market = dict(t1=list(s.market.tier1_visible) + list(s.market.tier1_deck),
+                      t2=list(s.market.tier2_visible) + list(s.market.tier2_deck),
+                      t3=list(s.market.tier3_visible) + list(s.market.tier3_deck))
+        for _ in range(n_states):
+            kids = list(s)
+            out.append(dict(players=players, gems_per_color=gpc, market=market, state=rrec_bytes(s).hex(),
+                            children=[rrec_bytes(k).hex() for k in kids],
+                            over=[k.is_game_over() for k in kids]))
+            if not kids:
+                break
+            # random walk biased towards buys so that markets refill and decks run down
+            buys = [k for k in kids if sum(len(p.cards) for p in k.players) > sum(len(p.cards) for p in s.players)]
+            s = rng.choice(buys) if buys and rng.random() < 0.7 else rng.choice(kids)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--bfs-depth', type=int, default=8)
@@ -290,6 +436,18 @@ def main():
         for goal in (3, 4):
             lines[str(goal)] = [repr(s) for s in State.newgame().solve(goal_pts=goal, verbose=False)]
         json.dump(lines, open(out / 'bfs_lines.json', 'w'), indent=0)
+
+    if want('realistic'):
+        NOISE.mode = 'const'
+        json.dump(gen_realistic_successors(), open(out / 'realistic_successors.json', 'w'))
+        runs = []
+        for players, goal, seed, beam in [(2, 6, None, 300), (2, 6, None, 3000), (2, 10, 0, 500), (3, 8, 0, 400),
+                                          (2, 15, 0, 2000), (3, 15, 0, 1000), (4, 6, 3, 200), (2, 15, 7, 20)]:
+            r = rstepper(players, goal, seed, beam)
+            runs.append(r)
+            print(f'realistic p={players} goal={goal} seed={seed} beam={beam}: plies={r["plies"]} winner={r["winner"]} '
+                  f'expanded={r["expanded"]} visited={r["visited"]} {r["wall_s"]}s', file=sys.stderr)
+        json.dump(runs, open(out / 'realistic_runs.json', 'w'), indent=0)
 
     if want('beam'):
         runs = []
