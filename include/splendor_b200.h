@@ -156,6 +156,26 @@ int32_t spl_topk(spl_ctx *ctx, const double *scores_dev, const spl_key *keys_dev
 int32_t spl_owner_partition(spl_ctx *ctx, const spl_key *keys_dev, int64_t n, int32_t n_ranks, int64_t *perm_dev,
                             int64_t *counts_host, void *stream);
 
+/* Row-based variants for the sharded driver (rows = 32-byte records {lo, hi, aux, link}):
+ *   spl_expand_rows     successors of front rows, link = (rank_base + parent) << 8 | ordinal
+ *   spl_route_keys      send buffer = candidate keys in (owner, arrival) order + per-owner counts;
+ *                       the permutation stays in the context for spl_compact_winners
+ *   spl_dedup_flags     owner side: first-arrival dedup of a received key list -> one winner byte each
+ *   spl_compact_winners source side: winner bytes (in send order) -> the winning rows in arrival order */
+int32_t spl_expand_rows(spl_ctx *ctx, const void *front_rows_dev, int64_t n, int64_t rank_base, void *out_rows_dev,
+                        int64_t cap, int64_t *n_out_host, void *stream);
+int32_t spl_route_keys(spl_ctx *ctx, const void *cand_rows_dev, int64_t n, int32_t n_ranks, spl_key *send_keys_dev,
+                       int64_t *counts_host, void *stream);
+int32_t spl_dedup_flags(spl_ctx *ctx, const spl_key *keys_dev, int64_t n, uint8_t *flags_dev, void *stream);
+int32_t spl_compact_winners(spl_ctx *ctx, const void *cand_rows_dev, int64_t n, const uint8_t *flags_send_order_dev,
+                            void *out_rows_dev, int64_t *n_out_host, void *stream);
+
+/* HEURISTICS[name] over rows; out[i] = rows[idx[i]] (scatter = 0) or out[idx[i]] = rows[i] (scatter = 1) */
+int32_t spl_score_rows(spl_ctx *ctx, int32_t heuristic, int32_t noise, const void *rows_dev, int64_t n, double *scores_dev,
+                       void *stream);
+int32_t spl_move_rows(spl_ctx *ctx, const void *rows_dev, const int64_t *idx_dev, int64_t n, void *out_rows_dev,
+                      int32_t scatter, void *stream);
+
 /* distributed beam cut: the radix select of spl_topk, one pass at a time, so that the host can
  * all-reduce the 2048-bin histogram (*hist_dev_out, uint32) between spl_dtopk_hist and spl_dtopk_pick.
  * word 0 = score passes, word 1/2 = key.hi / key.lo passes among score ties (det policy). */

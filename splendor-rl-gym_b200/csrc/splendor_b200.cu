@@ -82,6 +82,7 @@ struct spl_ctx {
     cudaEvent_t ev[8]{};
     long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     int64_t dtopk_n = 0;       // distributed top-k: elements staged by spl_dtopk_begin
+    int64_t route_n = -1;      // candidates of the last spl_route_keys (its permutation lives in idx[1])
     bool dtopk_recs = false;
 };
 
@@ -640,6 +641,123 @@ int32_t spl_owner_partition(spl_ctx *c, const spl_key *keys, int64_t n, int32_t 
     CK(c, cudaStreamSynchronize(st));
     c->d2h_bytes += 4 * (n_ranks + 1);
     for (int g = 0; g < n_ranks; ++g) counts_host[g] = (g + 1 < SORT_BINS ? base[g + 1] : (uint32_t)n) - base[g];
+    return SPL_OK;
+}
+
+// ---- row-based variants used by the sharded driver: rows are 32-byte records {lo, hi, aux, link}
+int32_t spl_expand_rows(spl_ctx *c, const void *front_rows, int64_t n, int64_t rank_base, void *out_rows, int64_t cap,
+                        int64_t *n_out, void *stream) {
+    if (!c || !n_out || n < 0 || n > (16ll << 20)) return fail(c, SPL_E_INVALID, "spl_expand_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0) return SPL_OK;
+    CKS(c, zero_ctr(c, st));
+    CKS(c, run_count(c, reinterpret_cast<const Rec *>(front_rows), n, st));
+    const int64_t total = (int64_t)c->h_ctr->total_cands;
+    *n_out = total;
+    if (total > cap) return fail(c, SPL_E_CAPACITY, "spl_expand_rows: %lld successors, capacity %lld", (long long)total, (long long)cap);
+    if (total == 0) return SPL_OK;
+    expand_kernel<MODE_LIST><<<nblk(n), TILE, sizeof(ExpandSmem2), st>>>(
+        reinterpret_cast<const Rec *>(front_rows), n, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(),
+        (uint32_t)total, nullptr, 0, 0, nullptr, reinterpret_cast<Rec *>(out_rows), rank_base, c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+int32_t spl_route_keys(spl_ctx *c, const void *cand_rows, int64_t n, int32_t n_ranks, spl_key *send_keys, int64_t *counts_host,
+                       void *stream) {
+    if (!c || !counts_host || n < 0 || n >= (1ll << 32) || n_ranks < 1 || n_ranks > 255)
+        return fail(c, SPL_E_INVALID, "spl_route_keys: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    for (int g = 0; g < n_ranks; ++g) counts_host[g] = 0;
+    c->route_n = n;
+    if (n == 0) return SPL_OK;
+    for (int b = 0; b < 2; ++b) {
+        CK(c, c->y[b].ensure((size_t)n * 8 + 8, 0, st));
+        CK(c, c->idx[b].ensure((size_t)n * 4 + 4, 0, st));
+    }
+    const Rec *rows = reinterpret_cast<const Rec *>(cand_rows);
+    owner_rows_kernel<<<nblk(n), TILE, 0, st>>>(rows, n, (uint32_t)n_ranks, c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>());
+    ++c->launches;
+    const unsigned nt = nblk(n, SORT_TILE);
+    const size_t msz = (size_t)SORT_BINS * nt;
+    CK(c, c->matrix.ensure(msz * 4, 0, st));
+    CK(c, c->matrix2.ensure(msz * 4, 0, st));
+    CKS(c, sort_pass(c, 0, 0, c->y[0].as<uint64_t>(), n, 0, nt, msz, st));  // stable: digit = owner; perm stays in idx[1]
+    gather_keys_kernel<<<nblk(n), TILE, 0, st>>>(rows, c->idx[1].as<uint32_t>(), n, send_keys);
+    ++c->launches;
+    std::vector<uint32_t> base(n_ranks + 1);
+    for (int g = 0; g <= n_ranks; ++g)
+        CK(c, cudaMemcpyAsync(&base[g], c->matrix2.as<uint32_t>() + (size_t)g * nt, 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += 4 * (n_ranks + 1);
+    for (int g = 0; g < n_ranks; ++g) counts_host[g] = base[g + 1] - base[g];
+    return SPL_OK;
+}
+
+int32_t spl_dedup_flags(spl_ctx *c, const spl_key *keys, int64_t n, uint8_t *flags, void *stream) {
+    if (!c || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dedup_flags: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return SPL_OK;
+    CKS(c, zero_ctr(c, st));
+    CKS(c, ensure_table(c, (uint64_t)n, st));
+    uint64_t tag;
+    CKS(c, next_epoch(c, tag));
+    CK(c, c->cand_slot.ensure((size_t)n * 4, 0, st));
+    probe_list_kernel<<<nblk(n), TILE, 0, st>>>(keys, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+    win_flags_kernel<<<nblk(n), TILE, 0, st>>>(c->cand_slot.as<uint32_t>(), c->table, n, flags);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    if (c->h_ctr->error) return fail(c, SPL_E_TABLE_FULL, "spl_dedup_flags: probe overflow (table full)");
+    c->occupied += c->h_ctr->n_new;
+    return SPL_OK;
+}
+
+int32_t spl_compact_winners(spl_ctx *c, const void *cand_rows, int64_t n, const uint8_t *flags_partitioned, void *out_rows,
+                            int64_t *n_out, void *stream) {
+    if (!c || !n_out || n < 0 || n != c->route_n) return fail(c, SPL_E_STATE, "spl_compact_winners: must follow spl_route_keys on the same candidates");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0) return SPL_OK;
+    CK(c, c->rtmp.ensure((size_t)n + 8, 0, st));
+    scatter_flags_kernel<<<nblk(n), TILE, 0, st>>>(flags_partitioned, c->idx[1].as<uint32_t>(), n, c->rtmp.as<uint8_t>());
+    const unsigned nt = nblk(n, TILE * 8);
+    CKS(c, zero_ctr(c, st));
+    CKS(c, prep_status(c, 0, nt, st));
+    compact_rows_kernel<<<nt, TILE, 0, st>>>(reinterpret_cast<const Rec *>(cand_rows), c->rtmp.as<uint8_t>(), n,
+                                              reinterpret_cast<Rec *>(out_rows), c->status[0].as<uint64_t>(), c->d_ctr, 0);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    *n_out = (int64_t)c->h_ctr->n_emitted;
+    return SPL_OK;
+}
+
+int32_t spl_score_rows(spl_ctx *c, int32_t heuristic, int32_t noise, const void *rows, int64_t n, double *scores, void *stream) {
+    if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_score_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return SPL_OK;
+    score_rows_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const Rec *>(rows), n, heuristic, noise, c->luts, scores);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+int32_t spl_move_rows(spl_ctx *c, const void *rows, const int64_t *idx, int64_t n, void *out_rows, int32_t scatter, void *stream) {
+    if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_move_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return SPL_OK;
+    move_rows_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const Rec *>(rows), idx, n, reinterpret_cast<Rec *>(out_rows), scatter);
+    ++c->launches;
+    CK(c, cudaGetLastError());
     return SPL_OK;
 }
 

@@ -31,8 +31,23 @@ import torch.distributed as dist
 from ._lib import check, lib
 from .engine import NOISE_IDS, TIE_IDS, Engine, _DevArray, heuristic_id
 
+import os
+import time
+
 SEL_BITS = 11
 I64_MAX = (1 << 63) - 1
+TIMING = bool(os.environ.get('SPL_TIMING'))
+PHASES = {}
+
+
+def _tick(name, t0):
+    """phase timer (SPL_TIMING=1): synchronises the device, so only for diagnosis"""
+    if not TIMING:
+        return 0.0
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    PHASES[name] = PHASES.get(name, 0.0) + (t1 - t0)
+    return t1
 
 
 def _bitlen(x: int) -> int:
@@ -100,9 +115,43 @@ class CudaBackend:
         hit = torch.nonzero(pts >= goal)
         return int(hit[0]) if hit.numel() else -1
 
-    def expand(self, front):
-        ck, ca, cl = self.eng.expand(front[:, :2].contiguous(), front[:, 2].contiguous())
-        return torch.cat([ck, ca[:, None], cl[:, None]], dim=1)
+    def expand_rows(self, front, rank_base):
+        """successors of the local queue slice as rows [m, 4]; link = (rank_base + parent) << 8 | ordinal"""
+        n = front.shape[0]
+        cap = max(64, n * 36)
+        while True:
+            out = torch.empty((cap, 4), dtype=torch.int64, device=self.device)
+            m = C.c_int64()
+            rc = lib.spl_expand_rows(self.eng._h, front.data_ptr(), n, rank_base, out.data_ptr(), cap, C.byref(m), self.eng._stream())
+            if rc == -6:
+                cap = m.value
+                continue
+            check(rc, self.eng._h)
+            return out[:m.value]
+
+    def route_keys(self, cand, world):
+        """keys of the candidates grouped by owner rank (arrival order inside a group) + per-owner counts"""
+        m = cand.shape[0]
+        send = torch.empty((max(m, 1), 2), dtype=torch.int64, device=self.device)
+        counts = (C.c_int64 * world)()
+        check(lib.spl_route_keys(self.eng._h, cand.data_ptr(), m, world, send.data_ptr(), counts, self.eng._stream()), self.eng._h)
+        return send[:m], np.array(counts[:], dtype=np.int64)
+
+    def dedup_flags(self, keys):
+        """owner side: one winner byte per received key (first arrival of a never-seen key)"""
+        n = keys.shape[0]
+        flags = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
+        check(lib.spl_dedup_flags(self.eng._h, keys.data_ptr(), n, flags.data_ptr(), self.eng._stream()), self.eng._h)
+        return flags[:n]
+
+    def compact_winners(self, cand, flags_send_order):
+        """source side: the winning rows in arrival order"""
+        m = cand.shape[0]
+        out = torch.empty((max(m, 1), 4), dtype=torch.int64, device=self.device)
+        k = C.c_int64()
+        check(lib.spl_compact_winners(self.eng._h, cand.data_ptr(), m, flags_send_order.data_ptr(), out.data_ptr(), C.byref(k),
+                                      self.eng._stream()), self.eng._h)
+        return out[:k.value]
 
     def owner_partition(self, keys, world):
         n = keys.shape[0]
@@ -118,7 +167,18 @@ class CudaBackend:
         return src
 
     def score(self, heuristic, noise, rows):
-        return self.eng.score(heuristic, rows[:, :2].contiguous(), rows[:, 2].contiguous(), noise)
+        n = rows.shape[0]
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        check(lib.spl_score_rows(self.eng._h, heuristic_id(heuristic), NOISE_IDS[noise], rows.data_ptr(), n, out.data_ptr(),
+                                 self.eng._stream()), self.eng._h)
+        return out
+
+    def move_rows(self, rows, idx, n_out, scatter):
+        """gather (out[i] = rows[idx[i]]) or scatter (out[idx[i]] = rows[i]) of 32-byte rows"""
+        out = torch.empty((max(n_out, 1), 4), dtype=torch.int64, device=self.device)
+        check(lib.spl_move_rows(self.eng._h, rows.data_ptr(), idx.data_ptr(), idx.shape[0], out.data_ptr(), int(scatter),
+                                self.eng._stream()), self.eng._h)
+        return out[:n_out]
 
     # ---- distributed top-k passes
     def dtopk_begin(self, scores, keys):
@@ -182,9 +242,9 @@ class ShardedSolver:
         backend.reset_visited()  # trail = {}
         # the root is held by rank 0; its key is registered in the visited set of its owner
         self.front = root if comm.rank == 0 else root[:0]
-        _, counts = backend.owner_partition(root[:, :2].contiguous(), comm.world)
+        send, counts = backend.route_keys(root, comm.world)
         if counts[comm.rank]:
-            backend.dedup(root[:, :2].contiguous())
+            backend.dedup_flags(send)
         self.level = 0
         self.ended = False
         self.goal_rank = -1
@@ -217,32 +277,32 @@ class ShardedSolver:
             info.update(ended=1, goal_rank=self.goal_rank)
             self.infos.append(info)
             return info
+        t0 = _tick('goal', time.perf_counter() if TIMING else 0.0)
         # 2. expand
-        cand = b.expand(front) if n_local else torch.empty((0, 4), dtype=torch.int64, device=dev)
+        cand = b.expand_rows(front, base) if n_local else torch.empty((0, 4), dtype=torch.int64, device=dev)
         m = cand.shape[0]
-        if m:
-            cand[:, 3] += base << 8  # link = global parent rank << 8 | ordinal
+        t0 = _tick('expand', t0)
         # 3. route keys to their owners
-        perm, counts = b.owner_partition(cand[:, :2].contiguous(), G) if m else (torch.empty(0, dtype=torch.int64, device=dev), np.zeros(G, np.int64))
+        send_keys, counts = b.route_keys(cand, G)
         all_counts = comm.gather_ints(*counts.tolist())  # [src, dst]
         recv_counts = all_counts[:, me]
-        send_keys = cand[perm][:, :2].contiguous() if m else cand[:, :2]
+        t0 = _tick('partition', t0)
         recv_keys = comm.all_to_all_rows(send_keys, counts, recv_counts)
+        t0 = _tick('a2a_keys', t0)
         # 4. first-arrival dedup at the owner
-        flags_recv = torch.zeros(recv_keys.shape[0], dtype=torch.uint8, device=dev)
-        if recv_keys.shape[0]:
-            flags_recv[b.dedup(recv_keys)] = 1
+        flags_recv = b.dedup_flags(recv_keys)
+        t0 = _tick('dedup', t0)
         # 5. winner bytes back to the source; compaction in arrival order
         flags_back = comm.all_to_all_rows(flags_recv, recv_counts, counts)
-        flags = torch.empty(m, dtype=torch.uint8, device=dev)
-        flags[perm] = flags_back
-        winners = cand[torch.nonzero(flags).flatten()]
+        winners = b.compact_winners(cand, flags_back)
+        t0 = _tick('flags_compact', t0)
         u_local = winners.shape[0]
         tot = comm.gather_ints(m, u_local)
         info.update(expanded=n_total, generated=int(tot[:, 0].sum()), unique=int(tot[:, 1].sum()))
         u_total = info['unique']
         if self.use_h and u_total:
             winners = self._beam_cut(winners, tot[:, 1], u_total)
+        t0 = _tick('beam_cut', t0)
         self.front = winners
         kv = self.comm.gather_ints(winners.shape[0], b.visited_count())
         kept_total = int(kv[:, 0].sum())
@@ -327,18 +387,18 @@ class ShardedSolver:
                     continue
                 # ties across ranks (stable policy only) go to the lower rank: it arrived first
                 b.count_less(words, g < me, (y, kl, kh), (ys[g], kls[g], khs[g]), grank, True)
-        rows = torch.cat([winners[idx], grank[:, None]], dim=1)
+        kept_rows = b.move_rows(winners, idx, k_local, False)  # local survivors in local rank order
+        if G == 1:
+            return kept_rows  # grank == arange: already the new queue
         # block distribution of the new queue by global rank
         chunk = -(-k_total // G)
         dest = grank // chunk if k_local else grank
         send_counts = torch.bincount(dest, minlength=G).cpu().numpy() if k_local else np.zeros(G, np.int64)
         all_counts = comm.gather_ints(*send_counts.tolist())
         recv_counts = all_counts[:, me]
-        got = comm.all_to_all_rows(rows, send_counts, recv_counts)
-        out = torch.empty((got.shape[0], 4), dtype=torch.int64, device=dev)
-        if got.shape[0]:
-            out[got[:, 4] - me * chunk] = got[:, :4]
-        return out
+        got = comm.all_to_all_rows(kept_rows, send_counts, recv_counts)
+        got_rank = comm.all_to_all_rows(grank, send_counts, recv_counts)
+        return b.move_rows(got, got_rank - me * chunk, got.shape[0], True)
 
     # ------------------------------------------------------------------ driver helpers
     def run(self, max_levels=None):

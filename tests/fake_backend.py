@@ -51,6 +51,37 @@ class FakeBackend:
         a = np.array(out, dtype=np.uint64).reshape(-1, 4)
         return torch.from_numpy(a.view(np.int64).copy())
 
+    def expand_rows(self, front, rank_base):
+        out = self.expand(front)
+        if out.shape[0]:
+            out[:, 3] += rank_base << 8
+        return out
+
+    def route_keys(self, cand, world):
+        perm, counts = self.owner_partition(cand[:, :2], world)
+        self._perm = perm
+        return cand[perm][:, :2].contiguous(), counts
+
+    def dedup_flags(self, keys):
+        flags = torch.zeros(keys.shape[0], dtype=torch.uint8)
+        src = self.dedup(keys)
+        if len(src):
+            flags[src] = 1
+        return flags
+
+    def compact_winners(self, cand, flags_send_order):
+        flags = torch.zeros(cand.shape[0], dtype=torch.uint8)
+        flags[self._perm] = flags_send_order
+        return cand[torch.nonzero(flags).flatten()]
+
+    def move_rows(self, rows, idx, n_out, scatter):
+        out = torch.empty((n_out, 4), dtype=torch.int64)
+        if scatter:
+            out[idx] = rows
+        else:
+            out = rows[idx]
+        return out
+
     def owner_partition(self, keys, world):
         k = _u(keys)
         own = ((k[:, 0] * np.uint64(0x9E3779B97F4A7C15) + k[:, 1]) >> np.uint64(40)) % np.uint64(world) if len(k) else np.zeros(0, np.uint64)

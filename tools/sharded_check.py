@@ -63,5 +63,9 @@ for rep in range(a.reps):
         exp = sum(i['expanded'] for i in sol.infos)
         print(f'world={comm.world} rep={rep} levels={len(sol.infos)} expanded={exp} wall={dt:.3f}s -> {exp / dt / 1e6:.2f} M expanded/s'
               + (' PARITY OK vs oracle' if check and rep == 0 else ''), flush=True)
+from splendor_rl_gym_b200 import sharded as _sh
+if _sh.TIMING and comm.rank == 0:
+    tot = sum(_sh.PHASES.values())
+    print('phases (s, all reps): ' + ', '.join(f'{k}={v:.3f} ({100 * v / tot:.0f}%)' for k, v in _sh.PHASES.items()))
 if comm.on:
     dist.destroy_process_group()
