@@ -147,7 +147,9 @@ def run_b200(a):
             a.beam = min(30_000_000, SHARDED_BEAM_PER_GPU * world)
     # visited table sized for the whole search up front (about 85 visited states per beam slot at
     # goal 15) so the timed region never rehashes; capped by the 32-bit slot index.
-    slots = int(min(0xFFFFFFF0, max(1 << 22, a.beam * 72 / 0.62 / world)))
+    # Capped at 2.2 G slots (70 GB): beyond ~75 GB the random probes fall out of the GPU's TLB reach and
+    # every probe pays a page walk (measured: 3.48 G slots -> 626 ms per solve, 2.2 G slots -> 394 ms).
+    slots = int(min(2_200_000_000, max(1 << 22, a.beam * 72 / 0.62 / world)))
     eng = S.Engine(local, table_slots=slots, max_table_bytes=int(150e9))
     k, aux = S.State.newgame().record()
     comm = Comm(eng.tdev)

@@ -34,7 +34,10 @@ eng = S.Engine(local, table_slots=max(1 << 22, int(a.beam * 110 / 0.6 / max(1, i
 comm = Comm(eng.tdev)
 use_h = a.bfs == 0
 check = comm.rank == 0 and not a.no_oracle
+from splendor_rl_gym_b200 import sharded as _sh0
 for rep in range(a.reps):
+    if rep == a.reps - 1 and rep > 0:
+        _sh0.PHASES.clear()  # phase times of the last (warm) repetition only
     if check and rep == 0:
         import oracle
         orc = oracle.Solver(255 if a.bfs else a.goal, use_heuristic=use_h, heuristic_name=a.heuristic, beam_width=a.beam,
@@ -66,6 +69,6 @@ for rep in range(a.reps):
 from splendor_rl_gym_b200 import sharded as _sh
 if _sh.TIMING and comm.rank == 0:
     tot = sum(_sh.PHASES.values())
-    print('phases (s, all reps): ' + ', '.join(f'{k}={v:.3f} ({100 * v / tot:.0f}%)' for k, v in _sh.PHASES.items()))
+    print('phases (s, last rep): ' + ', '.join(f'{k}={v:.3f} ({100 * v / tot:.0f}%)' for k, v in _sh.PHASES.items()))
 if comm.on:
     dist.destroy_process_group()
