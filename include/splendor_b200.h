@@ -66,7 +66,12 @@ enum {
 enum { SPL_H_SIMPLE = 0, SPL_H_BALANCED = 1, SPL_H_AGGRESSIVE = 2, SPL_H_EFFICIENCY = 3 };
 
 /* noise policy for the `randint(1,100)*0.01` term (src/solver.py:215,247,260,284), SURVEY.md 8a-N */
-enum { SPL_NOISE_CONST = 0 /* randint -> 50 */, SPL_NOISE_HASH = 1 /* 1 + splitmix64(lo^hi) % 100 */ };
+enum {
+    SPL_NOISE_CONST = 0,    /* randint -> 50 */
+    SPL_NOISE_HASH = 1,     /* randint -> 1 + splitmix64(lo^hi) % 100 */
+    SPL_NOISE_EXTERNAL = 2  /* the i-th state scored in a level (arrival order) gets the i-th randint(1, 100) of a
+                             * host-side stream, e.g. the reference's own seeded Mersenne Twister: see spl_solver_cut */
+};
 
 /* tie-break policy of the beam cut `sorted(next_queue, key=h, reverse=True)[:beam]` (:452-456) */
 enum { SPL_TIE_STABLE = 0 /* arrival order, as Python's stable sort */, SPL_TIE_KEY = 1 /* key descending */ };
@@ -206,6 +211,10 @@ int32_t spl_solver_create(spl_ctx *ctx, const spl_key *root_key_host, uint64_t r
 int32_t spl_solver_destroy(spl_solver *s);
 /* one `while queue` iteration; returns SPL_OK and fills *info_host; info->ended tells the caller to stop */
 int32_t spl_solver_step(spl_solver *s, spl_level_info *info_host, void *stream);
+/* SPL_NOISE_EXTERNAL only: spl_solver_step stops after expand + dedup with info->kept == -1 and
+ * info->unique == the number of states to score; the host then supplies that many draws (uint8, each the
+ * value randint(1, 100) returned, in arrival order) and this call scores, cuts and sorts the level. */
+int32_t spl_solver_cut(spl_solver *s, const uint8_t *draws_dev, int64_t n_draws, spl_level_info *info_host, void *stream);
 /* device views of the current queue (valid until the next step) */
 int32_t spl_solver_frontier(spl_solver *s, const spl_key **keys_dev, const uint64_t **aux_dev,
                             const uint64_t **link_dev, int64_t *n_host);

@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(TILE) probe_list_kernel(const spl_key *__restr
 // (libm pow, as CPython's float_pow), every * and + is a separately rounded IEEE double
 // (__dmul_rn/__dadd_rn cannot be contracted into FMA).
 __device__ __forceinline__ double score_state(int h, int noise_mode, uint64_t lo, uint64_t hi, uint64_t aux,
-                                              const ScoreLuts &L) {
+                                              const ScoreLuts &L, int r_ext = 50) {
     const uint32_t pts = (uint32_t)((aux >> 16) & 0xff), saved = (uint32_t)(aux & 0xffff);
     const uint32_t g = (uint32_t)(lo & GEM_MASK);
     uint32_t sum_g = 0, sum_b = 0, nnz = 0;
@@ -470,7 +470,8 @@ __device__ __forceinline__ double score_state(int h, int noise_mode, uint64_t lo
         sum_b += b;
         nnz += b > 0;
     }
-    const int r = noise_mode == 1 ? 1 + (int)(mix64(lo, hi) % 100ull) : 50;
+    // noise modes: 0 const (randint -> 50), 1 hash, 2 external (the i-th randint(1, 100) of a host-side stream)
+    const int r = noise_mode == 1 ? 1 + (int)(mix64(lo, hi) % 100ull) : noise_mode == 2 ? r_ext : 50;
     const double noise = __dmul_rn((double)r, 0.01);
     const int hh = (h >= 0 && h <= 3) ? h : 0;
     const double P = __ldg(L.pts + hh * 256 + pts);
@@ -1109,6 +1110,31 @@ __global__ void __launch_bounds__(TILE) compact_rows_kernel(const Rec *__restric
         ld_rec(rows + b0 + q, r);
         st_rec(out + pos, r);
         ++pos;
+    }
+}
+
+// scores of rows[i] with the i-th externally drawn randint (noise policy `mt`): order-preserving keys + range
+__global__ void __launch_bounds__(TILE) score_ext_kernel(const Rec *__restrict__ rows, const uint8_t *__restrict__ draws,
+                                                         int64_t n, int h, ScoreLuts L, uint64_t *__restrict__ sk,
+                                                         Counters *ctr) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    uint64_t kmin = ~0ull, kmax = 0;
+    if (i < n) {
+        Rec r;
+        ld_rec(rows + i, r);
+        const double sc = score_state(h, 2, r.lo, r.hi & HI_KEY_MASK, r.aux, L, draws[i]);
+        const uint64_t k = flip_f64((uint64_t)__double_as_longlong(sc));
+        sk[i] = k;
+        kmin = kmax = k;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+    }
+    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+        atomicMin(&ctr->sk_min, (unsigned long long)kmin);
+        atomicMax(&ctr->sk_max, (unsigned long long)kmax);
     }
 }
 

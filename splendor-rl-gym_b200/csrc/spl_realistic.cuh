@@ -162,7 +162,7 @@ __device__ __forceinline__ void r_fingerprint(const RConfigDev &C, const RRec &s
 }
 
 // multi_competitive_heuristic (src/solver.py:778-812), bit-exact: LUT pows, separately rounded ops
-__device__ __forceinline__ double r_score(const RConfigDev &C, const RRec &s, const ScoreLuts &L) {
+__device__ __forceinline__ double r_score(const RConfigDev &C, const RRec &s, const ScoreLuts &L, int r_ext = 50) {
     const int prev = (s.cur + C.P - 1) % C.P;
     const RPlayer &me = s.p[prev], &opp = s.p[s.cur];
     int bm[NCOL], bo[NCOL], pm, po, rm = 0, ro = 0, nnz = 0, am = 0, ao = 0;
@@ -187,7 +187,7 @@ __device__ __forceinline__ double r_score(const RConfigDev &C, const RRec &s, co
     acc = __dadd_rn(acc, rm > ro ? __dmul_rn(__ldg(L.small + 3 * 512 + (rm - ro)), 20.0) : 0.0);
     acc = __dadd_rn(acc, (double)((am - ao) * 5));
     acc = __dadd_rn(acc, __dmul_rn(__ldg(L.small + 3 * 512 + nnz), 3.0));
-    int r = 50;
+    int r = C.noise == 2 ? r_ext : 50;
     if (C.noise == 1) {
         uint64_t h = 0;
         for (int q = 0; q < C.P; ++q)
@@ -288,13 +288,14 @@ __global__ void __launch_bounds__(TILE) r_gather_kernel(const RRec *__restrict__
 
 __global__ void __launch_bounds__(TILE) r_score_kernel(const RRec *__restrict__ recs, int64_t n,
                                                        const RConfigDev *__restrict__ cfg, ScoreLuts L,
-                                                       uint64_t *__restrict__ sk, double *__restrict__ raw, Counters *ctr) {
+                                                       uint64_t *__restrict__ sk, double *__restrict__ raw, Counters *ctr,
+                                                       const uint8_t *__restrict__ draws = nullptr) {
     const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
     uint64_t kmin = ~0ull, kmax = 0;
     if (i < n) {
         RRec s;
         ld_rrec(recs + i, s);
-        const double sc = r_score(*cfg, s, L);
+        const double sc = r_score(*cfg, s, L, draws ? draws[i] : 50);
         if (raw) raw[i] = sc;
         if (sk) {
             const uint64_t k = flip_f64((uint64_t)__double_as_longlong(sc));

@@ -888,6 +888,10 @@ struct spl_solver {
     int goal = 15, use_h = 0, heuristic = 0, tie = 0, noise = 0, keep_links = 1;
     bool realistic = false;
     spl_rconfig rcfg{};
+    // external-noise mode: the level is split in two calls (expand+dedup | score+cut)
+    bool pending = false;
+    int64_t pend_n = 0, pend_uniq = 0;
+    spl_level_info pend_info{};
     int64_t beam = 300000;
     DevBuf front, uniq;
     int64_t n_front = 0;
@@ -918,6 +922,49 @@ static int save_links(spl_solver *s, cudaStream_t st) {
         unpack_rec_kernel<<<nblk(s->n_front), TILE, 0, st>>>(s->front.as<Rec>(), s->n_front, nullptr, nullptr, b->as<uint64_t>());
     ++c->launches;
     CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+// ------------------------------------------------------------------ second half of a speedrun level
+// beam cut (src/solver.py:452-456) or plain BFS hand-over, then bookkeeping
+static int speedrun_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t n_uniq, uint64_t sk_min, uint64_t sk_max,
+                        cudaStream_t st) {
+    spl_ctx *c = s->c;
+    int64_t kept = n_uniq;
+    if (s->use_h && n_uniq > 0) {
+        int which = 0;
+        CK(c, cudaEventRecord(c->ev[4], st));
+        CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), s->uniq.as<Rec>(), n_uniq, s->beam, sk_min, sk_max, s->tie == SPL_TIE_KEY, &which, &kept, st));
+        CK(c, cudaEventRecord(c->ev[5], st));
+        CK(c, s->front.ensure((size_t)kept * 32, 0, st));
+        gather_rec_kernel<<<nblk(kept), TILE, 0, st>>>(s->uniq.as<Rec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<Rec>());
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev[6], st));
+        CK(c, cudaStreamSynchronize(st));
+        float t;
+        cudaEventElapsedTime(&t, c->ev[4], c->ev[5]);
+        info->ms_select = t;  // select + cut + sort
+        cudaEventElapsedTime(&t, c->ev[5], c->ev[6]);
+        info->ms_sort = t;    // gather into rank order
+    } else {
+        s->front.swap(s->uniq);
+    }
+    s->n_front = kept;
+    s->level += 1;
+    info->kept = kept;
+    info->visited = (int64_t)c->occupied;
+    info->table_slots = c->cap;
+    if (kept == 0) {  // frontier exhausted: `puzzle` is the last dequeued state (src/solver.py:438,459)
+        s->ended = true;
+        s->goal_rank = n - 1;
+        s->n_front = n;
+        s->level -= 1;
+        info->ended = 1;
+        return SPL_OK;
+    }
+    CKS(c, save_links(s, st));
+    CK(c, cudaStreamSynchronize(st));
     return SPL_OK;
 }
 
@@ -971,6 +1018,8 @@ static int r_expand_all(spl_ctx *c, const RRec *front, int64_t n, int64_t rank_b
     CK(c, cudaGetLastError());
     return SPL_OK;
 }
+
+static int realistic_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t n_new, const uint8_t *draws, cudaStream_t st);
 
 static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
     spl_ctx *c = s->c;
@@ -1032,12 +1081,31 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
         r_gather_kernel<int64_t><<<nblk(n_new), TILE, 0, st>>>(c->rcand.as<RRec>(), c->ridx64.as<int64_t>(), n_new, s->uniq.as<RRec>());
         c->launches += 2;
         CK(c, cudaGetLastError());
-        CK(c, cudaEventRecord(c->ev[2], st));
+        if (s->rcfg.noise == SPL_NOISE_EXTERNAL) {  // wait for the host's randint draws
+            CK(c, cudaStreamSynchronize(st));
+            s->pending = true;
+            s->pend_n = n;
+            s->pend_uniq = n_new;
+            info->kept = -1;
+            info->visited = (int64_t)c->occupied;
+            info->table_slots = c->cap;
+            s->pend_info = *info;
+            return SPL_OK;
+        }
+    }
+    return realistic_cut(s, info, n, n_new, nullptr, st);
+}
+
+static int realistic_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t n_new, const uint8_t *draws, cudaStream_t st) {
+    spl_ctx *c = s->c;
+    int64_t kept = 0;
+    if (n_new) {
         // score + beam cut, ties by arrival order (:846)
+        CK(c, cudaEventRecord(c->ev[2], st));
         CKS(c, zero_ctr(c, st));
         CK(c, c->sk.ensure((size_t)n_new * 8, 0, st));
         r_score_kernel<<<nblk(n_new), TILE, 0, st>>>(s->uniq.as<RRec>(), n_new, c->rcfg.as<RConfigDev>(), c->luts,
-                                                      c->sk.as<uint64_t>(), nullptr, c->d_ctr);
+                                                      c->sk.as<uint64_t>(), nullptr, c->d_ctr, draws);
         ++c->launches;
         CK(c, cudaGetLastError());
         CKS(c, read_ctr(c, st));
@@ -1051,10 +1119,6 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
         CK(c, cudaEventRecord(c->ev[3], st));
         CK(c, cudaStreamSynchronize(st));
         float t;
-        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
-        info->ms_expand = t;
-        cudaEventElapsedTime(&t, c->ev[1], c->ev[2]);
-        info->ms_resolve = t;
         cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
         info->ms_select = t;
     }
@@ -1082,6 +1146,7 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
     if (!c || !root_key || !out) return fail(c, SPL_E_INVALID, "spl_solver_create: null argument");
     if (use_h && beam < 1) return fail(c, SPL_E_INVALID, "spl_solver_create: beam_width must be >= 1");
     if (use_h && tie != SPL_TIE_STABLE && tie != SPL_TIE_KEY) return fail(c, SPL_E_INVALID, "spl_solver_create: unknown tie policy %d", tie);
+    if (noise < 0 || noise > SPL_NOISE_EXTERNAL) return fail(c, SPL_E_INVALID, "spl_solver_create: unknown noise policy %d", noise);
     CK(c, cudaSetDevice(c->device));
     cudaStream_t st = 0;
     spl_solver *s = new spl_solver();
@@ -1130,6 +1195,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     if (!s || !info) return SPL_E_INVALID;
     spl_ctx *c = s->c;
     if (s->ended) return fail(c, SPL_E_STATE, "spl_solver_step: the search has already ended");
+    if (s->pending) return fail(c, SPL_E_STATE, "spl_solver_step: the previous level still waits for spl_solver_cut");
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
     if (s->realistic) return rsolver_step(s, info, st);
@@ -1192,7 +1258,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
             CKS(c, prep_status(c, 0, nt, st));
             CKS(c, reset_ticket(c, 0, st));
             CK(c, cudaEventRecord(c->ev[2], st));
-            if (s->use_h)
+            if (s->use_h && s->noise != SPL_NOISE_EXTERNAL)
                 resolve_kernel<SRC_PARENT, true><<<nt, TILE, sizeof(ResolveSmem), st>>>(
                     front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
                     c->table, c->cand_slot.as<uint32_t>(), nullptr, nullptr, p0, (uint64_t)n_uniq, s->uniq.as<Rec>(),
@@ -1209,7 +1275,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
             if ((int64_t)c->h_ctr->n_emitted != n_uniq + n_new)
                 return fail(c, SPL_E_CUDA, "internal: emitted %llu winners, expected %lld", (unsigned long long)c->h_ctr->n_emitted,
                             (long long)(n_uniq + n_new));
-            if (s->use_h) { sk_min = std::min<uint64_t>(sk_min, c->h_ctr->sk_min); sk_max = std::max<uint64_t>(sk_max, c->h_ctr->sk_max); }
+            if (s->use_h && s->noise != SPL_NOISE_EXTERNAL) { sk_min = std::min<uint64_t>(sk_min, c->h_ctr->sk_min); sk_max = std::max<uint64_t>(sk_max, c->h_ctr->sk_max); }
             n_uniq += n_new;
             float t;
             cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
@@ -1224,44 +1290,18 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     info->expanded = n;
     info->generated = generated;
     info->unique = n_uniq;
-    // ---- beam cut (src/solver.py:452-456) or plain BFS hand-over
-    int64_t kept = n_uniq;
-    if (s->use_h && n_uniq > 0) {
-        int which = 0;
-        CK(c, cudaEventRecord(c->ev[4], st));
-        CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), s->uniq.as<Rec>(), n_uniq, s->beam, sk_min, sk_max, s->tie == SPL_TIE_KEY, &which, &kept, st));
-        CK(c, cudaEventRecord(c->ev[5], st));
-        CK(c, s->front.ensure((size_t)kept * 32, 0, st));
-        gather_rec_kernel<<<nblk(kept), TILE, 0, st>>>(s->uniq.as<Rec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<Rec>());
-        ++c->launches;
-        CK(c, cudaGetLastError());
-        CK(c, cudaEventRecord(c->ev[6], st));
-        CK(c, cudaStreamSynchronize(st));
-        float t;
-        cudaEventElapsedTime(&t, c->ev[4], c->ev[5]);
-        ms[3] = t;  // select + cut + sort (split below by run_cut_sort's own event)
-        cudaEventElapsedTime(&t, c->ev[5], c->ev[6]);
-        ms[4] = t;
-    } else {
-        s->front.swap(s->uniq);
-    }
-    s->n_front = kept;
-    s->level += 1;
-    info->kept = kept;
-    info->visited = (int64_t)c->occupied;
-    info->table_slots = c->cap;
-    info->ms_count = ms[0]; info->ms_expand = ms[1]; info->ms_resolve = ms[2]; info->ms_select = ms[3]; info->ms_sort = ms[4];
-    if (kept == 0) {  // frontier exhausted: `puzzle` is the last dequeued state (src/solver.py:438,459)
-        s->ended = true;
-        s->goal_rank = n - 1;
-        s->n_front = n;
-        s->level -= 1;
-        info->ended = 1;
+    info->ms_count = ms[0]; info->ms_expand = ms[1]; info->ms_resolve = ms[2];
+    if (s->use_h && s->noise == SPL_NOISE_EXTERNAL && n_uniq > 0) {  // wait for the host's randint draws
+        s->pending = true;
+        s->pend_n = n;
+        s->pend_uniq = n_uniq;
+        info->kept = -1;
+        info->visited = (int64_t)c->occupied;
+        info->table_slots = c->cap;
+        s->pend_info = *info;
         return SPL_OK;
     }
-    CKS(c, save_links(s, st));
-    CK(c, cudaStreamSynchronize(st));
-    return SPL_OK;
+    return speedrun_cut(s, info, n, n_uniq, sk_min, sk_max, st);
 }
 
 int32_t spl_rexpand(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, void *out_recs, int64_t cap,
@@ -1345,6 +1385,26 @@ int32_t spl_rsolver_frontier(spl_solver *s, const void **recs, int64_t *n) {
     *recs = s->front.p;
     *n = s->n_front;
     return SPL_OK;
+}
+
+int32_t spl_solver_cut(spl_solver *s, const uint8_t *draws, int64_t n_draws, spl_level_info *info, void *stream) {
+    if (!s || !info) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    if (!s->pending) return fail(c, SPL_E_STATE, "spl_solver_cut: no level is waiting for draws");
+    if (!draws || n_draws != s->pend_uniq) return fail(c, SPL_E_INVALID, "spl_solver_cut: need exactly %lld draws", (long long)s->pend_uniq);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    *info = s->pend_info;
+    s->pending = false;
+    if (s->realistic) return realistic_cut(s, info, s->pend_n, s->pend_uniq, draws, st);
+    CKS(c, zero_ctr(c, st));
+    CK(c, c->sk.ensure((size_t)s->pend_uniq * 8, 0, st));
+    score_ext_kernel<<<nblk(s->pend_uniq), TILE, 0, st>>>(s->uniq.as<Rec>(), draws, s->pend_uniq, s->heuristic, c->luts,
+                                                            c->sk.as<uint64_t>(), c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    return speedrun_cut(s, info, s->pend_n, s->pend_uniq, c->h_ctr->sk_min, c->h_ctr->sk_max, st);
 }
 
 int32_t spl_solver_frontier(spl_solver *s, const spl_key **keys, const uint64_t **aux, const uint64_t **link, int64_t *n) {

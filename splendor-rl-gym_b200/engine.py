@@ -11,7 +11,7 @@ from ._lib import Config, Key, LevelInfo, check, lib
 
 HEURISTIC_IDS = {'simple': 0, 'balanced': 1, 'aggressive': 2, 'efficiency': 3, 'competitive': 1}
 TIE_IDS = {'stable': 0, 'det': 1, 'key': 1}
-NOISE_IDS = {'const': 0, 'hash': 1}
+NOISE_IDS = {'const': 0, 'hash': 1, 'mt': 2}
 
 M64 = (1 << 64) - 1
 
@@ -50,6 +50,59 @@ def unpack_record(lo: int, hi: int, aux: int):
     cards = tuple(i for i in range(90) if (m >> i) & 1)
     bonus = tuple((aux >> (24 + 5 * i)) & 31 for i in range(5))
     return cards, bonus, gems, (aux >> 16) & 0xff, aux & 0xffff
+
+
+class MTNoise:
+    """The reference's own noise source: `random.randint(1, 100)` of Python's global Mersenne Twister
+    (src/solver.py:4,215,247,260,284,810), drawn once per scored state in next_queue order.
+
+    `random.randint(1, 100)` is `1 + _randbelow(100)`: take the top 7 bits of one 32-bit MT19937 output and
+    retry while the value is >= 100.  The same stream is produced here in bulk with numpy's MT19937 bit
+    generator started from `random.getstate()`; `finish()` leaves the global `random` module exactly
+    where the reference would have left it."""
+
+    def __init__(self):
+        import random
+        ver, state, gauss = random.getstate()
+        self._ver, self._gauss = ver, gauss
+        self._init = (np.array(state[:-1], dtype=np.uint32), int(state[-1]))
+        self._bg = self._fresh()
+        self._buf = np.zeros(0, np.uint8)   # accepted draws not handed out yet
+        self._raw_at_buf_end = 0            # raw outputs consumed up to the end of the buffered draws
+        self._raw_pos = np.zeros(0, np.int64)
+        self.raw_used = 0                   # raw outputs the reference would have consumed so far
+
+    def _fresh(self):
+        bg = np.random.MT19937()
+        bg.state = {'bit_generator': 'MT19937', 'state': {'key': self._init[0].copy(), 'pos': self._init[1]}}
+        return bg
+
+    def draw(self, n: int) -> np.ndarray:
+        """the next n values of randint(1, 100) as uint8"""
+        while len(self._buf) < n:
+            m = max(1 << 16, int((n - len(self._buf)) * 1.4) + 1024)
+            raw = self._bg.random_raw(m) >> 25
+            ok = np.nonzero(raw < 100)[0]
+            self._buf = np.concatenate([self._buf, (raw[ok] + 1).astype(np.uint8)])
+            self._raw_pos = np.concatenate([self._raw_pos, ok + self._raw_at_buf_end + 1])
+            self._raw_at_buf_end += m
+        out, self._buf = self._buf[:n], self._buf[n:]
+        if n:
+            self.raw_used = int(self._raw_pos[n - 1])
+        self._raw_pos = self._raw_pos[n:]
+        return out
+
+    def finish(self):
+        """advance Python's global generator by exactly the outputs the reference would have consumed"""
+        import random
+        bg = self._fresh()
+        left = self.raw_used
+        while left > 0:
+            step = min(left, 1 << 24)
+            bg.random_raw(step)
+            left -= step
+        st = bg.state['state']
+        random.setstate((self._ver, tuple(int(x) for x in st['key']) + (int(st['pos']),), self._gauss))
 
 
 def _i64(x: int) -> int:
@@ -216,10 +269,16 @@ class LevelSolver:
         self._h = h
         self.infos = []
         self.ended = False
+        self.noise_source = MTNoise() if noise == 'mt' else None
 
     def step(self) -> dict:
         li = LevelInfo()
         check(lib.spl_solver_step(self._h, C.byref(li), self.eng._stream()), self.eng._h)
+        if li.kept == -1 and not li.ended:  # noise='mt': hand the level its randint draws (arrival order)
+            if self.noise_source is None:
+                raise RuntimeError("solver created with noise='mt' needs a noise_source")
+            draws = torch.from_numpy(self.noise_source.draw(li.unique)).to(self.eng.tdev)
+            check(lib.spl_solver_cut(self._h, draws.data_ptr(), li.unique, C.byref(li), self.eng._stream()), self.eng._h)
         d = li.as_dict()
         self.infos.append(d)
         self.ended = bool(li.ended)
@@ -273,6 +332,7 @@ class RLevelSolver(LevelSolver):
         self._dtype = root.dtype
         self.infos = []
         self.ended = False
+        self.noise_source = MTNoise() if rcfg.noise == 2 else None
 
     def frontier_size(self) -> int:
         p, n = C.c_void_p(), C.c_int64()

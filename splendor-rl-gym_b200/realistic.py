@@ -301,6 +301,8 @@ class MultiPlayerState:
             if turn > 1000:
                 print('Warning: Reached turn limit (1000)')
             _, ordinals = sol.path()
+            if sol.noise_source is not None:
+                sol.noise_source.finish()
         finally:
             sol.close()
         path = [self]

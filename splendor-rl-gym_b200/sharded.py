@@ -190,7 +190,10 @@ class CudaBackend:
     def dtopk_hist(self, word, shift, bits, first, smin):
         p = C.c_void_p()
         check(lib.spl_dtopk_hist(self.eng._h, word, shift, bits, int(first), smin, C.byref(p), self.eng._stream()), self.eng._h)
-        return torch.as_tensor(_DevArray(p.value, (1 << SEL_BITS,), '<i4'), device=self.device)
+        if getattr(self, '_hist_ptr', None) != p.value:  # the histogram lives at a fixed address inside the context
+            self._hist_ptr = p.value
+            self._hist = torch.as_tensor(_DevArray(p.value, (1 << SEL_BITS,), '<i4'), device=self.device)
+        return self._hist
 
     def dtopk_pick(self, word, shift, first, init_k, k):
         check(lib.spl_dtopk_pick(self.eng._h, word, shift, int(first), int(init_k), k, self.eng._stream()), self.eng._h)
@@ -344,7 +347,8 @@ class ShardedSolver:
                 bits = min(SEL_BITS, top)
                 shift = top - bits
                 hist = b.dtopk_hist(0, shift, bits, first, smin)
-                local_last, shift_last, bits_last = hist.clone(), shift, bits
+                if shift == 0 and not det:  # last score pass: remember the local tie counts
+                    local_last, shift_last, bits_last = hist.clone(), shift, bits
                 comm.all_reduce(hist, dist.ReduceOp.SUM)
                 b.dtopk_pick(0, shift, first, init_k, K)
                 first = init_k = False

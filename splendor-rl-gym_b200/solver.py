@@ -12,6 +12,9 @@ Tie-break / noise policy.  The reference adds `randint(1, 100) 
 from the unseeded global Mersenne Twister to every score, so it is not reproducible against
 itself.  This path replaces the draw by a declared deterministic source:
   noise='const' : randint -> 50            noise='hash' : randint -> 1 + splitmix64(key) % 100
+  noise='mt'    : the reference's own stream -- Python's global Mersenne Twister, one randint(1, 100)
+                  per scored state in next_queue order; `random.seed(S); solve(..., noise='mt')` then
+                  reproduces `random.seed(S)` + the UNMODIFIED reference (single GPU)
 and breaks score ties by arrival order (`tie_policy='stable'`, exactly what Python's stable
 `sorted(..., reverse=True)` does) or by canonical key, larger first (`tie_policy='det'`).
 """
@@ -207,6 +210,8 @@ class State:
                 if info['ended']:
                     break
             _, ordinals = sol.path()
+            if sol.noise_source is not None:
+                sol.noise_source.finish()  # leave `random` where the reference's own solve() would
         finally:
             sol.close()
         # replay the winning line through __iter__ so every field (saved, bonus, pts) is exact

@@ -449,6 +449,39 @@ def main():
                   f'expanded={r["expanded"]} visited={r["visited"]} {r["wall_s"]}s', file=sys.stderr)
         json.dump(runs, open(out / 'realistic_runs.json', 'w'), indent=0)
 
+    if want('mt'):
+        # The UNMODIFIED reference, only seeded: random.seed(S); solve(...).  No patched randint, no plug-ins.
+        import random as pyrandom
+        ref_solver.randint = pyrandom.randint
+        try:
+            runs = []
+            for h, goal, beam, seed in [('simple', 10, 2000, 0), ('aggressive', 15, 5000, 1), ('balanced', 15, 1000, 7),
+                                        ('efficiency', 12, 3000, 3), ('simple', 15, 300, 11)]:
+                pyrandom.seed(seed)
+                sol = State.newgame().solve(goal_pts=goal, use_heuristic=True, heuristic_name=h, beam_width=beam, verbose=False)
+                after = [pyrandom.randint(1, 100) for _ in range(4)]
+                pyrandom.seed(seed)
+                st = stepper(goal, True, h, beam)
+                assert [p['repr'] for p in st['path']] == [repr(x) for x in sol]
+                runs.append(dict(mode='speedrun', heuristic=h, goal=goal, beam=beam, seed=seed, moves=len(sol) - 1,
+                                 path=[dict(repr=repr(x), saved=x.saved, pts=x.pts) for x in sol], after=after,
+                                 visited=st['visited'], levels=st['levels']))
+                print(f'mt speedrun {h} goal={goal} beam={beam} seed={seed}: moves={len(sol) - 1}', file=sys.stderr)
+            for players, goal, mseed, beam, seed in [(2, 10, 0, 500, 5), (3, 8, 1, 300, 9), (2, 15, None, 1000, 2)]:
+                gpc = {2: 4, 3: 5, 4: 7}[players]
+                cfg = GameConfig(num_players=players, target_points=goal, gems_per_color=gpc, infinite_resources=False)
+                pyrandom.seed(seed)
+                sol = MultiPlayerState.newgame(cfg, shuffle_market=mseed is not None, seed=mseed).solve(beam_width=beam, verbose=False)
+                after = [pyrandom.randint(1, 100) for _ in range(4)]
+                runs.append(dict(mode='realistic', players=players, goal=goal, market_seed=mseed, beam=beam, seed=seed,
+                                 plies=len(sol) - 1, winner=sol[-1].get_winner(), after=after,
+                                 path_sha=[hashlib.sha256(rrec_bytes(x)).hexdigest()[:16] for x in sol],
+                                 final=[dict(pts=p.pts, cards=list(p.cards), saved=p.saved) for p in sol[-1].players]))
+                print(f'mt realistic p={players} goal={goal} beam={beam} seed={seed}: plies={len(sol) - 1}', file=sys.stderr)
+            json.dump(runs, open(out / 'mt_runs.json', 'w'), indent=0)
+        finally:
+            ref_solver.randint = NOISE
+
     if want('beam'):
         runs = []
         cfgs = []
