@@ -173,6 +173,11 @@ class CudaBackend:
                                  self.eng._stream()), self.eng._h)
         return out
 
+    def scatter_into(self, dst, rows, pos):
+        """dst[pos[i]] = rows[i] for 32-byte rows (dst is an existing [n, 4] int64 tensor)"""
+        check(lib.spl_move_rows(self.eng._h, rows.contiguous().data_ptr(), pos.contiguous().data_ptr(), pos.shape[0],
+                                dst.data_ptr(), 1, self.eng._stream()), self.eng._h)
+
     def move_rows(self, rows, idx, n_out, scatter):
         """gather (out[i] = rows[idx[i]]) or scatter (out[idx[i]] = rows[i]) of 32-byte rows"""
         out = torch.empty((max(n_out, 1), 4), dtype=torch.int64, device=self.device)
@@ -229,12 +234,21 @@ class CudaBackend:
 
 
 class ShardedSolver:
-    """State.solve (src/solver.py:390-464) over a frontier sharded across `comm.world` ranks."""
+    """State.solve (src/solver.py:390-464) over a frontier sharded across `comm.world` ranks.
+
+    Queue layout: global rank space [0, N) cut into blocks of `block_parents` ranks; block b lives on rank
+    b % G (block-cyclic), so that ROUND r = blocks r*G .. r*G+G-1 covers a contiguous range of global ranks,
+    rank 0's block first.  Rounds are processed in order, each bounded in memory; within a round the
+    receive buffers are concatenated by source rank -- hence every owner sees candidates in global arrival
+    order, and anything inserted by an earlier round is simply "visited" (it arrived earlier)."""
 
     def __init__(self, backend, comm: Comm, root_key: int, root_aux: int, goal_pts: int, use_heuristic: bool,
-                 heuristic: str, beam_width: int, tie: str = 'stable', noise: str = 'const'):
+                 heuristic: str, beam_width: int, tie: str = 'stable', noise: str = 'const',
+                 block_parents: int = 1 << 22, keep_links: bool = True):
         self.b, self.comm = backend, comm
         self.goal, self.use_h, self.h, self.beam, self.tie, self.noise = goal_pts, use_heuristic, heuristic, beam_width, tie, noise
+        self.C = int(block_parents)
+        self.keep_links = keep_links
         dev = backend.device
         m64 = (1 << 64) - 1
 
@@ -243,8 +257,9 @@ class ShardedSolver:
             return x - (1 << 64) if x >> 63 else x
         root = torch.tensor([[s64(root_key), s64(root_key >> 64), s64(root_aux), -1]], dtype=torch.int64, device=dev)
         backend.reset_visited()  # trail = {}
-        # the root is held by rank 0; its key is registered in the visited set of its owner
+        # the root is block 0 (rank 0); its key is registered in the visited set of its owner
         self.front = root if comm.rank == 0 else root[:0]
+        self.N = 1
         send, counts = backend.route_keys(root, comm.world)
         if counts[comm.rank]:
             backend.dedup_flags(send)
@@ -252,28 +267,74 @@ class ShardedSolver:
         self.ended = False
         self.goal_rank = -1
         self.infos = []
-        self.links = []  # per level: (base, local link column)
+        self._growth = 1.0   # unique / frontier of the previous level (sizes the next queue buffer)
+        self.links = []  # per level: local link column (block-cyclic local order)
         self._save_links()
 
-    def _sizes(self, n):
-        sizes = self.comm.gather_ints(n)[:, 0]
-        return sizes, int(sizes[:self.comm.rank].sum()), int(sizes.sum())
+    # ------------------------------------------------------------------ block-cyclic layout
+    def _local_count(self, n_total, g):
+        C, G = self.C, self.comm.world
+        nb = -(-n_total // C)                       # number of blocks
+        mine = len(range(g, nb, G))                 # blocks owned by g
+        if mine == 0:
+            return 0
+        last_owned = g + (mine - 1) * G
+        return (mine - 1) * C + (min(C, n_total - last_owned * C))
+
+    def _global_of_local(self, li, g):
+        """global rank of local index li (tensor or int) on rank g"""
+        C, G = self.C, self.comm.world
+        return ((li // C) * G + g) * C + li % C
+
+    def _locate(self, x):
+        C, G = self.C, self.comm.world
+        b = x // C
+        return b % G, (b // G) * C + x % C
 
     def _save_links(self):
-        _, base, _ = self._sizes(self.front.shape[0])
-        self.links.append((base, self.front[:, 3].clone()))
+        self.links.append(self.front[:, 3].clone() if self.keep_links else None)
+
+    def _redistribute(self, rows, x, dst, n_total_after):
+        """send rows with global ranks x (tensor) to their block-cyclic owners; scatter into dst (grown as needed)"""
+        comm, b, dev = self.comm, self.b, self.b.device
+        G, me, C = comm.world, comm.rank, self.C
+        blk = x // C
+        dest = blk % G
+        pos = (blk // G) * C + x % C
+        if G > 1:
+            send_counts = torch.bincount(dest, minlength=G).cpu().numpy() if x.numel() else np.zeros(G, np.int64)
+            # x is ascending, so the rows are already grouped by destination unless they span more than one cycle of G blocks
+            if x.numel() and int(blk[-1]) // G != int(blk[0]) // G:
+                order = torch.argsort(dest, stable=True)
+                rows, pos = b.move_rows(rows, order, order.shape[0], False), pos[order]
+            all_counts = comm.gather_ints(*send_counts.tolist())
+            recv_counts = all_counts[:, me]
+            rows = comm.all_to_all_rows(rows, send_counts, recv_counts)
+            pos = comm.all_to_all_rows(pos.contiguous(), send_counts, recv_counts)
+        need = self._local_count(n_total_after, me)
+        if dst is None or dst.shape[0] < need:
+            # first allocation of a level: size it for the growth seen in the previous level (no regrow copies)
+            guess = self._local_count(int(self.N * self._growth * 1.08) + 1024, me) if dst is None else 0
+            cap = max(need, guess, int(1.5 * (dst.shape[0] if dst is not None else 0)), 1024)
+            nd = torch.empty((cap, 4), dtype=torch.int64, device=dev)
+            if dst is not None and self._dst_used:
+                nd[:self._dst_used] = dst[:self._dst_used]
+            dst = nd
+        if rows.shape[0]:
+            b.scatter_into(dst, rows, pos)
+        self._dst_used = need
+        return dst
 
     # ------------------------------------------------------------------ one `while queue` iteration
     def step(self) -> dict:
         b, comm, dev = self.b, self.comm, self.b.device
-        G, me = comm.world, comm.rank
-        front = self.front
+        G, me, C = comm.world, comm.rank, self.C
+        front, N = self.front, self.N
         n_local = front.shape[0]
-        _, base, n_total = self._sizes(n_local)
-        info = dict(level=self.level, ended=0, frontier=n_total, expanded=0, generated=0, unique=0, kept=0, goal_rank=-1)
-        # 1. goal test
+        info = dict(level=self.level, ended=0, frontier=N, expanded=0, generated=0, unique=0, kept=0, goal_rank=-1)
+        # 1. goal test (src/solver.py:443-445): first state in global queue order with pts >= goal
         g = b.first_goal(front, self.goal) if n_local else -1
-        gt = torch.tensor([base + g if g >= 0 else I64_MAX], dtype=torch.int64, device=dev)
+        gt = torch.tensor([int(self._global_of_local(g, me)) if g >= 0 else I64_MAX], dtype=torch.int64, device=dev)
         comm.all_reduce(gt, dist.ReduceOp.MIN)
         if int(gt) != I64_MAX:
             self.ended, self.goal_rank = True, int(gt)
@@ -281,128 +342,131 @@ class ShardedSolver:
             self.infos.append(info)
             return info
         t0 = _tick('goal', time.perf_counter() if TIMING else 0.0)
-        # 2. expand
-        cand = b.expand_rows(front, base) if n_local else torch.empty((0, 4), dtype=torch.int64, device=dev)
-        m = cand.shape[0]
-        t0 = _tick('expand', t0)
-        # 3. route keys to their owners
-        send_keys, counts = b.route_keys(cand, G)
-        all_counts = comm.gather_ints(*counts.tolist())  # [src, dst]
-        recv_counts = all_counts[:, me]
-        t0 = _tick('partition', t0)
-        recv_keys = comm.all_to_all_rows(send_keys, counts, recv_counts)
-        t0 = _tick('a2a_keys', t0)
-        # 4. first-arrival dedup at the owner
-        flags_recv = b.dedup_flags(recv_keys)
-        t0 = _tick('dedup', t0)
-        # 5. winner bytes back to the source; compaction in arrival order
-        flags_back = comm.all_to_all_rows(flags_recv, recv_counts, counts)
-        winners = b.compact_winners(cand, flags_back)
-        t0 = _tick('flags_compact', t0)
-        u_local = winners.shape[0]
-        tot = comm.gather_ints(m, u_local)
-        info.update(expanded=n_total, generated=int(tot[:, 0].sum()), unique=int(tot[:, 1].sum()))
-        u_total = info['unique']
+        rounds = -(-(-(-N // C)) // G)
+        generated = u_total = 0
+        pieces, arrivals = [], []
+        nxt = None
+        self._dst_used = 0
+        for r in range(rounds):
+            blk = r * G + me
+            size = max(0, min(C, N - blk * C))
+            parents = front[r * C: r * C + size]
+            # 2. expand this rank's block of the round
+            cand = b.expand_rows(parents, blk * C) if size else torch.empty((0, 4), dtype=torch.int64, device=dev)
+            m = cand.shape[0]
+            t0 = _tick('expand', t0)
+            # 3. route keys to their owners
+            send_keys, counts = b.route_keys(cand, G)
+            all_counts = comm.gather_ints(*counts.tolist())  # [src, dst]
+            recv_counts = all_counts[:, me]
+            t0 = _tick('partition', t0)
+            recv_keys = comm.all_to_all_rows(send_keys, counts, recv_counts)
+            t0 = _tick('a2a_keys', t0)
+            # 4. first-arrival dedup at the owner (receive order == global arrival order inside the round)
+            flags_recv = b.dedup_flags(recv_keys)
+            t0 = _tick('dedup', t0)
+            # 5. winner bytes back to the source; compaction in arrival order
+            flags_back = comm.all_to_all_rows(flags_recv, recv_counts, counts)
+            winners = b.compact_winners(cand, flags_back)
+            t0 = _tick('flags_compact', t0)
+            w_all = comm.gather_ints(m, winners.shape[0])
+            generated += int(w_all[:, 0].sum())
+            abase = u_total + int(w_all[:me, 1].sum())     # global arrival index of my first winner of this round
+            u_total += int(w_all[:, 1].sum())
+            arr = abase + torch.arange(winners.shape[0], dtype=torch.int64, device=dev)
+            if self.use_h:
+                pieces.append(winners)
+                arrivals.append(arr)
+            else:  # pure BFS: the winners ARE the next queue, in arrival order -> place them right away
+                nxt = self._redistribute(winners, arr, nxt, u_total)
+                t0 = _tick('redistribute', t0)
+        info.update(expanded=N, generated=generated, unique=u_total)
         if self.use_h and u_total:
-            winners = self._beam_cut(winners, tot[:, 1], u_total)
-        t0 = _tick('beam_cut', t0)
-        self.front = winners
-        kv = self.comm.gather_ints(winners.shape[0], b.visited_count())
-        kept_total = int(kv[:, 0].sum())
-        info['kept'] = kept_total
-        info['visited'] = int(kv[:, 1].sum())
+            winners = torch.cat(pieces) if len(pieces) != 1 else pieces[0]
+            arr = torch.cat(arrivals) if len(arrivals) != 1 else arrivals[0]
+            del pieces, arrivals
+            rows, grank, k_total = self._beam_cut(winners, arr, u_total)
+            nxt = self._redistribute(rows, grank, None, k_total)
+            t0 = _tick('beam_cut', t0)
+            n_next = k_total
+        else:
+            n_next = u_total
+        vis = self.comm.gather_ints(b.visited_count())
+        info['kept'] = n_next
+        info['visited'] = int(vis[:, 0].sum())
         self.infos.append(info)
-        if kept_total == 0:  # frontier exhausted: `puzzle` stays the last dequeued state
-            self.ended, self.goal_rank = True, n_total - 1
+        if n_next == 0:  # frontier exhausted: `puzzle` stays the last dequeued state
+            self.ended, self.goal_rank = True, N - 1
             info['ended'] = 1
             return info
+        self._growth = max(1.0, n_next / max(1, N)) if not self.use_h else 1.0
+        self.front = nxt[:self._local_count(n_next, me)]
+        self.N = n_next
         self.level += 1
         self._save_links()
         return info
 
-    # ------------------------------------------------------------------ global beam cut + rank order
-    def _beam_cut(self, winners, u_all, u_total):
+    # ------------------------------------------------------------------ global beam cut + global ranks
+    def _beam_cut(self, winners, arr, u_total):
+        """-> (surviving local rows in local rank order, their global ranks, global survivor count).
+        Tie policy `stable` (arrival order) runs through the same key machinery as `det` with the synthetic
+        key (u_total - global arrival index): larger key == earlier arrival."""
         b, comm, dev = self.b, self.comm, self.b.device
         G, me = comm.world, comm.rank
         K = self.beam
-        det = self.tie == 'det'
         u_local = winners.shape[0]
         scores = b.score(self.h, self.noise, winners) if u_local else torch.empty(0, dtype=torch.float64, device=dev)
-        keys = winners[:, :2].contiguous() if det else None
+        if self.tie == 'det':
+            keys = winners[:, :2].contiguous()
+        else:
+            keys = torch.stack([u_total - arr, torch.zeros_like(arr)], dim=1).contiguous()
         smin, smax = b.dtopk_begin(scores, keys)
-        # global score-key range (unsigned 64-bit min / max, exchanged as 32-bit halves)
-        allr = comm.gather_ints(smin >> 32, smin & 0xffffffff, smax >> 32, smax & 0xffffffff)
-        mins = [(int(r[0]) << 32) | int(r[1]) for r, u in zip(allr, u_all) if u]
-        maxs = [(int(r[2]) << 32) | int(r[3]) for r, u in zip(allr, u_all) if u]
+        allr = comm.gather_ints(smin >> 32, smin & 0xffffffff, smax >> 32, smax & 0xffffffff, u_local)
+        mins = [(int(r[0]) << 32) | int(r[1]) for r in allr if r[4]]
+        maxs = [(int(r[2]) << 32) | int(r[3]) for r in allr if r[4]]
         smin, smax = min(mins), max(maxs)
         keep_all = u_total <= K
         all_ties = True
         if not keep_all:
             nbits = _bitlen(smax - smin)
-            state = [0, K, 0, u_total, 0, 0]
-            b.dtopk_set(state)
+            b.dtopk_set([0, K, 0, u_total, 0, 0])
             top, first, init_k = nbits, True, True
-            local_last, shift_last, bits_last = None, 0, 0
             while top > 0:
                 bits = min(SEL_BITS, top)
                 shift = top - bits
                 hist = b.dtopk_hist(0, shift, bits, first, smin)
-                if shift == 0 and not det:  # last score pass: remember the local tie counts
-                    local_last, shift_last, bits_last = hist.clone(), shift, bits
                 comm.all_reduce(hist, dist.ReduceOp.SUM)
                 b.dtopk_pick(0, shift, first, init_k, K)
                 first = init_k = False
                 top = shift
             state = b.dtopk_get()
-            T, quota, tie_count = state[0], state[1], state[3]
-            if det:
-                if quota < tie_count:
-                    all_ties = False
-                    for word, wbits in ((1, 41), (2, 64)):
-                        top, first = wbits, True
-                        while top > 0:
-                            bits = min(SEL_BITS, top)
-                            shift = top - bits
-                            hist = b.dtopk_hist(word, shift, bits, first, smin)
-                            comm.all_reduce(hist, dist.ReduceOp.SUM)
-                            b.dtopk_pick(word, shift, first, False, K)
-                            first = False
-                            top = shift
-            else:
+            quota, tie_count = state[1], state[3]
+            if quota < tie_count:  # split the score ties by key (det) / by arrival (stable, synthetic key)
                 all_ties = False
-                my_ties = u_local if nbits == 0 else int(local_last[(T >> shift_last) & ((1 << bits_last) - 1)])
-                ties = comm.gather_ints(my_ties)[:, 0]
-                before = int(ties[:me].sum())
-                state[1] = max(0, min(my_ties, quota - before))  # arrival order == (rank, local arrival)
-                b.dtopk_set(state)
-        idx, y, kl, kh = b.dtopk_cut(self.tie, keep_all, all_ties, smin, smax, u_local)
-        # global rank of every local survivor
+                # synthetic arrival keys are < 2^bitlen(u_total) with a zero high word: skip the constant digits
+                for word, wbits in (((1, 41), (2, 64)) if self.tie == 'det' else ((2, _bitlen(u_total)),)):
+                    top, first = wbits, True
+                    while top > 0:
+                        bits = min(SEL_BITS, top)
+                        shift = top - bits
+                        hist = b.dtopk_hist(word, shift, bits, first, smin)
+                        comm.all_reduce(hist, dist.ReduceOp.SUM)
+                        b.dtopk_pick(word, shift, first, False, K)
+                        first = False
+                        top = shift
+        idx, y, kl, kh = b.dtopk_cut('det', keep_all, all_ties, smin, smax, u_local)
+        # global rank of every local survivor: local index + #smaller composites on the other ranks
         k_local = idx.shape[0]
         k_all = comm.gather_ints(k_local)[:, 0]
         k_total = int(k_all.sum())
         grank = torch.arange(k_local, dtype=torch.int64, device=dev)
         if G > 1:
-            ys = comm.all_gather_v(y, k_all)
-            kls = comm.all_gather_v(kl, k_all) if det else [None] * G
-            khs = comm.all_gather_v(kh, k_all) if det else [None] * G
-            words = 3 if det else 1
+            ys, kls, khs = comm.all_gather_v(y, k_all), comm.all_gather_v(kl, k_all), comm.all_gather_v(kh, k_all)
             for g in range(G):
                 if g == me or k_all[g] == 0 or k_local == 0:
                     continue
-                # ties across ranks (stable policy only) go to the lower rank: it arrived first
-                b.count_less(words, g < me, (y, kl, kh), (ys[g], kls[g], khs[g]), grank, True)
-        kept_rows = b.move_rows(winners, idx, k_local, False)  # local survivors in local rank order
-        if G == 1:
-            return kept_rows  # grank == arange: already the new queue
-        # block distribution of the new queue by global rank
-        chunk = -(-k_total // G)
-        dest = grank // chunk if k_local else grank
-        send_counts = torch.bincount(dest, minlength=G).cpu().numpy() if k_local else np.zeros(G, np.int64)
-        all_counts = comm.gather_ints(*send_counts.tolist())
-        recv_counts = all_counts[:, me]
-        got = comm.all_to_all_rows(kept_rows, send_counts, recv_counts)
-        got_rank = comm.all_to_all_rows(grank, send_counts, recv_counts)
-        return b.move_rows(got, got_rank - me * chunk, got.shape[0], True)
+                b.count_less(3, False, (y, kl, kh), (ys[g], kls[g], khs[g]), grank, True)
+        return b.move_rows(winners, idx, k_local, False), grank, k_total
 
     # ------------------------------------------------------------------ driver helpers
     def run(self, max_levels=None):
@@ -421,10 +485,10 @@ class ShardedSolver:
         for lv in range(L, -1, -1):
             ranks[lv] = r
             if lv > 0:
-                base, col = self.links[lv]
+                owner, li = self._locate(r)
                 t = torch.zeros(1, dtype=torch.int64, device=dev)
-                if base <= r < base + col.shape[0]:
-                    t[0] = col[r - base]
+                if owner == self.comm.rank:
+                    t[0] = self.links[lv][li]
                 self.comm.all_reduce(t, dist.ReduceOp.SUM)
                 link = int(t)
                 ords[lv - 1] = link & 0xff
@@ -433,6 +497,12 @@ class ShardedSolver:
 
     def gather_frontier(self):
         """the whole current queue on every rank, in global rank order (tests / small cases only)"""
-        sizes, _, _ = self._sizes(self.front.shape[0])
-        cols = [torch.cat(self.comm.all_gather_v(self.front[:, c].contiguous(), sizes)) for c in range(4)]
-        return torch.stack(cols, dim=1)
+        G, dev = self.comm.world, self.b.device
+        sizes = [self._local_count(self.N, g) for g in range(G)]
+        out = torch.empty((self.N, 4), dtype=torch.int64, device=dev)
+        cols = [self.comm.all_gather_v(self.front[:, c].contiguous(), sizes) for c in range(4)]
+        for g in range(G):
+            if sizes[g]:
+                x = self._global_of_local(torch.arange(sizes[g], dtype=torch.int64, device=dev), g)
+                out[x] = torch.stack([cols[c][g] for c in range(4)], dim=1)
+        return out

@@ -74,6 +74,9 @@ class FakeBackend:
         flags[self._perm] = flags_send_order
         return cand[torch.nonzero(flags).flatten()]
 
+    def scatter_into(self, dst, rows, pos):
+        dst[pos] = rows
+
     def move_rows(self, rows, idx, n_out, scatter):
         out = torch.empty((n_out, 4), dtype=torch.int64)
         if scatter:

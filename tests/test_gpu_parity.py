@@ -311,14 +311,16 @@ def test_verbose_output_matches_reference_format(capsys):
 
 
 # ------------------------------------------------------------------ multi-GPU building blocks on one GPU
-@pytest.mark.parametrize('cfg', [(255, False, 'simple', 0, 'stable', 'const', 7), (15, True, 'aggressive', 20_000, 'stable', 'const', None),
-                                 (15, True, 'balanced', 20_000, 'det', 'hash', None)])
+@pytest.mark.parametrize('cfg', [(255, False, 'simple', 0, 'stable', 'const', 7, 1 << 20), (255, False, 'simple', 0, 'stable', 'const', 7, 3000),
+                                 (15, True, 'aggressive', 20_000, 'stable', 'const', None, 1 << 20),
+                                 (15, True, 'aggressive', 20_000, 'stable', 'const', None, 4096),
+                                 (15, True, 'balanced', 20_000, 'det', 'hash', None, 5000)])
 def test_sharded_solver_world1_vs_oracle(eng, cfg):
     """The sharded driver (routing, winner bytes, pass-wise select, global ranks) on a single rank, with the
     real CUDA backend, must reproduce the oracle level by level (the 2-rank logic is covered on gloo)."""
     from splendor_rl_gym_b200.sharded import Comm, CudaBackend, ShardedSolver
-    goal, use_h, hname, beam, tie, noise, max_levels = cfg
-    sol = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), 0, 0, goal, use_h, hname, beam, tie, noise)
+    goal, use_h, hname, beam, tie, noise, max_levels, block = cfg
+    sol = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), 0, 0, goal, use_h, hname, beam, tie, noise, block_parents=block)
     orc = oracle.Solver(goal, use_heuristic=use_h, heuristic_name=hname, beam_width=beam, policy=tie, noise=noise)
     while True:
         gi, oi = sol.step(), orc.step()

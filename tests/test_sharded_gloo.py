@@ -24,9 +24,9 @@ def _worker(rank, world, init_file, cfg, out_file):
     from splendor_rl_gym_b200.sharded import Comm, ShardedSolver
     dist.init_process_group('gloo', init_method=f'file://{init_file}', rank=rank, world_size=world)
     try:
-        goal, use_h, hname, beam, tie, noise = cfg
+        goal, use_h, hname, beam, tie, noise, block = cfg
         comm = Comm(torch.device('cpu'))
-        sol = ShardedSolver(FakeBackend(), comm, 0, 0, goal, use_h, hname, beam, tie, noise)
+        sol = ShardedSolver(FakeBackend(), comm, 0, 0, goal, use_h, hname, beam, tie, noise, block_parents=block)
         orc = oracle.Solver(goal, use_heuristic=use_h, heuristic_name=hname, beam_width=beam,
                             policy=tie, noise=noise)
         while True:
@@ -53,11 +53,14 @@ def _worker(rank, world, init_file, cfg, out_file):
 
 
 @pytest.mark.parametrize('world,cfg', [
-    (2, (4, False, 'simple', 0, 'stable', 'const')),          # exhaustive BFS, goal on dequeue
-    (2, (6, True, 'balanced', 300, 'stable', 'const')),       # beam, arrival-order ties split over ranks
-    (2, (6, True, 'aggressive', 257, 'det', 'hash')),         # beam, key tie-break
-    (3, (6, True, 'simple', 100, 'stable', 'const')),         # odd world size, mass ties (simple == pure noise)
-    (2, (15, True, 'efficiency', 7, 'stable', 'hash')),       # tiny beam: frontier dies out before the goal
+    (2, (4, False, 'simple', 0, 'stable', 'const', 1 << 20)),     # exhaustive BFS, goal on dequeue, one round
+    (2, (4, False, 'simple', 0, 'stable', 'const', 64)),          # ... many rounds of 64-parent blocks
+    (3, (4, False, 'simple', 0, 'stable', 'const', 1000)),        # ... odd world size, ragged last block
+    (2, (6, True, 'balanced', 300, 'stable', 'const', 1 << 20)),  # beam, arrival-order ties split over ranks
+    (2, (6, True, 'balanced', 300, 'stable', 'const', 37)),       # ... with multi-round arrival indices
+    (2, (6, True, 'aggressive', 257, 'det', 'hash', 50)),         # beam, key tie-break
+    (3, (6, True, 'simple', 100, 'stable', 'const', 16)),         # odd world size, mass ties (simple == pure noise)
+    (2, (15, True, 'efficiency', 7, 'stable', 'hash', 4)),        # tiny beam: frontier dies out before the goal
 ])
 def test_sharded_matches_oracle(world, cfg):
     with tempfile.TemporaryDirectory() as d:

@@ -24,13 +24,17 @@ ap.add_argument('--noise', default='const')
 ap.add_argument('--bfs', type=int, default=0)
 ap.add_argument('--no-oracle', action='store_true')
 ap.add_argument('--reps', type=int, default=1)
+ap.add_argument('--block', type=int, default=1 << 20, help='parents per block (round granularity)')
+ap.add_argument('--slots', type=int, default=0, help='visited-table slots per rank')
+ap.add_argument('--no-links', action='store_true')
 a = ap.parse_args()
 
 local = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(local)
 if int(os.environ.get('WORLD_SIZE', '1')) > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-eng = S.Engine(local, table_slots=max(1 << 22, int(a.beam * 110 / 0.6 / max(1, int(os.environ.get('WORLD_SIZE', '1'))))))
+eng = S.Engine(local, table_slots=a.slots or max(1 << 22, int(a.beam * 110 / 0.6 / max(1, int(os.environ.get('WORLD_SIZE', '1'))))),
+               max_table_bytes=int(120e9))
 comm = Comm(eng.tdev)
 use_h = a.bfs == 0
 check = comm.rank == 0 and not a.no_oracle
@@ -44,7 +48,8 @@ for rep in range(a.reps):
                             policy=a.tie, noise=a.noise)
     torch.cuda.synchronize()
     t0 = time.time()
-    sol = ShardedSolver(CudaBackend(eng), comm, 0, 0, 255 if a.bfs else a.goal, use_h, a.heuristic, a.beam, a.tie, a.noise)
+    sol = ShardedSolver(CudaBackend(eng), comm, 0, 0, 255 if a.bfs else a.goal, use_h, a.heuristic, a.beam, a.tie, a.noise,
+                        block_parents=a.block, keep_links=not a.no_links)
     while True:
         gi = sol.step()
         if rep == 0 and not a.no_oracle:
@@ -58,6 +63,10 @@ for rep in range(a.reps):
                     h = fr.cpu().numpy().view(np.uint64)
                     st, lk = orc.level(oi['level'] + 1)
                     assert (h[:, 0] == st['lo']).all() and (h[:, 1] == st['hi']).all() and (h[:, 2] == st['aux']).all() and (h[:, 3] == lk).all()
+        if a.bfs and comm.rank == 0:
+            torch.cuda.synchronize()
+            print(f"  level {gi['level']}: frontier={gi['frontier']} generated={gi['generated']} unique={gi['unique']} visited={gi.get('visited')} "
+                  f"t={time.time() - t0:.2f}s free={torch.cuda.mem_get_info()[0] / 2**30:.0f} GiB", flush=True)
         if gi['ended'] or (a.bfs and len(sol.infos) >= a.bfs):
             break
     torch.cuda.synchronize()
