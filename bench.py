@@ -127,7 +127,7 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------ GPU arm
-SHARDED_BEAM_PER_GPU = 4_000_000  # the sharded path materialises a level's candidates: per-rank queue bound
+SHARDED_BEAM_PER_GPU = 12_500_000  # N > 1: beam = 12.5 M per GPU (N = 8 -> 100 M, BASELINE configs[3]'s width)
 
 
 def run_b200(a):
@@ -144,7 +144,7 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
         if a.beam == 30_000_000:  # default: keep the per-GPU queue fixed (weak scaling)
-            a.beam = min(30_000_000, SHARDED_BEAM_PER_GPU * world)
+            a.beam = SHARDED_BEAM_PER_GPU * world
     # visited table sized for the whole search up front (about 85 visited states per beam slot at
     # goal 15) so the timed region never rehashes; capped by the 32-bit slot index.
     # Capped at 2.2 G slots (70 GB): beyond ~75 GB the random probes fall out of the GPU's TLB reach and
@@ -160,7 +160,7 @@ def run_b200(a):
             infos = sol.run()
             sol.close()
         else:  # frontier sharded by key hash over the ranks; every level bit-identical to world == 1
-            sol = ShardedSolver(CudaBackend(eng), comm, k, aux, a.goal, True, a.heuristic, a.beam, a.tie, a.noise)
+            sol = ShardedSolver(CudaBackend(eng), comm, k, aux, a.goal, True, a.heuristic, a.beam, a.tie, a.noise, keep_links=False)
             infos = sol.run()
         return infos
 
