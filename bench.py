@@ -261,7 +261,8 @@ def run_b200(a):
     # expand_kernel<PROBE>: read each parent (R), one visited-table key read per candidate (K),
     # one table insert per new unique (R)                       [SURVEY.md 8(d) terms R + K*b + R*u]
     expand_bytes = R_BYTES * n + K_BYTES * gen + R_BYTES * uniq
-    n_exp_launches = max(1, len(lv))
+    chunk = 4 << 20  # spl_config.chunk_parents default: one expand launch per 4 Mi parents of a level
+    n_exp_launches = max(1, sum(-(-i['frontier'] // chunk) for i in lv))
     peaks = {}
     try:
         peaks = json.load(open(ROOT / 'MEASURED_PEAKS.json'))
@@ -295,6 +296,8 @@ def run_b200(a):
         'stage_ms_per_step': {k_: round(v, 3) for k_, v in ms_stage.items()},
         'roofline': {'bound': 'hbm', 'kernel': 'expand_kernel<MODE_PROBE>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'traffic_note': 'ncu dram bytes of one saturated 4 Mi-parent launch (profiles/expand_kernel_traffic.json); '
+                                     'its algorithmic bytes are 2.6e9',
                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s (B200_PROFILING.md)',
                      'algorithmic_bytes_per_launch': expand_bytes / n_exp_launches,
                      'avg_launch_ms': ms_stage['expand'] / n_exp_launches, 'launches': n_exp_launches,
