@@ -183,7 +183,8 @@ int32_t spl_move_rows(spl_ctx *ctx, const void *rows_dev, const int64_t *idx_dev
 
 /* distributed beam cut: the radix select of spl_topk, one pass at a time, so that the host can
  * all-reduce the 2048-bin histogram (*hist_dev_out, uint32) between spl_dtopk_hist and spl_dtopk_pick.
- * word 0 = score passes, word 1/2 = key.hi / key.lo passes among score ties (det policy). */
+ * word 0 = score passes, word 1/2 = key.hi / key.lo passes among score ties (det policy).  The key array
+ * given to spl_dtopk_begin is read in place by the later passes: keep it alive until spl_dtopk_cut. */
 int32_t spl_dtopk_begin(spl_ctx *ctx, const double *scores_dev, const spl_key *keys_dev_or_null, int64_t n,
                         uint64_t *sk_min_host, uint64_t *sk_max_host, void *stream);
 int32_t spl_dtopk_hist(spl_ctx *ctx, int32_t word, int32_t shift, int32_t bits, int32_t first, uint64_t sk_min_global,
@@ -196,10 +197,12 @@ int32_t spl_dtopk_set(spl_ctx *ctx, const uint64_t state_host[6], void *stream);
 int32_t spl_dtopk_cut(spl_ctx *ctx, int32_t tie_policy, int32_t keep_all, int32_t all_ties, uint64_t sk_min_global,
                       uint64_t sk_max_global, int64_t *out_idx_dev, uint64_t *out_y_dev, uint64_t *out_klo_dev,
                       uint64_t *out_khi_dev, int64_t *kept_host, void *stream);
-/* out[i] (+)= #{ j : b[j] < a[i] } (or <= when inclusive) for ascending-sorted composite b; words = 1 | 3 */
+/* out[i] (+)= #{ j : b[j] < a[i] } (or <= when inclusive) for ascending-sorted composite b; words = 1 | 3;
+ * sorted_a = 1 promises that a is ascending too (lets each CTA bracket its slice of a inside b first) */
 int32_t spl_count_less(spl_ctx *ctx, int32_t words, int32_t inclusive, const uint64_t *ay_dev, const uint64_t *akl_dev,
                        const uint64_t *akh_dev, int64_t na, const uint64_t *by_dev, const uint64_t *bkl_dev,
-                       const uint64_t *bkh_dev, int64_t nb, int64_t *out_dev, int32_t accumulate, void *stream);
+                       const uint64_t *bkh_dev, int64_t nb, int64_t *out_dev, int32_t accumulate, int32_t sorted_a,
+                       void *stream);
 
 /* ---- fused level-synchronous solver: State.solve (src/solver.py:390-464) ------------------- */
 

@@ -76,7 +76,7 @@ def _load():
         'spl_dtopk_get': (i32, [vp, vp, vp]),
         'spl_dtopk_set': (i32, [vp, vp, vp]),
         'spl_dtopk_cut': (i32, [vp, i32, i32, i32, u64, u64, vp, vp, vp, vp, C.POINTER(i64), vp]),
-        'spl_count_less': (i32, [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, i64, vp, i32, vp]),
+        'spl_count_less': (i32, [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, i64, vp, i32, i32, vp]),
         'spl_rexpand': (i32, [vp, vp, vp, i64, vp, i64, C.POINTER(i64), vp]),
         'spl_rscore': (i32, [vp, vp, vp, i64, vp, vp]),
         'spl_rsolver_create': (i32, [vp, vp, vp, i64, i32, C.POINTER(vp)]),

@@ -662,8 +662,9 @@ constexpr int SEL_BINS = 1 << SEL_BITS;
 // WORD 0: x = sk - sk_min (score).  WORD 1 / 2 (det policy): key.hi / key.lo of the elements whose
 // score equals the score threshold (and, for WORD 2, whose key.hi equals the hi threshold).
 template <int WORD>
-__global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restrict__ sk, const Rec *__restrict__ recs,
-                                                        int64_t n, uint64_t sk_min, int shift, int bits, int first,
+// keys are read as kb[i * ks] (lo) and kb[i * ks + 1] (hi): ks = 4 for 32-byte records, 2 for a plain key array
+__global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restrict__ sk, const uint64_t *__restrict__ kb,
+                                                        int ks, int64_t n, uint64_t sk_min, int shift, int bits, int first,
                                                         const SelState *st, uint32_t *__restrict__ hist) {
     __shared__ uint32_t sh[SEL_BINS];
     for (int i = threadIdx.x; i < SEL_BINS; i += TILE) sh[i] = 0;
@@ -681,9 +682,9 @@ __global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restri
             if (WORD > 0) {
                 match = x == T;
                 if (match) {
-                    const uint64_t hi = recs[i].hi;
+                    const uint64_t hi = kb[i * ks + 1];
                     if (WORD == 1) x = hi;
-                    else { match = hi == Thi; x = recs[i].lo; }
+                    else { match = hi == Thi; x = kb[i * ks]; }
                 }
             }
             match = match && (first || hs >= 64 || (x >> hs) == (prefix >> hs));
@@ -792,8 +793,8 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
 // the key threshold found by the WORD 1/2 select passes (or every tie when `all_ties`).  Order of
 // emission is irrelevant here (the composite sort below fixes the ranks); also accumulates the
 // OR / AND of the kept keys so that sort passes over constant key digits can be skipped.
-__global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restrict__ sk, const Rec *__restrict__ recs,
-                                                       int64_t n, uint64_t sk_min, uint64_t sk_max, int keep_all,
+__global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restrict__ sk, const uint64_t *__restrict__ kb,
+                                                       int ks, int64_t n, uint64_t sk_min, uint64_t sk_max, int keep_all,
                                                        int all_ties, const SelState *st, uint64_t *__restrict__ out_y,
                                                        uint64_t *__restrict__ out_klo, uint64_t *__restrict__ out_khi,
                                                        uint32_t *__restrict__ out_idx, uint64_t *status_keep,
@@ -814,8 +815,8 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
         bool k = false;
         if (b0 + q < n) {
             x[q] = sk[b0 + q] - sk_min;
-            lo[q] = recs[b0 + q].lo;
-            hi[q] = recs[b0 + q].hi;
+            lo[q] = kb[(b0 + q) * ks];
+            hi[q] = kb[(b0 + q) * ks + 1];
             if (keep_all || x[q] > T) k = true;
             else if (x[q] == T) k = all_ties || hi[q] > Thi || (hi[q] == Thi && lo[q] >= Tlo);
             if (k) { or_lo |= lo[q]; or_hi |= hi[q]; and_lo &= lo[q]; and_hi &= hi[q]; }
@@ -1160,29 +1161,129 @@ __global__ void __launch_bounds__(TILE) move_rows_kernel(const Rec *__restrict__
 
 // for every a[i] (sorted or not): number of elements of the ascending-sorted composite list b that
 // are < a[i] (inclusive = 0) or <= a[i] (inclusive = 1); composite = (y, klo, khi) when words == 3
+__device__ __forceinline__ bool comp_less(int words, int inclusive, uint64_t by, uint64_t bl, uint64_t bh, uint64_t y,
+                                          uint64_t kl, uint64_t kh) {  // b < a (or b <= a)
+    if (by != y) return by < y;
+    if (words == 3) {
+        if (bh != kh) return bh < kh;
+        if (bl != kl) return bl < kl;
+    }
+    return inclusive;
+}
+__device__ __forceinline__ int64_t comp_lower(int words, int inclusive, const uint64_t *__restrict__ by,
+                                              const uint64_t *__restrict__ bkl, const uint64_t *__restrict__ bkh, int64_t lo,
+                                              int64_t hi, uint64_t y, uint64_t kl, uint64_t kh) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (comp_less(words, inclusive, by[mid], words == 3 ? bkl[mid] : 0, words == 3 ? bkh[mid] : 0, y, kl, kh)) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+// out[i] (+)= #{ j : b[j] < a[i] } (or <=) for ascending-sorted b.  When a is ascending too (sorted_a), the CTA
+// first brackets its slice of a inside b with two searches, so the per-element searches stay inside a short,
+// cache-resident window instead of walking the whole list.
 __global__ void __launch_bounds__(TILE) count_less_kernel(int words, int inclusive, const uint64_t *__restrict__ ay,
                                                           const uint64_t *__restrict__ akl, const uint64_t *__restrict__ akh,
                                                           int64_t na, const uint64_t *__restrict__ by,
                                                           const uint64_t *__restrict__ bkl, const uint64_t *__restrict__ bkh,
-                                                          int64_t nb, int64_t *__restrict__ out, int accumulate) {
-    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
-    if (i >= na) return;
-    const uint64_t y = ay[i], kl = words == 3 ? akl[i] : 0, kh = words == 3 ? akh[i] : 0;
-    int64_t lo = 0, hi = nb;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        const uint64_t my = by[mid];
-        bool less;  // b[mid] < a (or <= a)
-        if (my != y) less = my < y;
-        else if (words == 3) {
-            const uint64_t mh = bkh[mid], ml = bkl[mid];
-            if (mh != kh) less = mh < kh;
-            else if (ml != kl) less = ml < kl;
-            else less = inclusive;
-        } else less = inclusive;
-        if (less) lo = mid + 1; else hi = mid;
+                                                          int64_t nb, int64_t *__restrict__ out, int accumulate, int sorted_a) {
+    __shared__ int64_t s_lo, s_hi;
+    const int64_t i0 = (int64_t)blockIdx.x * TILE, i = i0 + threadIdx.x;
+    if (sorted_a) {
+        if (threadIdx.x < 2) {
+            const int64_t k = threadIdx.x == 0 ? i0 : min(i0 + TILE, na) - 1;
+            const int64_t r = comp_lower(words, threadIdx.x == 0 ? 0 : 1, by, bkl, bkh, 0, nb, ay[k], words == 3 ? akl[k] : 0,
+                                         words == 3 ? akh[k] : 0);
+            if (threadIdx.x == 0) s_lo = r; else s_hi = r;
+        }
+        __syncthreads();
     }
-    out[i] = (accumulate ? out[i] : 0) + lo;
+    if (i >= na) return;
+    const int64_t lo = sorted_a ? s_lo : 0, hi = sorted_a ? s_hi : nb;
+    const int64_t r = comp_lower(words, inclusive, by, bkl, bkh, lo, hi, ay[i], words == 3 ? akl[i] : 0, words == 3 ? akh[i] : 0);
+    out[i] = (accumulate ? out[i] : 0) + r;
+}
+
+// ---- owner partition specialised for <= 32 ranks: two kernels, keys read twice, no (digit, index) pairs
+constexpr int PART_ITEMS = 8;                    // rows per thread; a warp owns 256 consecutive rows
+constexpr int PART_TILE = TILE * PART_ITEMS;     // 2048 rows per CTA
+__global__ void __launch_bounds__(TILE) owner_hist_kernel(const Rec *__restrict__ rows, int64_t n, uint32_t n_ranks,
+                                                          uint32_t *__restrict__ matrix, uint32_t ntiles) {
+    __shared__ uint32_t sh[32];
+    if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t wbase = (int64_t)blockIdx.x * PART_TILE + (int64_t)w * (32 * PART_ITEMS);
+    uint32_t mine = 0;  // lane g accumulates the warp's count for owner g
+#pragma unroll
+    for (int q = 0; q < PART_ITEMS; ++q) {
+        const int64_t i = wbase + q * 32 + lane;
+        uint32_t o = 0xffffffffu;
+        if (i < n) {
+            uint64_t lo, hi;
+            ld_cg_u64x2(reinterpret_cast<const uint64_t *>(rows + i), lo, hi);
+            o = owner_of_key(lo, hi & HI_KEY_MASK, n_ranks);
+        }
+        for (uint32_t g = 0; g < n_ranks; ++g) {
+            const uint32_t c = __popc(__ballot_sync(0xffffffffu, o == g));
+            if (lane == g) mine += c;
+        }
+    }
+    if (lane < n_ranks && mine) atomicAdd(&sh[lane], mine);
+    __syncthreads();
+    if (threadIdx.x < n_ranks) matrix[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = sh[threadIdx.x];  // owner-major
+}
+__global__ void __launch_bounds__(TILE) owner_scatter_kernel(const Rec *__restrict__ rows, int64_t n, uint32_t n_ranks,
+                                                             const uint32_t *__restrict__ matrix_scanned, uint32_t ntiles,
+                                                             spl_key *__restrict__ send_keys, uint32_t *__restrict__ perm) {
+    __shared__ uint32_t wcnt[TILE / 32][32];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t wbase = (int64_t)blockIdx.x * PART_TILE + (int64_t)w * (32 * PART_ITEMS);
+    uint64_t klo[PART_ITEMS], khi[PART_ITEMS];
+    uint32_t own[PART_ITEMS];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < PART_ITEMS; ++q) {
+        const int64_t i = wbase + q * 32 + lane;
+        own[q] = 0xffffffffu;
+        if (i < n) {
+            ld_cg_u64x2(reinterpret_cast<const uint64_t *>(rows + i), klo[q], khi[q]);
+            own[q] = owner_of_key(klo[q], khi[q] & HI_KEY_MASK, n_ranks);
+        }
+        for (uint32_t g = 0; g < n_ranks; ++g) {
+            const uint32_t c = __popc(__ballot_sync(0xffffffffu, own[q] == g));
+            if (lane == g) mine += c;
+        }
+    }
+    wcnt[w][lane] = lane < n_ranks ? mine : 0;
+    __syncthreads();
+    if (threadIdx.x < n_ranks) {  // exclusive over warps + the tile's global base for this owner
+        uint32_t run = matrix_scanned[(uint64_t)threadIdx.x * ntiles + blockIdx.x];
+        for (int ww = 0; ww < TILE / 32; ++ww) {
+            const uint32_t c = wcnt[ww][threadIdx.x];
+            wcnt[ww][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    uint32_t base = lane < n_ranks ? wcnt[w][lane] : 0;  // lane g holds the warp's running position for owner g
+#pragma unroll
+    for (int q = 0; q < PART_ITEMS; ++q) {
+        const int64_t i = wbase + q * 32 + lane;
+        uint32_t pos = 0;
+        for (uint32_t g = 0; g < n_ranks; ++g) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, own[q] == g);
+            const uint32_t b = __shfl_sync(0xffffffffu, base, g);
+            if (own[q] == g) pos = b + __popc(bal & ((1u << lane) - 1));
+            if (lane == g) base += __popc(bal);
+        }
+        if (i < n) {
+            send_keys[pos].lo = klo[q];
+            send_keys[pos].hi = khi[q];
+            perm[pos] = (uint32_t)i;
+        }
+    }
 }
 
 // move every occupied slot of an old table into a larger one (tags preserved)

@@ -84,6 +84,7 @@ struct spl_ctx {
     int64_t dtopk_n = 0;       // distributed top-k: elements staged by spl_dtopk_begin
     int64_t route_n = -1;      // candidates of the last spl_route_keys (its permutation lives in idx[1])
     bool dtopk_recs = false;
+    const uint64_t *dtopk_keys = nullptr;  // caller-owned [n][2] key array of the distributed top-k
 };
 
 static int fail(spl_ctx *c, int code, const char *fmt, ...) {
@@ -352,7 +353,7 @@ static int run_count(spl_ctx *c, const Rec *front, int64_t n, cudaStream_t st) {
 
 // radix select of the k-th largest element under (score desc[, key desc]); leaves the thresholds and
 // the tie quota in d_sel / h_sel (score in x = sk - sk_min space).
-static int run_select(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t k, uint64_t sk_min,
+static int run_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t k, uint64_t sk_min,
                       uint64_t sk_max, int det, cudaStream_t st) {
     const int nbits = bitlen(sk_max - sk_min);
     const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
@@ -363,7 +364,7 @@ static int run_select(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n
     int top = nbits, first = 1, init_k = 1;
     while (top > 0) {
         const int bits = std::min(SEL_BITS, top), shift = top - bits;
-        sel_hist_kernel<0><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+        sel_hist_kernel<0><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
         sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, 0, shift, first, init_k, (uint64_t)k, c->d_sel);
         c->launches += 2;
         first = init_k = 0;
@@ -379,8 +380,8 @@ static int run_select(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n
             first = 1;
             while (top > 0) {
                 const int bits = std::min(SEL_BITS, top), shift = top - bits;
-                if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
-                else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+                if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+                else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
                 sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, 0, (uint64_t)k, c->d_sel);
                 c->launches += 2;
                 first = 0;
@@ -419,16 +420,18 @@ static int sort_pass(spl_ctx *c, int wide, int cur, const uint64_t *dig, int64_t
 
 // beam cut + rank sort.  stable: arrival-order cut, stable descending sort by score.  det: cut and sort
 // by (score desc, key desc).  On return idx[*which] holds the kept source indices in rank order.
-static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t cap_kept, int keep_all,
+static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t cap_kept, int keep_all,
                        int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int *which, int64_t *kept_out,
                        cudaStream_t st);
 
 static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t k, uint64_t sk_min,
                         uint64_t sk_max, int det, int *which, int64_t *kept_out, cudaStream_t st) {
     const int keep_all = n <= k;
-    if (!keep_all) CKS(c, run_select(c, sk, recs, n, k, sk_min, sk_max, det, st));
+    const uint64_t *kb = reinterpret_cast<const uint64_t *>(recs);
+    const int ks = 4;
+    if (!keep_all) CKS(c, run_select(c, sk, kb, ks, n, k, sk_min, sk_max, det, st));
     const int all_ties = keep_all || c->h_sel->tie_count != ~0ull;
-    CKS(c, do_cut_sort(c, sk, recs, n, std::min(n, k), keep_all, all_ties, sk_min, sk_max, det, which, kept_out, st));
+    CKS(c, do_cut_sort(c, sk, kb, ks, n, std::min(n, k), keep_all, all_ties, sk_min, sk_max, det, which, kept_out, st));
     if (*kept_out != std::min(n, k))
         return fail(c, SPL_E_CUDA, "internal: cut kept %lld states, expected %lld", (long long)*kept_out, (long long)std::min(n, k));
     return SPL_OK;
@@ -436,7 +439,7 @@ static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t
 
 // cut by the thresholds currently in d_sel / h_sel (x-space score threshold `prefix`, arrival quota
 // `k_rem` for the stable policy, key threshold khi/klo for det), then rank-sort the survivors.
-static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t cap_kept, int keep_all,
+static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t cap_kept, int keep_all,
                        int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int *which, int64_t *kept_out,
                        cudaStream_t st) {
     int64_t kept = cap_kept;
@@ -456,7 +459,7 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t 
     uint64_t vary_lo = 0, vary_hi = 0;
     if (det) {
         CKS(c, zero_ctr(c, st));
-        cut_det_kernel<<<ct, TILE, 0, st>>>(sk, recs, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->y[0].as<uint64_t>(),
+        cut_det_kernel<<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->y[0].as<uint64_t>(),
                                              c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(), c->idx[0].as<uint32_t>(),
                                              c->status[2].as<uint64_t>(), c->d_ctr, 1);
         ++c->launches;
@@ -680,6 +683,30 @@ int32_t spl_route_keys(spl_ctx *c, const void *cand_rows, int64_t n, int32_t n_r
         CK(c, c->idx[b].ensure((size_t)n * 4 + 4, 0, st));
     }
     const Rec *rows = reinterpret_cast<const Rec *>(cand_rows);
+    if (n_ranks <= 32) {  // two kernels: per-tile owner histogram -> scan -> stable scatter of the keys
+        const unsigned nt = nblk(n, PART_TILE);
+        const size_t msz = (size_t)n_ranks * nt;
+        CK(c, c->matrix.ensure(msz * 4 + 4, 0, st));
+        CK(c, c->matrix2.ensure(msz * 4 + 4, 0, st));
+        owner_hist_kernel<<<nt, TILE, 0, st>>>(rows, n, (uint32_t)n_ranks, c->matrix.as<uint32_t>(), nt);
+        const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
+        CKS(c, prep_status(c, 1, st_tiles, st));
+        CKS(c, reset_ticket(c, 2, st));
+        scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
+                                                    c->status[1].as<uint64_t>(), c->d_ctr, 2);
+        owner_scatter_kernel<<<nt, TILE, 0, st>>>(rows, n, (uint32_t)n_ranks, c->matrix2.as<uint32_t>(), nt, send_keys,
+                                                   c->idx[1].as<uint32_t>());
+        c->launches += 3;
+        CK(c, cudaGetLastError());
+        std::vector<uint32_t> base(n_ranks + 1);
+        for (int g = 0; g < n_ranks; ++g)
+            CK(c, cudaMemcpyAsync(&base[g], c->matrix2.as<uint32_t>() + (size_t)g * nt, 4, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        base[n_ranks] = (uint32_t)n;
+        c->d2h_bytes += 4 * n_ranks;
+        for (int g = 0; g < n_ranks; ++g) counts_host[g] = base[g + 1] - base[g];
+        return SPL_OK;
+    }
     owner_rows_kernel<<<nblk(n), TILE, 0, st>>>(rows, n, (uint32_t)n_ranks, c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>());
     ++c->launches;
     const unsigned nt = nblk(n, SORT_TILE);
@@ -775,10 +802,8 @@ int32_t spl_dtopk_begin(spl_ctx *c, const double *scores, const spl_key *keys, i
     CK(c, c->sk.ensure((size_t)n * 8, 0, st));
     flip_scores_kernel<<<nblk(n), TILE, 0, st>>>(scores, n, c->sk.as<uint64_t>(), c->d_ctr);
     ++c->launches;
-    if (keys) {
-        CK(c, c->tmp_rec.ensure((size_t)n * 32, 0, st));
-        pack_rec_kernel<<<nblk(n), TILE, 0, st>>>(keys, nullptr, n, c->tmp_rec.as<Rec>());
-        ++c->launches;
+    if (keys) {  // the caller's key array must stay alive until spl_dtopk_cut
+        c->dtopk_keys = reinterpret_cast<const uint64_t *>(keys);
         c->dtopk_recs = true;
     }
     CKS(c, read_ctr(c, st));
@@ -798,10 +823,10 @@ int32_t spl_dtopk_hist(spl_ctx *c, int32_t word, int32_t shift, int32_t bits, in
     if (n == 0) return SPL_OK;
     const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
     const uint64_t *sk = c->sk.as<uint64_t>();
-    const Rec *recs = c->tmp_rec.as<Rec>();
-    if (word == 0) sel_hist_kernel<0><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
-    else if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
-    else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, recs, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
+    const uint64_t *kb = c->dtopk_keys;
+    if (word == 0) sel_hist_kernel<0><<<grid, TILE, 0, st>>>(sk, kb, 2, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
+    else if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, 2, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
+    else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, 2, n, sk_min_global, shift, bits, first, c->d_sel, c->d_hist);
     ++c->launches;
     CK(c, cudaGetLastError());
     return SPL_OK;
@@ -852,7 +877,7 @@ int32_t spl_dtopk_cut(spl_ctx *c, int32_t tie_policy, int32_t keep_all, int32_t 
     if (det && !c->dtopk_recs) return fail(c, SPL_E_STATE, "spl_dtopk_cut: det policy needs keys in spl_dtopk_begin");
     int which = 0;
     int64_t kept = 0;
-    CKS(c, do_cut_sort(c, c->sk.as<uint64_t>(), c->tmp_rec.as<Rec>(), n, n, keep_all, all_ties, sk_min_global, sk_max_global,
+    CKS(c, do_cut_sort(c, c->sk.as<uint64_t>(), c->dtopk_keys, 2, n, n, keep_all, all_ties, sk_min_global, sk_max_global,
                        det, &which, &kept, st));
     if (kept) {
         idx_widen_kernel<<<nblk(kept), TILE, 0, st>>>(c->idx[which].as<uint32_t>(), kept, out_idx);
@@ -869,12 +894,12 @@ int32_t spl_dtopk_cut(spl_ctx *c, int32_t tie_policy, int32_t keep_all, int32_t 
 
 int32_t spl_count_less(spl_ctx *c, int32_t words, int32_t inclusive, const uint64_t *ay, const uint64_t *akl,
                        const uint64_t *akh, int64_t na, const uint64_t *by, const uint64_t *bkl, const uint64_t *bkh,
-                       int64_t nb, int64_t *out, int32_t accumulate, void *stream) {
+                       int64_t nb, int64_t *out, int32_t accumulate, int32_t sorted_a, void *stream) {
     if (!c || (words != 1 && words != 3) || na < 0 || nb < 0) return fail(c, SPL_E_INVALID, "spl_count_less: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
     if (na == 0) return SPL_OK;
-    count_less_kernel<<<nblk(na), TILE, 0, st>>>(words, inclusive, ay, akl, akh, na, by, bkl, bkh, nb, out, accumulate);
+    count_less_kernel<<<nblk(na), TILE, 0, st>>>(words, inclusive, ay, akl, akh, na, by, bkl, bkh, nb, out, accumulate, sorted_a);
     ++c->launches;
     CK(c, cudaGetLastError());
     return SPL_OK;

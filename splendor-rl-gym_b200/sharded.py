@@ -224,13 +224,13 @@ class CudaBackend:
         m = kept.value
         return idx[:m], y[:m], (kl[:m] if det else None), (kh[:m] if det else None)
 
-    def count_less(self, words, inclusive, a, b, out, accumulate):
+    def count_less(self, words, inclusive, a, b, out, accumulate, sorted_a=False):
         (ay, akl, akh), (by, bkl, bkh) = a, b
         check(lib.spl_count_less(self.eng._h, words, int(inclusive), ay.data_ptr(),
                                  akl.data_ptr() if words == 3 else None, akh.data_ptr() if words == 3 else None,
                                  ay.shape[0], by.data_ptr(), bkl.data_ptr() if words == 3 else None,
                                  bkh.data_ptr() if words == 3 else None, by.shape[0], out.data_ptr(), int(accumulate),
-                                 self.eng._stream()), self.eng._h)
+                                 int(sorted_a), self.eng._stream()), self.eng._h)
 
 
 class ShardedSolver:
@@ -420,7 +420,9 @@ class ShardedSolver:
             keys = winners[:, :2].contiguous()
         else:
             keys = torch.stack([u_total - arr, torch.zeros_like(arr)], dim=1).contiguous()
+        t0 = _tick('bc_score_keys', time.perf_counter() if TIMING else 0.0)
         smin, smax = b.dtopk_begin(scores, keys)
+        t0 = _tick('bc_begin', t0)
         allr = comm.gather_ints(smin >> 32, smin & 0xffffffff, smax >> 32, smax & 0xffffffff, u_local)
         mins = [(int(r[0]) << 32) | int(r[1]) for r in allr if r[4]]
         maxs = [(int(r[2]) << 32) | int(r[3]) for r in allr if r[4]]
@@ -454,19 +456,26 @@ class ShardedSolver:
                         b.dtopk_pick(word, shift, first, False, K)
                         first = False
                         top = shift
+        t0 = _tick('bc_select', t0)
         idx, y, kl, kh = b.dtopk_cut('det', keep_all, all_ties, smin, smax, u_local)
+        t0 = _tick('bc_cut_sort', t0)
         # global rank of every local survivor: local index + #smaller composites on the other ranks
         k_local = idx.shape[0]
         k_all = comm.gather_ints(k_local)[:, 0]
         k_total = int(k_all.sum())
         grank = torch.arange(k_local, dtype=torch.int64, device=dev)
         if G > 1:
-            ys, kls, khs = comm.all_gather_v(y, k_all), comm.all_gather_v(kl, k_all), comm.all_gather_v(kh, k_all)
+            # one all-gather of the three sort words (rows of a [3, k] block), then one ranked search per peer
+            packed = comm.all_gather_v(torch.stack([y, kl, kh]).t().contiguous().reshape(-1), k_all * 3)
             for g in range(G):
                 if g == me or k_all[g] == 0 or k_local == 0:
                     continue
-                b.count_less(3, False, (y, kl, kh), (ys[g], kls[g], khs[g]), grank, True)
-        return b.move_rows(winners, idx, k_local, False), grank, k_total
+                other = packed[g].reshape(-1, 3).t().contiguous()
+                b.count_less(3, False, (y, kl, kh), (other[0], other[1], other[2]), grank, True, True)
+        t0 = _tick('bc_ranks', t0)
+        out = b.move_rows(winners, idx, k_local, False)
+        _tick('bc_gather', t0)
+        return out, grank, k_total
 
     # ------------------------------------------------------------------ driver helpers
     def run(self, max_levels=None):

@@ -189,7 +189,7 @@ class FakeBackend:
         order = np.argsort(y, kind='stable')
         return torch.from_numpy(idx[order].astype(np.int64)), torch.from_numpy(y[order].view(np.int64).copy()), None, None
 
-    def count_less(self, words, inclusive, a, b, out, accumulate):
+    def count_less(self, words, inclusive, a, b, out, accumulate, sorted_a=False):
         ay, by = _u(a[0]), _u(b[0])
         if words == 1:
             c = np.searchsorted(by, ay, side='right' if inclusive else 'left')

@@ -362,7 +362,7 @@ def test_owner_partition_and_count_less(eng):
     a = torch.sort(torch.from_numpy(rng.integers(0, 1000, size=5000, dtype=np.int64)).to(eng.tdev)).values
     bb = torch.sort(torch.from_numpy(rng.integers(0, 1000, size=7000, dtype=np.int64)).to(eng.tdev)).values
     out = torch.zeros(5000, dtype=torch.int64, device=eng.tdev)
-    b.count_less(1, False, (a, None, None), (bb, None, None), out, False)
+    b.count_less(1, False, (a, None, None), (bb, None, None), out, False, True)
     assert (out.cpu().numpy() == np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='left')).all()
     b.count_less(1, True, (a, None, None), (bb, None, None), out, True)
     want = np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='left') + np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='right')
