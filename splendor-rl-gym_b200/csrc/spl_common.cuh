@@ -52,11 +52,10 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
 }
 // whole 32 B visited-table slot in one request (LDG.E.256.STRONG.GPU): {lo, hi|tag, ~t, spare}
 __device__ __forceinline__ void ld_slot(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &v) {
-    uint64_t d;
-    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(v), "=l"(d) : "l"(p));
-    (void)d;
+    uint64_t spare;
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(v), "=l"(spare) : "l"(p));
+    (void)spare;
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ld_rec(const Rec *p, Rec &r) {  // 256-bit load (LDG.E.256 on sm_100)
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];"
                  : "=l"(r.lo), "=l"(r.hi), "=l"(r.aux), "=l"(r.link)

@@ -110,14 +110,14 @@ __device__ __forceinline__ void make_child(const SmemTabs &s, const uint16_t *__
 // arrival of this epoch already holds the slot.  `tinv` = ~t, t = arrival index in this epoch:
 // atomicMax(~t) keeps the FIRST arrival (src/solver.py:447-450) regardless of thread order.
 // `i` is the home slot (slot_of(hash_key())), usually prefetched into L2 a few iterations ago.
-template <bool PRELOADED>
 __device__ __forceinline__ uint32_t probe_at(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t i,
                                              uint64_t klo, uint64_t khi, uint64_t tinv, uint32_t &n_new,
-                                             unsigned int *error, uint64_t a = 0, uint64_t b = 0, uint64_t v = 0) {
+                                             unsigned int *error) {
     const uint64_t want_hi = khi | (tag << TAG_SHIFT);
     for (int probes = 0; probes < MAX_PROBE; ++probes) {
         uint64_t *slot = table + (i << 2);
-        if (!PRELOADED || probes > 0) ld_slot(slot, a, b, v);
+        uint64_t a, b, v;
+        ld_slot(slot, a, b, v);
         if ((a | b) == 0) {  // empty: claim with one 128-bit CAS
             cas128(slot, 0, 0, klo, want_hi, a, b);
             if ((a | b) == 0) {
@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t probe_at(uint64_t *__restrict__ table, uint6
 }
 __device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t klo,
                                                  uint64_t khi, uint64_t tinv, uint32_t &n_new, unsigned int *error) {
-    return probe_at<false>(table, cap, tag, slot_of(hash_key(klo, khi), cap), klo, khi, tinv, n_new, error);
+    return probe_at(table, cap, tag, slot_of(hash_key(klo, khi), cap), klo, khi, tinv, n_new, error);
 }
 
 // ------------------------------------------------------------------ count + scan
@@ -241,15 +241,6 @@ __device__ __forceinline__ uint32_t buy_gems(const SmemTabs &s, uint64_t lo, uin
     return ng;
 }
 
-#ifndef SPL_PIPE
-#define SPL_PIPE 0   // measured on B200 (profiles/README.md r1b): lookahead only adds L2 requests -- the probe stream is
-                     // bound by the DRAM random-access rate, not by exposed latency
-#endif
-#ifndef SPL_PF
-#define SPL_PF 1   // 0: no lookahead, 1: prefetch.global.L2 of the home slot, 2: cp.async of the home slot into smem
-#endif
-constexpr int PIPE = SPL_PIPE;  // probes in flight per thread: lookahead distance in loop iterations
-constexpr int PIPE_N = SPL_PIPE > 0 ? SPL_PIPE : 1;
 constexpr int BUY_WIN = 4096;  // buy-list window (entries) staged in shared memory
 
 struct ExpandSmem2 {
@@ -258,61 +249,14 @@ struct ExpandSmem2 {
     uint32_t tk[TILE], nb[TILE], pref[TILE], prefb[TILE + 1];
     uint16_t units[TILE / 32][128];   // per warp: (parent lane << 2 | round) of every 32-take unit
     uint16_t blist[BUY_WIN];          // (parent << 7 | key bit) of every buy successor in the window
-    uint64_t r_klo[PIPE_N][TILE], r_khi[PIPE_N][TILE];  // pipeline ring: keys whose home slot is being fetched
-    uint32_t r_idx[PIPE_N][TILE], r_t[PIPE_N][TILE];
-#if SPL_PF == 2
-    ulonglong2 r_ab[PIPE_N][TILE];   // async copy of the home slot: key halves ...
-    uint64_t r_v[PIPE_N][TILE];      // ... and its ~t word
-#endif
     uint32_t warp_sums[TILE / 32 + 1];
 };
 
-template <class SM>
-__device__ __forceinline__ void stage_issue(SM &S, uint32_t slot_i, uint64_t *table, uint64_t cap, uint64_t klo,
-                                            uint64_t khi) {
-    const unsigned tid = threadIdx.x;
-    const uint64_t idx = slot_of(hash_key(klo, khi), cap);
-    S.r_klo[slot_i][tid] = klo;
-    S.r_khi[slot_i][tid] = khi;
-    S.r_idx[slot_i][tid] = (uint32_t)idx;
-#if SPL_PF == 1
-    prefetch_l2(table + (idx << 2));
-#elif SPL_PF == 2
-    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&S.r_ab[slot_i][tid]);
-    const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(&S.r_v[slot_i][tid]);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(table + (idx << 2)) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1), "l"(table + (idx << 2) + 2) : "memory");
-#endif
-}
-__device__ __forceinline__ void stage_commit() {
-#if SPL_PF == 2
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <class SM>
-__device__ __forceinline__ void stage_consume(SM &S, uint32_t slot_i, uint64_t *table, uint64_t cap, uint64_t tag,
-                                              uint32_t *cand_slot, uint32_t &n_new, unsigned int *error) {
-    const unsigned tid = threadIdx.x;
-#if SPL_PF == 2
-    asm volatile("cp.async.wait_group %0;" ::"n"(PIPE_N - 1) : "memory");
-#endif
-    const uint32_t tt = S.r_t[slot_i][tid];
-    if (tt != DEAD) {
-#if SPL_PF == 2
-        const ulonglong2 ab = S.r_ab[slot_i][tid];
-        cand_slot[tt] = probe_at<true>(table, cap, tag, S.r_idx[slot_i][tid], S.r_klo[slot_i][tid], S.r_khi[slot_i][tid],
-                                       ~(uint64_t)tt, n_new, error, ab.x, ab.y, S.r_v[slot_i][tid]);
-#else
-        cand_slot[tt] = probe_at<false>(table, cap, tag, S.r_idx[slot_i][tid], S.r_klo[slot_i][tid], S.r_khi[slot_i][tid],
-                                        ~(uint64_t)tt, n_new, error);
-#endif
-    }
-}
-
 // One CTA expands one tile of TILE parents.  Successors are enumerated in two divergence-free
 // streams -- gem takes (warp-uniform units of 32 consecutive table edges of one parent, coalesced)
-// and card buys (a compacted list built by warp-ballot-free bit iteration) -- and every probe of
-// the visited table is software-pipelined PIPE iterations behind an L2 prefetch of its home slot.
+// and card buys (a compacted list built by bit iteration) -- and each one probes the visited table
+// directly: software lookahead (L2 prefetch / cp.async rings) was measured to lose because the probe
+// stream is bound by HBM's random-line service rate (profiles/README.md r1b, r1c).
 // Arrival index t = off[parent] + ordinal is unchanged by the processing order.
 template <int MODE>
 __global__ void __launch_bounds__(TILE) expand_kernel(const Rec *__restrict__ front, int64_t n_par,
@@ -354,29 +298,20 @@ __global__ void __launch_bounds__(TILE) expand_kernel(const Rec *__restrict__ fr
     __syncthreads();
     uint32_t n_new = 0;
     // ---- gem takes (src/solver.py:381-388)
-    for (uint32_t u = 0; u < nu + PIPE; ++u) {
-        if (MODE == MODE_PROBE && PIPE > 0 && u >= PIPE)  // consume the stage issued PIPE iterations ago
-            stage_consume(S, u % PIPE_N, table, cap, tag, cand_slot, n_new, &ctr->error);
-        if (u < nu) {
-            const uint32_t unit = S.units[w][u], j = (w << 5) + (unit >> 2), q = ((unit & 3) << 5) + lane;
-            const uint32_t tkj = S.tk[j];
-            const bool act = q < (tkj & 0xff);
-            uint32_t tt = DEAD;
-            if (act) {
-                const uint32_t e = __ldg(takes_edges + (tkj >> 8) + q);
-                const uint64_t klo = (S.lo[j] & ~GEM_MASK) | e, khi = S.hi[j];
-                tt = c0 + S.pref[j] + S.nb[j] + q;
-                if (MODE == MODE_PROBE) {
-                    if (PIPE > 0) stage_issue(S, u % PIPE_N, table, cap, klo, khi);
-                    else cand_slot[tt] = probe_insert(table, cap, tag, klo, khi, ~(uint64_t)tt, n_new, &ctr->error);
-                } else {
-                    Rec r{klo, khi, S.aux[j], ((uint64_t)(rank_base + p0 + j) << 8) | (S.nb[j] + q)};
-                    st_rec(cand_out + tt, r);
-                }
+    for (uint32_t u = 0; u < nu; ++u) {
+        const uint32_t unit = S.units[w][u], j = (w << 5) + (unit >> 2), q = ((unit & 3) << 5) + lane;
+        const uint32_t tkj = S.tk[j];
+        if (q < (tkj & 0xff)) {
+            const uint32_t e = __ldg(takes_edges + (tkj >> 8) + q);
+            const uint64_t klo = (S.lo[j] & ~GEM_MASK) | e, khi = S.hi[j];
+            const uint32_t tt = c0 + S.pref[j] + S.nb[j] + q;
+            if (MODE == MODE_PROBE) {
+                cand_slot[tt] = probe_insert(table, cap, tag, klo, khi, ~(uint64_t)tt, n_new, &ctr->error);
+            } else {
+                Rec r{klo, khi, S.aux[j], ((uint64_t)(rank_base + p0 + j) << 8) | (S.nb[j] + q)};
+                st_rec(cand_out + tt, r);
             }
-            if (MODE == MODE_PROBE && PIPE > 0) S.r_t[u % PIPE_N][tid] = tt;
         }
-        if (MODE == MODE_PROBE && PIPE > 0) stage_commit();
     }
     // ---- card buys (src/solver.py:369-374), window by window
     for (uint32_t w0 = 0; w0 < total_buys; w0 += BUY_WIN) {
@@ -399,36 +334,24 @@ __global__ void __launch_bounds__(TILE) expand_kernel(const Rec *__restrict__ fr
             }
         }
         __syncthreads();
-        const uint32_t nbw = min((uint32_t)BUY_WIN, total_buys - w0), rounds = (nbw + TILE - 1) / TILE;
-        for (uint32_t u = 0; u < rounds + PIPE; ++u) {
-            if (MODE == MODE_PROBE && PIPE > 0 && u >= PIPE)
-                stage_consume(S, u % PIPE_N, table, cap, tag, cand_slot, n_new, &ctr->error);
-            if (u < rounds) {
-                const uint32_t i = u * TILE + tid;
-                uint32_t tt = DEAD;
-                if (i < nbw) {
-                    const uint32_t ent = S.blist[i], j = ent >> 7;
-                    const int pos = ent & 127;
-                    const uint64_t lo = S.lo[j], aux = S.aux[j];
-                    uint32_t saved, cd;
-                    const uint32_t ng = buy_gems(S.tabs, lo, aux, pos, saved, cd);
-                    uint64_t klo = (lo & ~GEM_MASK) | ng, khi = S.hi[j];
-                    if (pos < 64) klo |= 1ull << pos; else khi |= 1ull << (pos - 64);
-                    const uint32_t ord = w0 + i - S.prefb[j];
-                    tt = c0 + S.pref[j] + ord;
-                    if (MODE == MODE_PROBE) {
-                        if (PIPE > 0) stage_issue(S, u % PIPE_N, table, cap, klo, khi);
-                        else cand_slot[tt] = probe_insert(table, cap, tag, klo, khi, ~(uint64_t)tt, n_new, &ctr->error);
-                    } else {
-                        const uint64_t caux = aux + saved + ((uint64_t)((cd >> 15) & 7) << 16) +
-                                              (1ull << (24 + 5 * ((cd >> 18) & 7)));
-                        Rec r{klo, khi, caux, ((uint64_t)(rank_base + p0 + j) << 8) | ord};
-                        st_rec(cand_out + tt, r);
-                    }
-                }
-                if (MODE == MODE_PROBE && PIPE > 0) S.r_t[u % PIPE_N][tid] = tt;
+        const uint32_t nbw = min((uint32_t)BUY_WIN, total_buys - w0);
+        for (uint32_t i = tid; i < nbw; i += TILE) {
+            const uint32_t ent = S.blist[i], j = ent >> 7;
+            const int pos = ent & 127;
+            const uint64_t lo = S.lo[j], aux = S.aux[j];
+            uint32_t saved, cd;
+            const uint32_t ng = buy_gems(S.tabs, lo, aux, pos, saved, cd);
+            uint64_t klo = (lo & ~GEM_MASK) | ng, khi = S.hi[j];
+            if (pos < 64) klo |= 1ull << pos; else khi |= 1ull << (pos - 64);
+            const uint32_t ord = w0 + i - S.prefb[j];
+            const uint32_t tt = c0 + S.pref[j] + ord;
+            if (MODE == MODE_PROBE) {
+                cand_slot[tt] = probe_insert(table, cap, tag, klo, khi, ~(uint64_t)tt, n_new, &ctr->error);
+            } else {
+                const uint64_t caux = aux + saved + ((uint64_t)((cd >> 15) & 7) << 16) + (1ull << (24 + 5 * ((cd >> 18) & 7)));
+                Rec r{klo, khi, caux, ((uint64_t)(rank_base + p0 + j) << 8) | ord};
+                st_rec(cand_out + tt, r);
             }
-            if (MODE == MODE_PROBE && PIPE > 0) stage_commit();
         }
     }
     if (MODE == MODE_PROBE) {

@@ -1069,7 +1069,7 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
         info->table_slots = c->cap;
         return SPL_OK;
     }
-    int64_t total = 0, n_new = 0, kept = 0;
+    int64_t total = 0, n_new = 0;
     CK(c, cudaEventRecord(c->ev[0], st));
     CKS(c, r_expand_all(c, front, n, 0, true, &total, st));
     CK(c, cudaEventRecord(c->ev[1], st));
@@ -1379,13 +1379,11 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
         if (e != cudaSuccess) rc = fail(c, SPL_E_CUDA, "root upload: %s", cudaGetErrorString(e));
     }
     if (rc == SPL_OK) {  // trail = {self: None}: register the root's identity fingerprint
-        int64_t total = 0;
         s->n_front = 1;
         cudaError_t e = c->rkeys.ensure(16, 0, st);
         if (e == cudaSuccess) e = c->rcand.ensure(96, 0, st);
         if (e == cudaSuccess) e = c->cand_slot.ensure(4, 0, st);
         if (e != cudaSuccess) rc = fail(c, SPL_E_NOMEM, "realistic scratch alloc");
-        (void)total;
     }
     if (rc == SPL_OK) rc = zero_ctr(c, st);
     if (rc == SPL_OK) {
