@@ -177,7 +177,7 @@ int32_t spl_compact_winners(spl_ctx *ctx, const void *cand_rows_dev, int64_t n, 
 
 /* HEURISTICS[name] over rows; out[i] = rows[idx[i]] (scatter = 0) or out[idx[i]] = rows[i] (scatter = 1) */
 int32_t spl_score_rows(spl_ctx *ctx, int32_t heuristic, int32_t noise, const void *rows_dev, int64_t n, double *scores_dev,
-                       void *stream);
+                       const uint8_t *draws_dev_or_null /* SPL_NOISE_EXTERNAL: randint value per row */, void *stream);
 int32_t spl_move_rows(spl_ctx *ctx, const void *rows_dev, const int64_t *idx_dev, int64_t n, void *out_rows_dev,
                       int32_t scatter, void *stream);
 

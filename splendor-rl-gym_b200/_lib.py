@@ -68,7 +68,7 @@ def _load():
         'spl_route_keys': (i32, [vp, vp, i64, i32, vp, vp, vp]),
         'spl_dedup_flags': (i32, [vp, vp, i64, vp, vp]),
         'spl_compact_winners': (i32, [vp, vp, i64, vp, vp, C.POINTER(i64), vp]),
-        'spl_score_rows': (i32, [vp, i32, i32, vp, i64, vp, vp]),
+        'spl_score_rows': (i32, [vp, i32, i32, vp, i64, vp, vp, vp]),
         'spl_move_rows': (i32, [vp, vp, vp, i64, vp, i32, vp]),
         'spl_dtopk_begin': (i32, [vp, vp, vp, i64, C.POINTER(u64), C.POINTER(u64), vp]),
         'spl_dtopk_hist': (i32, [vp, i32, i32, i32, i32, u64, C.POINTER(vp), vp]),

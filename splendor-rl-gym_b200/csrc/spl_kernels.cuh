@@ -1063,12 +1063,13 @@ __global__ void __launch_bounds__(TILE) score_ext_kernel(const Rec *__restrict__
 }
 
 __global__ void __launch_bounds__(TILE) score_rows_kernel(const Rec *__restrict__ rows, int64_t n, int h, int noise_mode,
-                                                          ScoreLuts L, double *__restrict__ out) {
+                                                          ScoreLuts L, double *__restrict__ out,
+                                                          const uint8_t *__restrict__ draws) {
     const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
     if (i < n) {
         Rec r;
         ld_rec(rows + i, r);
-        out[i] = score_state(h, noise_mode, r.lo, r.hi & HI_KEY_MASK, r.aux, L);
+        out[i] = score_state(h, noise_mode, r.lo, r.hi & HI_KEY_MASK, r.aux, L, draws ? draws[i] : 50);
     }
 }
 // out[i] = rows[idx[i]] (gather) or out[idx[i]] = rows[i] (scatter), 64-bit indices

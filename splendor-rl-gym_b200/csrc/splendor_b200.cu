@@ -766,12 +766,13 @@ int32_t spl_compact_winners(spl_ctx *c, const void *cand_rows, int64_t n, const 
     return SPL_OK;
 }
 
-int32_t spl_score_rows(spl_ctx *c, int32_t heuristic, int32_t noise, const void *rows, int64_t n, double *scores, void *stream) {
-    if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_score_rows: bad arguments");
+int32_t spl_score_rows(spl_ctx *c, int32_t heuristic, int32_t noise, const void *rows, int64_t n, double *scores,
+                       const uint8_t *draws, void *stream) {
+    if (!c || n < 0 || (noise == SPL_NOISE_EXTERNAL && !draws)) return fail(c, SPL_E_INVALID, "spl_score_rows: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
     if (n == 0) return SPL_OK;
-    score_rows_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const Rec *>(rows), n, heuristic, noise, c->luts, scores);
+    score_rows_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const Rec *>(rows), n, heuristic, noise, c->luts, scores, draws);
     ++c->launches;
     CK(c, cudaGetLastError());
     return SPL_OK;

@@ -166,11 +166,11 @@ class CudaBackend:
         _, _, src = self.eng.dedup(keys.contiguous(), aux)
         return src
 
-    def score(self, heuristic, noise, rows):
+    def score(self, heuristic, noise, rows, draws=None):
         n = rows.shape[0]
         out = torch.empty(n, dtype=torch.float64, device=self.device)
         check(lib.spl_score_rows(self.eng._h, heuristic_id(heuristic), NOISE_IDS[noise], rows.data_ptr(), n, out.data_ptr(),
-                                 self.eng._stream()), self.eng._h)
+                                 draws.data_ptr() if draws is not None else None, self.eng._stream()), self.eng._h)
         return out
 
     def scatter_into(self, dst, rows, pos):
@@ -268,6 +268,10 @@ class ShardedSolver:
         self.goal_rank = -1
         self.infos = []
         self._growth = 1.0   # unique / frontier of the previous level (sizes the next queue buffer)
+        self.noise_source = None
+        if noise == 'mt':
+            from .engine import MTNoise
+            self.noise_source = MTNoise()
         self.links = []  # per level: local link column (block-cyclic local order)
         self._save_links()
 
@@ -415,7 +419,13 @@ class ShardedSolver:
         G, me = comm.world, comm.rank
         K = self.beam
         u_local = winners.shape[0]
-        scores = b.score(self.h, self.noise, winners) if u_local else torch.empty(0, dtype=torch.float64, device=dev)
+        draws = None
+        if self.noise == 'mt':
+            # every rank replays the same seeded stream (src/solver.py:215 etc.): the state with global arrival
+            # index a is the a-th one the reference's sorted(..., key=heuristic) would have scored in this level
+            level_draws = torch.from_numpy(self.noise_source.draw(u_total)).to(dev)
+            draws = level_draws[arr].contiguous()
+        scores = b.score(self.h, self.noise, winners, draws) if u_local else torch.empty(0, dtype=torch.float64, device=dev)
         if self.tie == 'det':
             keys = winners[:, :2].contiguous()
         else:

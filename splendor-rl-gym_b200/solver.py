@@ -14,7 +14,8 @@ itself.  This path replaces the draw by a declared deterministic source:
   noise='const' : randint -> 50            noise='hash' : randint -> 1 + splitmix64(key) % 100
   noise='mt'    : the reference's own stream -- Python's global Mersenne Twister, one randint(1, 100)
                   per scored state in next_queue order; `random.seed(S); solve(..., noise='mt')` then
-                  reproduces `random.seed(S)` + the UNMODIFIED reference (single GPU)
+                  reproduces `random.seed(S)` + the UNMODIFIED reference (any number of GPUs: every rank
+                  replays the same stream and indexes it by global arrival order)
 and breaks score ties by arrival order (`tie_policy='stable'`, exactly what Python's stable
 `sorted(..., reverse=True)` does) or by canonical key, larger first (`tie_policy='det'`).
 """
@@ -192,6 +193,8 @@ class State:
                 if stats is not None:
                     stats.append(info)
             _, ordinals = sh.path()
+            if sh.noise_source is not None:
+                sh.noise_source.finish()
             path = [self]
             for o in ordinals:
                 path.append(path[-1]._successors(eng)[o])

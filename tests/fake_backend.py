@@ -101,10 +101,12 @@ class FakeBackend:
                 src.append(i)
         return torch.tensor(src, dtype=torch.int64)
 
-    def score(self, heuristic, noise, rows):
+    def score(self, heuristic, noise, rows, draws=None):
         r = _u(rows)
         recs = np.zeros(r.shape[0], oracle.STATE_DTYPE)
         recs['lo'], recs['hi'], recs['aux'] = r[:, 0], r[:, 1], r[:, 2]
+        if noise == 'mt':
+            raise NotImplementedError('mt noise is exercised on the GPU box (tools/mt_multi_check.py)')
         return torch.from_numpy(oracle.score(recs, heuristic, noise))
 
     # ---- distributed top-k passes (numpy restatement of csrc sel_hist / sel_pick / cut kernels)
