@@ -249,6 +249,8 @@ int32_t spl_rexpand(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, 
                     int64_t cap, int64_t *n_out_host, void *stream);
 /* multi_competitive_heuristic (:778-812), bit-exact doubles */
 int32_t spl_rscore(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, int64_t n, double *scores_dev, void *stream);
+/* max(p.pts for p in state.players) per record: the progress line at :832-836 */
+int32_t spl_rmaxpts(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, int64_t n, uint8_t *out_dev, void *stream);
 /* MultiPlayerState.solve (:750-860): beam always applied, ties by arrival order, game over when play
  * returns to the player who triggered the final round.  Steps / path / destroy via spl_solver_*. */
 int32_t spl_rsolver_create(spl_ctx *ctx, const spl_rconfig *cfg, const void *root_rec_host, int64_t beam_width,

@@ -33,3 +33,20 @@ def get_buys() -> Buys:
 
 def load_buys(*, update: bool = False) -> Buys:  # noqa: ARG001 - signature parity with src/buys.py:25
     return get_buys()
+
+
+def store_buys(buys: Buys, path='buys.pickle'):
+    """Write the table in the reference's cache format (src/buys.py:20-22): a pickled {gems: card indices} dict
+    that the reference's `load_buys()` reads back unchanged."""
+    import pickle
+    with open(path, 'wb') as f:
+        pickle.dump(buys, f, pickle.HIGHEST_PROTOCOL)
+
+
+def export_buys_to_txt(path: str = 'buys.txt'):
+    """Dump `key: card indices` per line, the format of the reference's debug exporter (src/buys.py:44-49)."""
+    buys = get_buys()
+    with open(path, mode='w', encoding='utf-8') as f:
+        print('Writing buys to a text file...')
+        for g in buys:
+            f.write(f'{g}: {buys[g]}\n')

@@ -316,6 +316,17 @@ __global__ void __launch_bounds__(TILE) r_score_kernel(const RRec *__restrict__ 
     }
 }
 
+// max over players of pts, per state (the reference's progress line, src/solver.py:832-836)
+__global__ void __launch_bounds__(TILE) r_maxpts_kernel(const RRec *__restrict__ recs, int64_t n,
+                                                        const RConfigDev *__restrict__ cfg, uint8_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) {
+        int m = 0;
+        for (int q = 0; q < cfg->P; ++q) m = max(m, r_pts(*cfg, recs[i].p[q]));
+        out[i] = (uint8_t)min(m, 255);
+    }
+}
+
 __global__ void r_root_key_kernel(const RRec *root, const RConfigDev *cfg, spl_key *key) {
     RRec s;
     ld_rrec(root, s);

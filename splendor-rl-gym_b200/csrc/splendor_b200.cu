@@ -1360,6 +1360,18 @@ int32_t spl_rscore(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t
     return SPL_OK;
 }
 
+int32_t spl_rmaxpts(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, uint8_t *out, void *stream) {
+    if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_rmaxpts: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return SPL_OK;
+    CKS(c, upload_rconfig(c, cfg, st));
+    r_maxpts_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const RRec *>(recs), n, c->rcfg.as<RConfigDev>(), out);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
 int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_rec_host, int64_t beam, int32_t keep_links,
                            spl_solver **out) {
     if (!c || !cfg || !root_rec_host || !out) return fail(c, SPL_E_INVALID, "spl_rsolver_create: null argument");

@@ -334,6 +334,25 @@ class RLevelSolver(LevelSolver):
         self.ended = False
         self.noise_source = MTNoise() if rcfg.noise == 2 else None
 
+    def progress(self, rcfg, running_max: int):
+        """(rank, record, max pts) of every queued state that raises the running maximum of max-player-points
+        while the queue is scanned in order, up to the first finished game (src/solver.py:825-836)."""
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib.spl_rsolver_frontier(self._h, C.byref(p), C.byref(n)), self.eng._h)
+        if n.value == 0:
+            return []
+        mp = torch.empty(n.value, dtype=torch.uint8, device=self.eng.tdev)
+        check(lib.spl_rmaxpts(self.eng._h, C.byref(rcfg), p.value, n.value, mp.data_ptr(), self.eng._stream()), self.eng._h)
+        mp = mp.to(torch.int64)
+        run = torch.cummax(mp, 0).values
+        prev = torch.clamp(torch.cat([torch.full((1,), running_max, dtype=torch.int64, device=mp.device), run[:-1]]), min=running_max)
+        hits = torch.nonzero(mp > prev).flatten().tolist()
+        if not hits:
+            return []
+        recs = torch.as_tensor(_DevArray(p.value, (n.value, 96), '|u1'), device=self.eng.tdev)
+        sel = recs[torch.tensor(hits, device=self.eng.tdev)].cpu().numpy().reshape(-1).view(self._dtype)
+        return [(h, sel[i], int(mp[h])) for i, h in enumerate(hits)]
+
     def frontier_size(self) -> int:
         p, n = C.c_void_p(), C.c_int64()
         check(lib.spl_rsolver_frontier(self._h, C.byref(p), C.byref(n)), self.eng._h)

@@ -252,6 +252,11 @@ class MultiPlayerState:
         return MultiPlayerState(cfg, tuple(players), GemPool(pool), market, int(rec['cur']), self.turn_number + 1,
                                 triggered, frp, _sequences=self._sequences)
 
+    @staticmethod
+    def _rec_pts(rec, player: int) -> int:
+        m = int(rec['p'][player]['mlo']) | int(rec['p'][player]['mhi']) << 64
+        return sum(deck[c].pt for c in range(90) if (m >> c) & 1)
+
     def _successors(self, eng: Engine, noise='const'):
         recs = eng.rexpand(self.rconfig(noise), self.record())
         return [self._child_from_record(r) for r in recs]
@@ -286,12 +291,23 @@ class MultiPlayerState:
             print(f'Market Shuffled: {"Yes" if self.market.tier1_deck != self.market.tier1_deck[:1] else "No (deterministic)"}')
             print('=' * 60)
             print()
-        sol = eng.rsolver(self.rconfig(noise), self.record(), beam_width)
+        rcfg = self.rconfig(noise)
+        sol = eng.rsolver(rcfg, self.record(), beam_width)
         try:
             turn = 0
+            max_pts = 0
             while True:
                 if verbose and turn % 100 == 0:
                     print(f'{turn=:<10} Queue size: {sol.frontier_size()}')
+                if verbose:  # `max_pts=...` lines of src/solver.py:832-836 (states before the first finished game)
+                    for _, rec, mp in sol.progress(rcfg, max_pts):
+                        cur = int(rec['cur'])
+                        if self._rec_pts(rec, cur) >= self.config.target_points:
+                            break
+                        max_pts = mp
+                        g = int(rec['p'][cur]['gems'])
+                        gems = tuple((g >> (3 * k)) & 7 for k in range(COLOR_NUM))
+                        print(f'{max_pts=:<7} Turn {turn}, P{cur}: {self._rec_pts(rec, cur)}pts, {gems!r}')
                 info = sol.step()
                 if stats is not None:
                     stats.append(info)

@@ -482,6 +482,27 @@ def main():
         finally:
             ref_solver.randint = NOISE
 
+    if want('verbose'):
+        # stdout of the reference's own solve(verbose=True) (noise const, ties by arrival order)
+        import contextlib
+        import io
+        NOISE.mode = 'const'
+        texts = {}
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            State.newgame().solve(goal_pts=6, use_heuristic=True, heuristic_name='balanced@stable', beam_width=1000, verbose=True)
+        texts['speedrun_goal6_balanced_beam1000'] = buf.getvalue().replace('balanced@stable', 'balanced')
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            State.newgame().solve(goal_pts=4, verbose=True)
+        texts['speedrun_goal4_bfs'] = buf.getvalue()
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            MultiPlayerState.newgame(GameConfig(num_players=2, target_points=6, gems_per_color=4, infinite_resources=False)).solve(
+                beam_width=300, verbose=True)
+        texts['realistic_2p_goal6_beam300'] = buf.getvalue()
+        json.dump(texts, open(out / 'verbose.json', 'w'), indent=0)
+
     if want('beam'):
         runs = []
         cfgs = []

@@ -32,3 +32,23 @@ def test_cli_realistic():
     out = _run('6', '--realistic', '-w', '3000', '-q')
     assert 'Game Over! Winner: Player 0' in out and 'Player 0: 6 points, 8 cards' in out and 'Player 1: 5 points, 8 cards' in out
     assert 'Total moves: 34' in out
+
+
+def _strip_cache_noise(text):
+    # the reference prints `Unpickling buys...` / `Generating buys...` when its pickle cache is first touched
+    # (src/buys.py:25-36); that I/O is outside the path
+    return [l for l in text.splitlines() if not l.endswith('buys...') and l != 'Pickling finished.']
+
+
+def test_verbose_output_equals_reference(golden, capsys):
+    """stdout of solve(verbose=True) -- banner, `turn=` and prefix-max `max_pts=` lines --
+    is line for line what the reference prints (fixtures: tests/golden/verbose.json)."""
+    import splendor_rl_gym_b200 as S
+    want = golden['verbose']
+    S.State.newgame().solve(goal_pts=6, use_heuristic=True, heuristic_name='balanced', beam_width=1000, verbose=True)
+    assert capsys.readouterr().out.splitlines() == _strip_cache_noise(want['speedrun_goal6_balanced_beam1000'])
+    S.State.newgame().solve(goal_pts=4, verbose=True)
+    assert capsys.readouterr().out.splitlines() == _strip_cache_noise(want['speedrun_goal4_bfs'])
+    cfg = S.GameConfig(num_players=2, target_points=6, gems_per_color=4, infinite_resources=False)
+    S.MultiPlayerState.newgame(cfg).solve(beam_width=300, verbose=True)
+    assert capsys.readouterr().out.splitlines() == _strip_cache_noise(want['realistic_2p_goal6_beam300'])

@@ -134,3 +134,17 @@ def test_no_cpu_fallback():
     h = C.c_void_p()
     rc = S.lib.spl_create(C.byref(Config(0, 0, 0, 0, 0)), C.byref(h))
     assert rc == -2 and b'no CPU fallback' in S.lib.spl_last_error(None)
+
+
+def test_buys_cache_files_are_reference_compatible(tmp_path, golden):
+    """buys.pickle / buys.txt written from the native table load as the reference's own (src/buys.py:20-49)."""
+    import pickle
+    from splendor_rl_gym_b200.buys import export_buys_to_txt, get_buys, store_buys
+    store_buys(get_buys(), tmp_path / 'buys.pickle')
+    back = pickle.load(open(tmp_path / 'buys.pickle', 'rb'))
+    assert back == get_buys() and (tmp_path / 'buys.pickle').stat().st_size > 1_000_000  # tests/test_buys.py:30-38
+    for k, want in golden['tables']['buys']['samples'].items():
+        assert list(back[tuple(map(int, k.split(',')))]) == want
+    export_buys_to_txt(tmp_path / 'buys.txt')
+    first = open(tmp_path / 'buys.txt').readline()
+    assert first == '(0, 0, 0, 0, 0): ()\n'
