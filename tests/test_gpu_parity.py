@@ -367,3 +367,56 @@ def test_owner_partition_and_count_less(eng):
     b.count_less(1, True, (a, None, None), (bb, None, None), out, True)
     want = np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='left') + np.searchsorted(bb.cpu().numpy(), a.cpu().numpy(), side='right')
     assert (out.cpu().numpy() == want).all()
+
+
+# ------------------------------------------------------------------ edge cases of solve()
+def test_solve_edge_cases(eng):
+    root = S.State.newgame()
+    # goal already met by the root: the loop ends at the first dequeue (src/solver.py:443-445)
+    assert [repr(s) for s in root.solve(goal_pts=0, verbose=False)] == ['(0, 0, 0, 0, 0)']
+    # beam of one state, both tie policies: still a legal line that reaches the goal or dies out like the oracle's
+    for tie in ('stable', 'det'):
+        sol = root.solve(goal_pts=3, use_heuristic=True, heuristic_name='aggressive', beam_width=1, verbose=False, tie_policy=tie)
+        orc = oracle.Solver(3, use_heuristic=True, heuristic_name='aggressive', beam_width=1, policy=tie)
+        orc.run()
+        want = [oracle.unpack_state(r) for r in orc.path()]
+        assert [(s.cards, s.gems, s.saved) for s in sol] == [(w['cards'], w['gems'], w['saved']) for w in want]
+    # a hand-built root (owned cards, gems, saved) with the maximum fan-out region nearby
+    st = S.State.newgame()
+    for card in (40, 5, 21):
+        st = st.buy_card(card)
+    st.gems = (1, 2, 0, 0, 3)
+    st = S.State(cards=st.cards, bonus=st.bonus, gems=st.gems, pts=st.pts, saved=st.saved)
+    sol = st.solve(goal_pts=st.pts + 3, verbose=False)
+    rec = oracle.pack_state(st.cards, st.bonus, st.gems, st.pts, st.saved)
+    orc = oracle.Solver(st.pts + 3, root=rec)
+    orc.run()
+    want = [oracle.unpack_state(r) for r in orc.path()]
+    assert [(s.cards, s.gems, s.saved, s.pts) for s in sol] == [(w['cards'], w['gems'], w['saved'], w['pts']) for w in want]
+
+
+def test_max_fanout_state(eng):
+    """190 successors (90 buys + 100 takes) -- the ordinal must fit the 8-bit link field."""
+    recs = oracle.pack_state((), (7, 7, 7, 7, 7), (2, 2, 2, 2, 2), 0, 0)
+    ck, ca, cl = eng.expand(*eng.to_device(np.stack([recs['lo'], recs['hi']], 1), recs['aux']))
+    want = oracle.expand(recs)
+    assert len(want) == 190 == ck.shape[0]
+    assert (ck.cpu().numpy().view(np.uint64)[:, 0] == want['lo']).all() and (ca.cpu().numpy().view(np.uint64) == want['aux']).all()
+    assert cl.cpu().tolist() == list(range(190))
+
+
+def test_table_growth_during_beam_search(golden):
+    """a 4096-slot table must grow by rehash many times without changing any level"""
+    eng2 = S.Engine(0, table_slots=4096, chunk_parents=1024)
+    run = next(r for r in golden['beam_runs'] if r['base'] == 'aggressive' and r['beam'] == 20000 and r['policy'] == 'stable')
+    k, a = S.State.newgame().record()
+    sol = eng2.solver(k, a, run['goal'], True, 'aggressive', run['beam'], 'stable', run['noise'])
+    for want in run['levels']:
+        gi = sol.step()
+        if gi['ended']:
+            break
+        fr = sol.frontier().cpu().numpy().view(np.uint64)
+        assert_digest(level_digest(fr[:, 0], fr[:, 1], fr[:, 2], fr[:, 3]), want['kept'], f"growth level {want['level']}")
+    assert gi['ended'] and gi['table_slots'] > 4096 * 256
+    sol.close()
+    eng2.close()
