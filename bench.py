@@ -288,7 +288,7 @@ def run_b200(a):
         'config': {'workload': f'C3 (BASELINE configs[2]): speedrun goal {a.goal} -u -H {a.heuristic}, beam {a.beam}, '
                                f'noise={a.noise}, ties={a.tie}; one step = one full solve from the root state',
                    'l2': 'working set (visited table %.1f GB) >> 126 MB L2; no flush needed' % (slots * 32 / 1e9),
-                   'beam': a.beam, 'goal': a.goal, 'heuristic': a.heuristic, 'parallelism': f'hash-sharded x{world}'},
+                   'beam': a.beam, 'goal': a.goal, 'heuristic': a.heuristic, 'parallelism': 'single GPU, fused expand+probe kernels'},
         'time_to_solve_goal15_s': ms / a.steps * 1e-3,
         'generated_per_s': float(gen) * a.steps / (ms * 1e-3) if world == 1 else None,
         'levels': len(infos), 'expanded_per_step': n, 'generated_per_step': gen, 'unique_per_step': uniq,
