@@ -1,16 +1,18 @@
-"""Colour enum of the five gem colours (mirrors the reference's src/color.py:4-15)."""
-from enum import Enum
+"""The five gem colours, in the column order of the packed records (bits 3c..3c+2 of the gems word,
+bonus field c of the aux word).  Same names and values as the reference's `Color` enum (src/color.py)."""
+import enum
+
+_NAMES = ('WHITE', 'BLUE', 'GREEN', 'RED', 'BLACK')
 
 
-class Color(Enum):
-    WHITE = 0
-    BLUE = 1
-    GREEN = 2
-    RED = 3
-    BLACK = 4
+class Color(enum.Enum):
+    _ignore_ = ['_i', '_n']
+    for _i, _n in enumerate(_NAMES):
+        vars()[_n] = _i
 
     def __repr__(self):
-        return self.__str__()
+        return f'Color.{self.name}'
 
 
-COLOR_NUM = len(Color)
+COLOR_NUM = len(_NAMES)
+assert [c.value for c in Color] == list(range(COLOR_NUM))
