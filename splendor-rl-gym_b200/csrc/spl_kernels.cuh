@@ -32,6 +32,7 @@ struct SelState {            // radix-select state (device)
     unsigned long long c_gt;    // elements strictly above the current bucket
     unsigned long long tie_count;  // size of the bucket chosen by the last pick
     unsigned long long khi, klo;   // det policy: key threshold among score ties (keys >= it are kept)
+    unsigned long long rank_t;     // dictionary path: descending rank of the threshold score (~0 = no dictionary)
 };
 
 // ------------------------------------------------------------------ per-parent derivation
@@ -658,12 +659,162 @@ __global__ void __launch_bounds__(1024) sel_pick_kernel(uint32_t *hist, int word
     }
 }
 
+// ------------------------------------------------------------------ score dictionary (beam threshold, few distinct scores)
+// The heuristics map a state to one of a few hundred distinct doubles per level (points, bonuses and
+// savings are small integers; noise `const` adds the same draw to every state).  One pass counts the
+// distinct scores in a small hash table, a single CTA sorts them, finds the threshold score and its
+// tie quota, and numbers the scores by descending rank; the cut then emits that rank instead of the
+// 64-bit score, so the rank sort needs ceil(log2(distinct)/8) passes instead of up to 8.  More than
+// DICT_MAX distinct scores (noise `hash` / `mt` on large levels): the radix select above is used.
+constexpr int DICT_CAP = 1 << 14;    // hash slots
+constexpr int DICT_MAX = 2048;       // most distinct scores the dictionary path handles
+constexpr int DICT_LOCAL = 1024;     // per-CTA staging slots
+constexpr unsigned long long DICT_EMPTY = ~0ull;  // not a score: flip_f64 never yields all ones
+
+struct ScoreDict {
+    unsigned long long key[DICT_CAP];  // distinct order-preserving score keys
+    unsigned int cnt[DICT_CAP];        // occurrences
+    unsigned int rank[DICT_CAP];       // descending rank (dict_rank_kernel)
+    unsigned int n, over;              // distinct scores inserted; 1 = too many, dictionary abandoned
+};
+
+__device__ __forceinline__ uint32_t dict_hash(unsigned long long v) {
+    return (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 40);
+}
+__device__ __forceinline__ void dict_add(ScoreDict *d, unsigned long long v, unsigned int c) {
+    uint32_t s = dict_hash(v) & (DICT_CAP - 1);
+    for (int p = 0; p < DICT_CAP; ++p, s = (s + 1) & (DICT_CAP - 1)) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&d->key[s]);
+        if (cur != v) {
+            if (cur != DICT_EMPTY) continue;
+            if (*reinterpret_cast<volatile unsigned int *>(&d->over)) return;
+            cur = atomicCAS(&d->key[s], DICT_EMPTY, v);
+            if (cur == DICT_EMPTY) {
+                if (atomicAdd(&d->n, 1u) >= (unsigned)DICT_MAX) atomicExch(&d->over, 1u);
+            } else if (cur != v) {
+                continue;
+            }
+        }
+        atomicAdd(&d->cnt[s], c);
+        return;
+    }
+    atomicExch(&d->over, 1u);
+}
+__device__ __forceinline__ uint32_t dict_rank_of(const ScoreDict *__restrict__ d, unsigned long long v) {
+    uint32_t s = dict_hash(v) & (DICT_CAP - 1);
+    for (int p = 0; p < DICT_CAP && __ldg(&d->key[s]) != v; ++p) s = (s + 1) & (DICT_CAP - 1);
+    return __ldg(&d->rank[s]);
+}
+
+__global__ void __launch_bounds__(TILE) dict_build_kernel(const uint64_t *__restrict__ sk, int64_t n, ScoreDict *d) {
+    __shared__ unsigned long long lkey[DICT_LOCAL];
+    __shared__ unsigned int lcnt[DICT_LOCAL];
+    for (int i = threadIdx.x; i < DICT_LOCAL; i += TILE) { lkey[i] = DICT_EMPTY; lcnt[i] = 0; }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    int iter = 0;
+    for (int64_t base = (int64_t)blockIdx.x * TILE; base < n; base += (int64_t)gridDim.x * TILE, ++iter) {
+        if ((iter & 15) == 15 &&
+            __any_sync(0xffffffffu, *reinterpret_cast<volatile unsigned int *>(&d->over) != 0)) break;
+        const int64_t i = base + threadIdx.x;
+        const bool ok = i < n;
+        const unsigned long long v = ok ? sk[i] : 0;
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(act, v);
+            if (lane == (unsigned)(__ffs(peers) - 1)) {
+                const unsigned int c = (unsigned int)__popc(peers);
+                uint32_t s = dict_hash(v) & (DICT_LOCAL - 1);
+                bool done = false;
+                for (int p = 0; p < 16 && !done; ++p, s = (s + 1) & (DICT_LOCAL - 1)) {
+                    unsigned long long cur = lkey[s];
+                    if (cur != v) {
+                        if (cur != DICT_EMPTY) continue;
+                        cur = atomicCAS(&lkey[s], DICT_EMPTY, v);
+                        if (cur != DICT_EMPTY && cur != v) continue;
+                    }
+                    atomicAdd(&lcnt[s], c);
+                    done = true;
+                }
+                if (!done) dict_add(d, v, c);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DICT_LOCAL; i += TILE)
+        if (lkey[i] != DICT_EMPTY) dict_add(d, lkey[i], lcnt[i]);
+}
+
+// 1 CTA of 1024 threads: sort the distinct scores (descending), locate the k-th largest element,
+// publish the threshold in SelState (same fields the radix select leaves) and number the scores.
+__global__ void __launch_bounds__(1024) dict_rank_kernel(ScoreDict *d, uint64_t k, uint64_t sk_min, SelState *st) {
+    __shared__ unsigned long long skey[DICT_MAX];
+    __shared__ unsigned int sslot[DICT_MAX];
+    __shared__ unsigned long long s_scan[1024];
+    __shared__ unsigned int s_n;
+    const int t = threadIdx.x;
+    if (d->over || d->n > (unsigned)DICT_MAX) {
+        if (t == 0) st->rank_t = ~0ull;
+        return;
+    }
+    if (t == 0) s_n = 0;
+    for (int i = t; i < DICT_MAX; i += 1024) { skey[i] = 0; sslot[i] = 0xFFFFFFFFu; }  // pads sort last
+    __syncthreads();
+    for (int s = t; s < DICT_CAP; s += 1024) {
+        const unsigned long long kk = d->key[s];
+        if (kk != DICT_EMPTY) {
+            const unsigned int j = atomicAdd(&s_n, 1u);
+            if (j < (unsigned)DICT_MAX) { skey[j] = kk; sslot[j] = (unsigned int)s; }
+        }
+    }
+    __syncthreads();
+    const int D = (int)min(s_n, (unsigned)DICT_MAX);
+    for (int size = 2; size <= DICT_MAX; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int i = ((t / stride) * 2 * stride) + (t % stride), j = i + stride;
+            const bool desc = (i & size) == 0;
+            const unsigned long long a = skey[i], b = skey[j];
+            if (desc ? a < b : a > b) {
+                skey[i] = b; skey[j] = a;
+                const unsigned int sa = sslot[i];
+                sslot[i] = sslot[j]; sslot[j] = sa;
+            }
+            __syncthreads();
+        }
+    const int e0 = 2 * t, e1 = 2 * t + 1;
+    const unsigned long long c0 = e0 < D ? d->cnt[sslot[e0]] : 0, c1 = e1 < D ? d->cnt[sslot[e1]] : 0;
+    s_scan[t] = c0 + c1;
+    __syncthreads();
+    for (int dd = 1; dd < 1024; dd <<= 1) {
+        const unsigned long long v = t >= dd ? s_scan[t - dd] : 0;
+        __syncthreads();
+        s_scan[t] += v;
+        __syncthreads();
+    }
+    const unsigned long long incl = s_scan[t], excl = incl - (c0 + c1);
+    if (excl < k && k <= incl) {
+        unsigned long long above = excl, cnt = c0;
+        int j = e0;
+        if (above + c0 < k) { above += c0; j = e1; cnt = c1; }
+        st->prefix = skey[j] - sk_min;
+        st->k_rem = k - above;
+        st->c_gt = above;
+        st->tie_count = cnt;
+        st->rank_t = (unsigned long long)j;
+    }
+    if (e0 < D) d->rank[sslot[e0]] = (unsigned int)e0;
+    if (e1 < D) d->rank[sslot[e1]] = (unsigned int)e1;
+}
+
 // ------------------------------------------------------------------ beam cut in arrival order
 // keep x > T, plus the first k_rem arrivals with x == T (Python's stable sort keeps equal keys in
 // arrival order, src/solver.py:453).  Emits (y = sk_max - sk, src index) pairs for the rank sort.
 constexpr int CUT_ITEMS = 32;  // 8192 elements per tile: 4x fewer look-back hops than 8 (0.30 -> see profiles)
+// DICT: y = descending rank of the score among the level's distinct scores (ScoreDict)
+template <bool DICT>
 __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ sk, int64_t n, uint64_t sk_min,
                                                    uint64_t sk_max, int keep_all, const SelState *st,
+                                                   const ScoreDict *__restrict__ dict,
                                                    uint64_t *__restrict__ out_y, uint32_t *__restrict__ out_idx,
                                                    uint64_t *status_tie, uint64_t *status_keep, Counters *ctr,
                                                    int ticket_id) {
@@ -706,7 +857,7 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
 #pragma unroll
     for (int q = 0; q < CUT_ITEMS; ++q)
         if (keepmask >> q & 1) {
-            out_y[pos] = (sk_max - sk_min) - x[q];
+            out_y[pos] = DICT ? (uint64_t)dict_rank_of(dict, x[q] + sk_min) : (sk_max - sk_min) - x[q];
             out_idx[pos] = (uint32_t)(b0 + q);
             ++pos;
         }
@@ -716,9 +867,11 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
 // the key threshold found by the WORD 1/2 select passes (or every tie when `all_ties`).  Order of
 // emission is irrelevant here (the composite sort below fixes the ranks); also accumulates the
 // OR / AND of the kept keys so that sort passes over constant key digits can be skipped.
+template <bool DICT>
 __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restrict__ sk, const uint64_t *__restrict__ kb,
                                                        int ks, int64_t n, uint64_t sk_min, uint64_t sk_max, int keep_all,
-                                                       int all_ties, const SelState *st, uint64_t *__restrict__ out_y,
+                                                       int all_ties, const SelState *st,
+                                                       const ScoreDict *__restrict__ dict, uint64_t *__restrict__ out_y,
                                                        uint64_t *__restrict__ out_klo, uint64_t *__restrict__ out_khi,
                                                        uint32_t *__restrict__ out_idx, uint64_t *status_keep,
                                                        Counters *ctr, int ticket_id) {
@@ -755,7 +908,7 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
 #pragma unroll
     for (int q = 0; q < CUT_ITEMS; ++q)
         if (keepmask >> q & 1) {
-            out_y[pos] = (sk_max - sk_min) - x[q];
+            out_y[pos] = DICT ? (uint64_t)dict_rank_of(dict, x[q] + sk_min) : (sk_max - sk_min) - x[q];
             out_klo[pos] = ~lo[q];                 // ascending sort of ~key == descending key
             out_khi[pos] = ~hi[q] & HI_KEY_MASK;
             out_idx[pos] = (uint32_t)(b0 + q);

@@ -73,6 +73,8 @@ struct spl_ctx {
     Counters *d_ctr = nullptr, *h_ctr = nullptr;
     SelState *d_sel = nullptr, *h_sel = nullptr;
     uint32_t *d_hist = nullptr;
+    ScoreDict *d_dict = nullptr;
+    int dict_skip = 0;  // levels left before the dictionary path is tried again after a miss
     DevBuf status[3];
     // scratch
     DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2;
@@ -219,6 +221,7 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaMallocHost(&c->h_sel, sizeof(SelState)));
     CKC(cudaMalloc(&c->d_hist, SEL_BINS * 4));
     CKC(cudaMemset(c->d_hist, 0, SEL_BINS * 4));
+    CKC(cudaMalloc(&c->d_dict, sizeof(ScoreDict)));
     for (auto &ev : c->ev) CKC(cudaEventCreate(&ev));
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
@@ -242,7 +245,7 @@ int32_t spl_destroy(spl_ctx *c) {
     cudaDeviceSynchronize();
     cudaFree(c->table); cudaFree(c->d_tabs); cudaFree(c->d_takes_idx); cudaFree(c->d_takes_edges);
     cudaFree(c->d_lut); cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr); cudaFree(c->d_sel); cudaFreeHost(c->h_sel);
-    cudaFree(c->d_hist);
+    cudaFree(c->d_hist); cudaFree(c->d_dict);
     for (auto *b : c->pool_links) delete b;
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     delete c;
@@ -351,6 +354,27 @@ static int run_count(spl_ctx *c, const Rec *front, int64_t n, cudaStream_t st) {
     return read_ctr(c, st);
 }
 
+// det policy: split the score ties at the threshold (d_sel->prefix) by key, larger first
+static int select_ties_by_key(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t k,
+                              uint64_t sk_min, cudaStream_t st) {
+    const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
+    for (int word = 1; word <= 2; ++word) {
+        int top = word == 1 ? 41 : 64, first = 1;
+        while (top > 0) {
+            const int bits = std::min(SEL_BITS, top), shift = top - bits;
+            if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+            else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+            sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, 0, (uint64_t)k, c->d_sel);
+            c->launches += 2;
+            first = 0;
+            top = shift;
+        }
+    }
+    CK(c, cudaGetLastError());
+    c->h_sel->tie_count = ~0ull;  // marks "threshold key valid"
+    return SPL_OK;
+}
+
 // radix select of the k-th largest element under (score desc[, key desc]); leaves the thresholds and
 // the tie quota in d_sel / h_sel (score in x = sk - sk_min space).
 static int run_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t k, uint64_t sk_min,
@@ -360,6 +384,7 @@ static int run_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks
     memset(c->h_sel, 0, sizeof(SelState));
     c->h_sel->k_rem = (unsigned long long)k;
     c->h_sel->tie_count = (unsigned long long)n;  // nbits == 0: every score equal
+    c->h_sel->rank_t = ~0ull;
     CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
     int top = nbits, first = 1, init_k = 1;
     while (top > 0) {
@@ -374,23 +399,36 @@ static int run_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks
     CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     c->d2h_bytes += sizeof(SelState);
-    if (det && c->h_sel->k_rem < c->h_sel->tie_count) {  // split the score ties by key, larger first
-        for (int word = 1; word <= 2; ++word) {
-            top = word == 1 ? 41 : 64;
-            first = 1;
-            while (top > 0) {
-                const int bits = std::min(SEL_BITS, top), shift = top - bits;
-                if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
-                else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
-                sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, 0, (uint64_t)k, c->d_sel);
-                c->launches += 2;
-                first = 0;
-                top = shift;
-            }
-        }
-        CK(c, cudaGetLastError());
-        c->h_sel->tie_count = ~0ull;  // marks "threshold key valid"
+    if (det && c->h_sel->k_rem < c->h_sel->tie_count) CKS(c, select_ties_by_key(c, sk, kb, ks, n, k, sk_min, st));
+    return SPL_OK;
+}
+
+// Dictionary select (few distinct scores): count the distinct scores, rank them, find the k-th largest
+// element.  Leaves d_sel / h_sel as run_select does plus rank_t; *used = 0 when the level has more
+// than DICT_MAX distinct scores (nothing decided: the caller falls back to the radix select).
+static int run_dict_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t k,
+                           uint64_t sk_min, int det, int *used, cudaStream_t st) {
+    *used = 0;
+    if (c->dict_skip > 0) { --c->dict_skip; return SPL_OK; }
+    const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
+    CK(c, cudaMemsetAsync(c->d_dict->key, 0xFF, sizeof(c->d_dict->key), st));
+    CK(c, cudaMemsetAsync(c->d_dict->cnt, 0, sizeof(ScoreDict) - sizeof(c->d_dict->key), st));
+    memset(c->h_sel, 0, sizeof(SelState));
+    c->h_sel->rank_t = ~0ull;
+    CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
+    dict_build_kernel<<<grid, TILE, 0, st>>>(sk, n, c->d_dict);
+    dict_rank_kernel<<<1, 1024, 0, st>>>(c->d_dict, (uint64_t)k, sk_min, c->d_sel);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += sizeof(SelState);
+    if (c->h_sel->rank_t == ~0ull) {
+        c->dict_skip = 3;
+        return SPL_OK;
     }
+    *used = 1;
+    if (det && k < n && c->h_sel->k_rem < c->h_sel->tie_count) CKS(c, select_ties_by_key(c, sk, kb, ks, n, k, sk_min, st));
     return SPL_OK;
 }
 
@@ -421,7 +459,7 @@ static int sort_pass(spl_ctx *c, int wide, int cur, const uint64_t *dig, int64_t
 // beam cut + rank sort.  stable: arrival-order cut, stable descending sort by score.  det: cut and sort
 // by (score desc, key desc).  On return idx[*which] holds the kept source indices in rank order.
 static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t cap_kept, int keep_all,
-                       int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int *which, int64_t *kept_out,
+                       int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int use_dict, int *which, int64_t *kept_out,
                        cudaStream_t st);
 
 static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t k, uint64_t sk_min,
@@ -429,9 +467,11 @@ static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t
     const int keep_all = n <= k;
     const uint64_t *kb = reinterpret_cast<const uint64_t *>(recs);
     const int ks = 4;
-    if (!keep_all) CKS(c, run_select(c, sk, kb, ks, n, k, sk_min, sk_max, det, st));
+    int use_dict = 0;
+    CKS(c, run_dict_select(c, sk, kb, ks, n, std::min(n, k), sk_min, det, &use_dict, st));
+    if (!keep_all && !use_dict) CKS(c, run_select(c, sk, kb, ks, n, k, sk_min, sk_max, det, st));
     const int all_ties = keep_all || c->h_sel->tie_count != ~0ull;
-    CKS(c, do_cut_sort(c, sk, kb, ks, n, std::min(n, k), keep_all, all_ties, sk_min, sk_max, det, which, kept_out, st));
+    CKS(c, do_cut_sort(c, sk, kb, ks, n, std::min(n, k), keep_all, all_ties, sk_min, sk_max, det, use_dict, which, kept_out, st));
     if (*kept_out != std::min(n, k))
         return fail(c, SPL_E_CUDA, "internal: cut kept %lld states, expected %lld", (long long)*kept_out, (long long)std::min(n, k));
     return SPL_OK;
@@ -440,7 +480,7 @@ static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t
 // cut by the thresholds currently in d_sel / h_sel (x-space score threshold `prefix`, arrival quota
 // `k_rem` for the stable policy, key threshold khi/klo for det), then rank-sort the survivors.
 static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t cap_kept, int keep_all,
-                       int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int *which, int64_t *kept_out,
+                       int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int use_dict, int *which, int64_t *kept_out,
                        cudaStream_t st) {
     int64_t kept = cap_kept;
     const uint64_t T = keep_all ? 0 : c->h_sel->prefix;
@@ -459,18 +499,28 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
     uint64_t vary_lo = 0, vary_hi = 0;
     if (det) {
         CKS(c, zero_ctr(c, st));
-        cut_det_kernel<<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->y[0].as<uint64_t>(),
-                                             c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(), c->idx[0].as<uint32_t>(),
-                                             c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        if (use_dict)
+            cut_det_kernel<true><<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->d_dict,
+                                                       c->y[0].as<uint64_t>(), c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(),
+                                                       c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        else
+            cut_det_kernel<false><<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, nullptr,
+                                                        c->y[0].as<uint64_t>(), c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(),
+                                                        c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
         ++c->launches;
         CK(c, cudaGetLastError());
         CKS(c, read_ctr(c, st));
         vary_lo = c->h_ctr->key_or[0] ^ c->h_ctr->key_and[0];
         vary_hi = (c->h_ctr->key_or[1] ^ c->h_ctr->key_and[1]) & HI_KEY_MASK;
     } else {
-        cut_kernel<<<ct, TILE, 0, st>>>(sk, n, sk_min, sk_max, keep_all, c->d_sel, c->y[0].as<uint64_t>(),
-                                         c->idx[0].as<uint32_t>(), c->status[1].as<uint64_t>(),
-                                         c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        if (use_dict)
+            cut_kernel<true><<<ct, TILE, 0, st>>>(sk, n, sk_min, sk_max, keep_all, c->d_sel, c->d_dict, c->y[0].as<uint64_t>(),
+                                                   c->idx[0].as<uint32_t>(), c->status[1].as<uint64_t>(),
+                                                   c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        else
+            cut_kernel<false><<<ct, TILE, 0, st>>>(sk, n, sk_min, sk_max, keep_all, c->d_sel, nullptr, c->y[0].as<uint64_t>(),
+                                                    c->idx[0].as<uint32_t>(), c->status[1].as<uint64_t>(),
+                                                    c->status[2].as<uint64_t>(), c->d_ctr, 1);
         ++c->launches;
         CK(c, cudaGetLastError());
     }
@@ -482,8 +532,8 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
         kept = (int64_t)(last & ((1ull << 62) - 1));
         if (kept > cap_kept) return fail(c, SPL_E_CUDA, "internal: cut kept %lld > capacity %lld", (long long)kept, (long long)cap_kept);
     }
-    // y = sk_max - sk in [0, sk_max - sk_min - T]
-    const int nbits = bitlen((sk_max - sk_min) - T);
+    // y = sk_max - sk in [0, sk_max - sk_min - T], or (dictionary) the score's descending rank in [0, rank_t]
+    const int nbits = use_dict ? bitlen(c->h_sel->rank_t) : bitlen((sk_max - sk_min) - T);
     int cur = 0;
     const unsigned nt = nblk(kept, SORT_TILE);
     if (kept > 1 && (nbits > 0 || vary_lo || vary_hi)) {
@@ -850,7 +900,7 @@ int32_t spl_dtopk_get(spl_ctx *c, uint64_t state_host[6], void *stream) {
     CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     c->d2h_bytes += sizeof(SelState);
-    memcpy(state_host, c->h_sel, sizeof(SelState));
+    memcpy(state_host, c->h_sel, 6 * sizeof(uint64_t));  // the six fields of the ABI; rank_t is internal
     return SPL_OK;
 }
 
@@ -858,7 +908,8 @@ int32_t spl_dtopk_set(spl_ctx *c, const uint64_t state_host[6], void *stream) {
     if (!c || !state_host) return SPL_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
-    memcpy(c->h_sel, state_host, sizeof(SelState));
+    memcpy(c->h_sel, state_host, 6 * sizeof(uint64_t));
+    c->h_sel->rank_t = ~0ull;
     CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
     CK(c, cudaStreamSynchronize(st));
     c->h2d_bytes += sizeof(SelState);
@@ -879,7 +930,7 @@ int32_t spl_dtopk_cut(spl_ctx *c, int32_t tie_policy, int32_t keep_all, int32_t 
     int which = 0;
     int64_t kept = 0;
     CKS(c, do_cut_sort(c, c->sk.as<uint64_t>(), c->dtopk_keys, 2, n, n, keep_all, all_ties, sk_min_global, sk_max_global,
-                       det, &which, &kept, st));
+                       det, 0, &which, &kept, st));
     if (kept) {
         idx_widen_kernel<<<nblk(kept), TILE, 0, st>>>(c->idx[which].as<uint32_t>(), kept, out_idx);
         ++c->launches;
