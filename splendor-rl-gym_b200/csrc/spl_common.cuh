@@ -61,6 +61,10 @@ __device__ __forceinline__ void ld_rec(const Rec *p, Rec &r) {  // 256-bit load 
                  : "=l"(r.lo), "=l"(r.hi), "=l"(r.aux), "=l"(r.link)
                  : "l"(p));
 }
+// four consecutive u64 of a read-only stream (32-byte aligned)
+__device__ __forceinline__ void ld_u64x4(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
 __device__ __forceinline__ void st_rec(Rec *p, const Rec &r) {
     asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(r.lo), "l"(r.hi), "l"(r.aux), "l"(r.link)
                  : "memory");
@@ -148,23 +152,32 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_s
 
 // Decoupled look-back over tiles that were handed out by an atomic ticket (so every
 // predecessor tile is already resident).  status word = flag << 62 | value;
-// flag 1 = tile aggregate published, 2 = inclusive prefix published.  Called by ONE thread.
+// flag 1 = tile aggregate published, 2 = inclusive prefix published.  Called by ALL 32 lanes of
+// warp 0 (converged); every lane gets the result.  The warp inspects 32 predecessors per step, so a
+// deep window of aggregate-only tiles costs one L2 round trip per 32 tiles instead of one per tile.
 __device__ __forceinline__ uint64_t lookback_exclusive(volatile uint64_t *status, uint32_t tile, uint64_t aggregate,
                                                        uint64_t base0) {
     constexpr uint64_t VAL = (1ull << 62) - 1;
+    const unsigned lane = threadIdx.x & 31;
     if (tile == 0) {
-        status[0] = (2ull << 62) | ((base0 + aggregate) & VAL);
+        if (lane == 0) status[0] = (2ull << 62) | ((base0 + aggregate) & VAL);
         return base0;
     }
-    status[tile] = (1ull << 62) | (aggregate & VAL);
+    if (lane == 0) status[tile] = (1ull << 62) | (aggregate & VAL);
     uint64_t excl = 0;
-    for (int64_t j = (int64_t)tile - 1;; --j) {
+    for (int64_t j = (int64_t)tile - 1;; j -= 32) {
+        const int64_t idx = j - lane;  // lane 0 = nearest predecessor; idx < 0 = before tile 0 (which always ends the walk)
         uint64_t s;
-        do { s = status[j]; } while ((s >> 62) == 0);
-        excl += s & VAL;
-        if ((s >> 62) == 2) break;
+        do { s = idx >= 0 ? status[idx] : (2ull << 62); } while (__any_sync(0xffffffffu, (s >> 62) == 0));
+        const unsigned incl = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        const unsigned first = incl ? (unsigned)__ffs(incl) - 1 : 32u;
+        uint64_t v = lane <= first ? (s & VAL) : 0;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (incl) break;
     }
-    status[tile] = (2ull << 62) | ((excl + aggregate) & VAL);
+    if (lane == 0) status[tile] = (2ull << 62) | ((excl + aggregate) & VAL);
     return excl;
 }
 

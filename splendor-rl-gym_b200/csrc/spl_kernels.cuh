@@ -170,9 +170,12 @@ __global__ void __launch_bounds__(TILE) count_scan_kernel(const Rec *__restrict_
     }
     uint32_t total;
     const uint32_t excl = block_excl_scan(cnt, warp_sums, total);
-    if (threadIdx.x == 0) {
-        s_base = lookback_exclusive(status, tile, total, 0);
-        if ((int64_t)(tile + 1) * TILE >= n_par) ctr->total_cands = s_base + total;
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status, tile, total, 0);
+        if (threadIdx.x == 0) {
+            s_base = e;
+            if ((int64_t)(tile + 1) * TILE >= n_par) ctr->total_cands = e + total;
+        }
     }
     __syncthreads();
     if (p < n_par) off[p] = (uint32_t)(s_base + excl);
@@ -503,9 +506,12 @@ __global__ void __launch_bounds__(TILE) resolve_kernel(const Rec *__restrict__ f
     }
     uint32_t tile_wins;
     block_excl_scan(mywins, S.warp_sums, tile_wins);
-    if (threadIdx.x == 0) {
-        S.base = out_base + lookback_exclusive(status, tile, tile_wins, 0);
-        if ((uint64_t)c0 + ncand >= total) ctr->n_emitted = S.base + tile_wins;
+    if (threadIdx.x < 32) {
+        const uint64_t e = out_base + lookback_exclusive(status, tile, tile_wins, 0);
+        if (threadIdx.x == 0) {
+            S.base = e;
+            if ((uint64_t)c0 + ncand >= total) ctr->n_emitted = e + tile_wins;
+        }
     }
     // ---- word prefix of winner counts (exclusive), processed TILE words at a time
     uint32_t carry = 0;
@@ -828,14 +834,27 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
     const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * CUT_ITEMS;
     uint64_t x[CUT_ITEMS];
     uint32_t ties = 0;
+    if (b0 + CUT_ITEMS <= n) {  // the thread's 256 contiguous bytes as 8 x 32-byte loads (whole sectors)
 #pragma unroll
-    for (int q = 0; q < CUT_ITEMS; ++q) {
-        x[q] = (b0 + q < n) ? sk[b0 + q] - sk_min : 0;
-        ties += (b0 + q < n) && !keep_all && x[q] == T;
+        for (int q = 0; q < CUT_ITEMS; q += 4) ld_u64x4(sk + b0 + q, x[q], x[q + 1], x[q + 2], x[q + 3]);
+#pragma unroll
+        for (int q = 0; q < CUT_ITEMS; ++q) {
+            x[q] -= sk_min;
+            ties += !keep_all && x[q] == T;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < CUT_ITEMS; ++q) {
+            x[q] = (b0 + q < n) ? sk[b0 + q] - sk_min : 0;
+            ties += (b0 + q < n) && !keep_all && x[q] == T;
+        }
     }
     uint32_t tot;
     uint32_t tie_ex = block_excl_scan(ties, warp_sums, tot);
-    if (threadIdx.x == 0) s_tie_base = keep_all ? 0 : lookback_exclusive(status_tie, tile, tot, 0);
+    if (threadIdx.x < 32) {
+        const uint64_t e = keep_all ? 0 : lookback_exclusive(status_tie, tile, tot, 0);
+        if (threadIdx.x == 0) s_tie_base = e;
+    }
     __syncthreads();
     uint64_t tie_rank = s_tie_base + tie_ex;
     uint32_t keepmask = 0, kept = 0;
@@ -851,7 +870,10 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
         kept += k;
     }
     const uint32_t keep_ex = block_excl_scan(kept, warp_sums, tot);
-    if (threadIdx.x == 0) s_keep_base = lookback_exclusive(status_keep, tile, tot, 0);
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status_keep, tile, tot, 0);
+        if (threadIdx.x == 0) s_keep_base = e;
+    }
     __syncthreads();
     uint64_t pos = s_keep_base + keep_ex;
 #pragma unroll
@@ -902,7 +924,10 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
     }
     uint32_t tot;
     const uint32_t keep_ex = block_excl_scan(kept, warp_sums, tot);
-    if (threadIdx.x == 0) s_keep_base = lookback_exclusive(status_keep, tile, tot, 0);
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status_keep, tile, tot, 0);
+        if (threadIdx.x == 0) s_keep_base = e;
+    }
     __syncthreads();
     uint64_t pos = s_keep_base + keep_ex;
 #pragma unroll
@@ -968,7 +993,10 @@ __global__ void __launch_bounds__(TILE) scan_u32_kernel(const uint32_t *__restri
     }
     uint32_t tot;
     uint32_t ex = block_excl_scan(sum, warp_sums, tot);
-    if (threadIdx.x == 0) s_base = lookback_exclusive(status, tile, tot, 0);
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status, tile, tot, 0);
+        if (threadIdx.x == 0) s_base = e;
+    }
     __syncthreads();
     uint32_t run = (uint32_t)s_base + ex;
 #pragma unroll
@@ -1174,9 +1202,12 @@ __global__ void __launch_bounds__(TILE) compact_rows_kernel(const Rec *__restric
     }
     uint32_t tot;
     const uint32_t ex = block_excl_scan(__popc(mask), warp_sums, tot);
-    if (threadIdx.x == 0) {
-        s_base = lookback_exclusive(status, tile, tot, 0);
-        if (((int64_t)tile + 1) * TILE * 8 >= n) ctr->n_emitted = s_base + tot;
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status, tile, tot, 0);
+        if (threadIdx.x == 0) {
+            s_base = e;
+            if (((int64_t)tile + 1) * TILE * 8 >= n) ctr->n_emitted = e + tot;
+        }
     }
     __syncthreads();
     uint64_t pos = s_base + ex;

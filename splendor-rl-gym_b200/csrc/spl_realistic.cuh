@@ -234,9 +234,12 @@ __global__ void __launch_bounds__(TILE) r_count_scan_kernel(const RRec *__restri
     }
     uint32_t total;
     const uint32_t excl = block_excl_scan(cnt, warp_sums, total);
-    if (threadIdx.x == 0) {
-        s_base = lookback_exclusive(status, tile, total, 0);
-        if ((int64_t)(tile + 1) * TILE >= n) ctr->total_cands = s_base + total;
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status, tile, total, 0);
+        if (threadIdx.x == 0) {
+            s_base = e;
+            if ((int64_t)(tile + 1) * TILE >= n) ctr->total_cands = e + total;
+        }
     }
     __syncthreads();
     if (p < n) off[p] = (uint32_t)(s_base + excl);
