@@ -524,38 +524,39 @@ __global__ void __launch_bounds__(TILE) resolve_kernel(const Rec *__restrict__ f
         carry += tot;
     }
     __syncthreads();
-    // ---- pass 2: emit winners in arrival order
+    // ---- pass 2: emit winners in arrival order, one thread per winner (consecutive threads write
+    // consecutive records): winner q of the tile sits in the last word whose exclusive prefix is <= q
     uint64_t kmin = ~0ull, kmax = 0;
-    for (uint32_t w = threadIdx.x; w < nwords; w += TILE) {
-        uint32_t bits = S.win[w];
-        uint64_t pos = S.base + S.wpre[w];
-        while (bits) {
-            const uint32_t i = (w << 5) + (__ffs(bits) - 1);
-            bits &= bits - 1;
-            Rec r;
-            if (SRC == SRC_PARENT) {
-                const uint32_t j = owner_of(S.E.pref, i);
-                const uint32_t ord = i - S.E.pref[j];
-                make_child(S.E.tabs, takes_edges, S.E.lo[j], S.E.hi[j], S.E.aux[j], S.E.bm_lo[j], S.E.bm_hi[j],
-                           S.E.nb[j], S.E.tk[j], ord, r.lo, r.hi, r.aux);
-                r.link = ((uint64_t)(rank_base + (int64_t)tile * TILE + j) << 8) | ord;
-            } else {
-                const uint64_t t = (uint64_t)c0 + i;
-                r.lo = list_keys[t].lo;
-                r.hi = list_keys[t].hi & HI_KEY_MASK;
-                r.aux = list_aux ? list_aux[t] : 0;
-                r.link = t;
-                if (out_src) out_src[pos] = (int64_t)t;
-            }
-            st_rec(out + pos, r);
-            if (SCORE) {
-                const double sc = score_state(h, noise_mode, r.lo, r.hi, r.aux, L);
-                const uint64_t k = flip_f64((uint64_t)__double_as_longlong(sc));
-                out_sk[pos] = k;
-                kmin = min(kmin, k);
-                kmax = max(kmax, k);
-            }
-            ++pos;
+    for (uint32_t q = threadIdx.x; q < tile_wins; q += TILE) {
+        uint32_t lo_w = 0, hi_w = nwords;  // invariant: wpre[lo_w] <= q < wpre[hi_w] (wpre[nwords] = tile_wins)
+        while (hi_w - lo_w > 1) {
+            const uint32_t mid = (lo_w + hi_w) >> 1;
+            if (S.wpre[mid] <= q) lo_w = mid; else hi_w = mid;
+        }
+        const uint32_t i = (lo_w << 5) + (uint32_t)nth_set_bit32(S.win[lo_w], (int)(q - S.wpre[lo_w]));
+        const uint64_t pos = S.base + q;
+        Rec r;
+        if (SRC == SRC_PARENT) {
+            const uint32_t j = owner_of(S.E.pref, i);
+            const uint32_t ord = i - S.E.pref[j];
+            make_child(S.E.tabs, takes_edges, S.E.lo[j], S.E.hi[j], S.E.aux[j], S.E.bm_lo[j], S.E.bm_hi[j],
+                       S.E.nb[j], S.E.tk[j], ord, r.lo, r.hi, r.aux);
+            r.link = ((uint64_t)(rank_base + (int64_t)tile * TILE + j) << 8) | ord;
+        } else {
+            const uint64_t t = (uint64_t)c0 + i;
+            r.lo = list_keys[t].lo;
+            r.hi = list_keys[t].hi & HI_KEY_MASK;
+            r.aux = list_aux ? list_aux[t] : 0;
+            r.link = t;
+            if (out_src) out_src[pos] = (int64_t)t;
+        }
+        st_rec(out + pos, r);
+        if (SCORE) {
+            const double sc = score_state(h, noise_mode, r.lo, r.hi, r.aux, L);
+            const uint64_t k = flip_f64((uint64_t)__double_as_longlong(sc));
+            out_sk[pos] = k;
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
         }
     }
     if (SCORE) {
