@@ -816,6 +816,8 @@ __global__ void __launch_bounds__(1024) dict_rank_kernel(ScoreDict *d, uint64_t 
 // ------------------------------------------------------------------ beam cut in arrival order
 // keep x > T, plus the first k_rem arrivals with x == T (Python's stable sort keeps equal keys in
 // arrival order, src/solver.py:453).  Emits (y = sk_max - sk, src index) pairs for the rank sort.
+// status_keep carries the running count of elements ABOVE the threshold, status_tie the running count
+// of ties: survivors in total = above + min(ties, quota) (read back by the host from the last tile).
 constexpr int CUT_ITEMS = 32;  // 8192 elements per tile: 4x fewer look-back hops than 8 (0.30 -> see profiles)
 // DICT: y = descending rank of the score among the level's distinct scores (ScoreDict)
 template <bool DICT>
@@ -834,56 +836,50 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
     const uint64_t T = keep_all ? 0 : st->prefix, quota = keep_all ? 0 : st->k_rem;
     const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * CUT_ITEMS;
     uint64_t x[CUT_ITEMS];
-    uint32_t ties = 0;
+    uint32_t cnt = 0;  // elements above the threshold (low half) | ties with it (high half); both <= 32
     if (b0 + CUT_ITEMS <= n) {  // the thread's 256 contiguous bytes as 8 x 32-byte loads (whole sectors)
 #pragma unroll
         for (int q = 0; q < CUT_ITEMS; q += 4) ld_u64x4(sk + b0 + q, x[q], x[q + 1], x[q + 2], x[q + 3]);
 #pragma unroll
         for (int q = 0; q < CUT_ITEMS; ++q) {
             x[q] -= sk_min;
-            ties += !keep_all && x[q] == T;
+            cnt += (keep_all || x[q] > T) ? 1u : (x[q] == T ? 0x10000u : 0u);
         }
     } else {
 #pragma unroll
         for (int q = 0; q < CUT_ITEMS; ++q) {
             x[q] = (b0 + q < n) ? sk[b0 + q] - sk_min : 0;
-            ties += (b0 + q < n) && !keep_all && x[q] == T;
+            if (b0 + q < n) cnt += (keep_all || x[q] > T) ? 1u : (x[q] == T ? 0x10000u : 0u);
         }
     }
+    // One block scan and two independent chains walked by two warps at once: elements above the
+    // threshold, and ties.  Ties are kept in arrival order up to `quota`, so the survivors before this
+    // thread number above_before + min(ties_before, quota).
     uint32_t tot;
-    uint32_t tie_ex = block_excl_scan(ties, warp_sums, tot);
+    const uint32_t ex = block_excl_scan(cnt, warp_sums, tot);  // tile totals <= 8192: the halves never carry
     if (threadIdx.x < 32) {
-        const uint64_t e = keep_all ? 0 : lookback_exclusive(status_tie, tile, tot, 0);
+        const uint64_t e = keep_all ? 0 : lookback_exclusive(status_tie, tile, tot >> 16, 0);
         if (threadIdx.x == 0) s_tie_base = e;
+    } else if (threadIdx.x < 64) {
+        const uint64_t e = lookback_exclusive(status_keep, tile, tot & 0xffffu, 0);
+        if (threadIdx.x == 32) s_keep_base = e;
     }
     __syncthreads();
-    uint64_t tie_rank = s_tie_base + tie_ex;
-    uint32_t keepmask = 0, kept = 0;
+    uint64_t tie_rank = s_tie_base + (ex >> 16);
+    uint64_t pos = s_keep_base + (ex & 0xffffu) + min(tie_rank, quota);
 #pragma unroll
     for (int q = 0; q < CUT_ITEMS; ++q) {
         bool k = false;
         if (b0 + q < n) {
-            if (keep_all) k = true;
-            else if (x[q] > T) k = true;
+            if (keep_all || x[q] > T) k = true;
             else if (x[q] == T) { k = tie_rank < quota; ++tie_rank; }
         }
-        keepmask |= (uint32_t)k << q;
-        kept += k;
-    }
-    const uint32_t keep_ex = block_excl_scan(kept, warp_sums, tot);
-    if (threadIdx.x < 32) {
-        const uint64_t e = lookback_exclusive(status_keep, tile, tot, 0);
-        if (threadIdx.x == 0) s_keep_base = e;
-    }
-    __syncthreads();
-    uint64_t pos = s_keep_base + keep_ex;
-#pragma unroll
-    for (int q = 0; q < CUT_ITEMS; ++q)
-        if (keepmask >> q & 1) {
+        if (k) {
             out_y[pos] = DICT ? (uint64_t)dict_rank_of(dict, x[q] + sk_min) : (sk_max - sk_min) - x[q];
             out_idx[pos] = (uint32_t)(b0 + q);
             ++pos;
         }
+    }
 }
 
 // det policy (ties -> larger canonical key first): keep x > T, plus the score ties whose key is >=

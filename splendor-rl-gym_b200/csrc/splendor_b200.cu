@@ -524,12 +524,16 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
         ++c->launches;
         CK(c, cudaGetLastError());
     }
-    {   // survivors actually written = inclusive prefix published by the last cut tile
-        uint64_t last = 0;
+    {   // survivors actually written, from the inclusive prefixes published by the last cut tile
+        uint64_t last = 0, last_tie = 0;
         CK(c, cudaMemcpyAsync(&last, c->status[2].as<uint64_t>() + (ct - 1), 8, cudaMemcpyDeviceToHost, st));
+        if (!det && !keep_all)
+            CK(c, cudaMemcpyAsync(&last_tie, c->status[1].as<uint64_t>() + (ct - 1), 8, cudaMemcpyDeviceToHost, st));
         CK(c, cudaStreamSynchronize(st));
-        c->d2h_bytes += 8;
-        kept = (int64_t)(last & ((1ull << 62) - 1));
+        c->d2h_bytes += 16;
+        constexpr uint64_t VAL = (1ull << 62) - 1;
+        kept = (int64_t)(last & VAL);  // det: kept states; stable: states above the threshold
+        if (!det && !keep_all) kept += (int64_t)std::min<uint64_t>(last_tie & VAL, c->h_sel->k_rem);
         if (kept > cap_kept) return fail(c, SPL_E_CUDA, "internal: cut kept %lld > capacity %lld", (long long)kept, (long long)cap_kept);
     }
     // y = sk_max - sk in [0, sk_max - sk_min - T], or (dictionary) the score's descending rank in [0, rank_t]
