@@ -75,6 +75,8 @@ enum {
 
 /* tie-break policy of the beam cut `sorted(next_queue, key=h, reverse=True)[:beam]` (:452-456) */
 enum { SPL_TIE_STABLE = 0 /* arrival order, as Python's stable sort */, SPL_TIE_KEY = 1 /* key descending */ };
+/* what makes two speedrun states "the same" for the visited set (spl_set_identity) */
+enum { SPL_IDENT_KEY = 0 /* exact 105-bit (cards, gems) key */, SPL_IDENT_PYHASH = 1 /* the reference's hash((cards, gems)) */ };
 
 typedef struct {
     int32_t device;            /* CUDA device ordinal */
@@ -119,6 +121,18 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out);
 int32_t spl_destroy(spl_ctx *ctx);
 /* forget every visited state (trail = {}), keep the allocation */
 int32_t spl_reset_visited(spl_ctx *ctx, void *stream);
+
+/* Identity of the speedrun solver's visited set (`trail`, src/solver.py:426, :447-449).  SPL_IDENT_KEY
+ * (default): the exact (cards, gems) key.  SPL_IDENT_PYHASH: the reference's own State.hash =
+ * hash((cards, gems)) (src/solver.py:316; State.__eq__ compares only that value, :335-336) -- two states
+ * whose 64-bit CPython hashes collide are merged, first arrival wins, exactly as the reference's dict does.
+ * Applies to solvers created afterwards on this context (speedrun solver only; stage operators and
+ * realistic mode keep their own identities).  SURVEY.md 8(f).3. */
+int32_t spl_set_identity(spl_ctx *ctx, int32_t identity);
+
+/* out[i] = hash((cards, gems)) of keys[i] as CPython computes it (unsigned 64-bit view); device buffers.
+ * Replaces: State.__init__'s `self.hash = hash((self.cards, self.gems))`, src/solver.py:316. */
+int32_t spl_pyhash(spl_ctx *ctx, const spl_key *keys_dev, int64_t n, uint64_t *out_dev, void *stream);
 int32_t spl_visited_count(spl_ctx *ctx, int64_t *n_host);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 int32_t spl_launch_count(spl_ctx *ctx, int64_t *n_host);

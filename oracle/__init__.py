@@ -52,6 +52,10 @@ def lib():
         L.orc_solver_new.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int]
         L.orc_solver_new.restype = C.c_void_p
         L.orc_solver_free.argtypes = [C.c_void_p]
+        L.orc_solver_set_identity.argtypes = [C.c_void_p, C.c_int]
+        L.orc_solver_set_identity.restype = None
+        L.orc_pyhash.argtypes = [C.c_void_p]
+        L.orc_pyhash.restype = C.c_uint64
         L.orc_solver_step.argtypes = [C.c_void_p, C.POINTER(LevelInfo)]
         L.orc_solver_nlevels.argtypes = [C.c_void_p]
         L.orc_solver_level_size.argtypes = [C.c_void_p, C.c_int]
@@ -126,6 +130,17 @@ def expand(state_rec: np.ndarray) -> np.ndarray:
     return out[:n].copy()
 
 
+def pyhash(states: np.ndarray) -> np.ndarray:
+    """hash((cards, gems)) of src/solver.py:316 as an unsigned 64-bit value, per packed state"""
+    states = np.ascontiguousarray(states)
+    out = np.zeros(len(states), np.uint64)
+    base = states.ctypes.data
+    L = lib()
+    for i in range(len(states)):
+        out[i] = L.orc_pyhash(base + i * STATE_DTYPE.itemsize)
+    return out
+
+
 def score(states: np.ndarray, heuristic: str, noise: str = 'const') -> np.ndarray:
     states = np.ascontiguousarray(states)
     out = np.zeros(len(states), np.float64)
@@ -141,13 +156,15 @@ class Solver:
     """Level stepper over the oracle's restatement of State.solve (src/solver.py:390-464)."""
 
     def __init__(self, goal_pts=15, *, use_heuristic=False, heuristic_name='simple', beam_width=300_000,
-                 policy='stable', noise='const', root=None):
+                 policy='stable', noise='const', root=None, identity='key'):
         if root is None:
             root = pack_state((), (0,) * 5, (0,) * 5, 0, 0)
         self._root = np.ascontiguousarray(root)
         self._h = lib().orc_solver_new(self._root.ctypes.data, goal_pts, int(use_heuristic),
                                        HEURISTIC_IDS.get(heuristic_name, 0), beam_width,
                                        POLICY_IDS[policy], NOISE_IDS[noise])
+        if identity != 'key':  # 'pyhash': dedup on the reference's own 64-bit hash((cards, gems))
+            lib().orc_solver_set_identity(self._h, {'key': 0, 'pyhash': 1}[identity])
         self.infos = []
         self.done = False
 

@@ -56,6 +56,8 @@ def _load():
         'spl_create': (i32, [C.POINTER(Config), C.POINTER(vp)]),
         'spl_destroy': (i32, [vp]),
         'spl_reset_visited': (i32, [vp, vp]),
+        'spl_set_identity': (i32, [vp, i32]),
+        'spl_pyhash': (i32, [vp, vp, i64, vp, vp]),
         'spl_visited_count': (i32, [vp, C.POINTER(i64)]),
         'spl_launch_count': (i32, [vp, C.POINTER(i64)]),
         'spl_transfer_bytes': (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),

@@ -74,7 +74,8 @@ struct spl_ctx {
     SelState *d_sel = nullptr, *h_sel = nullptr;
     uint32_t *d_hist = nullptr;
     ScoreDict *d_dict = nullptr;
-    int dict_skip = 0;  // levels left before the dictionary path is tried again after a miss
+    int dict_skip = 0;
+    int identity = IDENT_KEY;  // visited-table identity of the speedrun solver (spl_set_identity)  // levels left before the dictionary path is tried again after a miss
     DevBuf status[3];
     // scratch
     DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2;
@@ -223,8 +224,9 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaMemset(c->d_hist, 0, SEL_BINS * 4));
     CKC(cudaMalloc(&c->d_dict, sizeof(ScoreDict)));
     for (auto &ev : c->ev) CKC(cudaEventCreate(&ev));
-    CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
-    CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
+    CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE, IDENT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
+    CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE, IDENT_PYHASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
+    CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST, IDENT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     uint64_t slots = cfg->table_slots ? cfg->table_slots : (1ull << 22);
     slots = std::min<uint64_t>(slots, c->max_table_bytes / 32);
     slots = std::max<uint64_t>(slots, 1024);
@@ -258,6 +260,24 @@ int32_t spl_reset_visited(spl_ctx *c, void *stream) {
     CK(c, cudaMemsetAsync(c->table, 0, c->cap * 32, (cudaStream_t)stream));
     c->occupied = 0;
     c->epoch = 0;
+    return SPL_OK;
+}
+
+int32_t spl_set_identity(spl_ctx *c, int32_t identity) {
+    if (!c) return SPL_E_INVALID;
+    if (identity != SPL_IDENT_KEY && identity != SPL_IDENT_PYHASH) return fail(c, SPL_E_INVALID, "spl_set_identity: unknown identity %d", identity);
+    c->identity = identity == SPL_IDENT_PYHASH ? IDENT_PYHASH : IDENT_KEY;
+    return SPL_OK;
+}
+
+int32_t spl_pyhash(spl_ctx *c, const spl_key *keys, int64_t n, uint64_t *out, void *stream) {
+    if (!c || n < 0 || (n && (!keys || !out))) return fail(c, SPL_E_INVALID, "spl_pyhash: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return SPL_OK;
+    pyhash_kernel<<<nblk(n), TILE, 0, st>>>(keys, n, out);
+    ++c->launches;
+    CK(c, cudaGetLastError());
     return SPL_OK;
 }
 
@@ -578,7 +598,7 @@ int32_t spl_expand(spl_ctx *c, const spl_key *keys, const uint64_t *aux, int64_t
     if (total > cap) return fail(c, SPL_E_CAPACITY, "spl_expand: %lld successors, capacity %lld", (long long)total, (long long)cap);
     if (total == 0) return SPL_OK;
     CK(c, c->tmp_rec2.ensure((size_t)total * 32, 0, st));
-    expand_kernel<MODE_LIST><<<nblk(n), TILE, sizeof(ExpandSmem2), st>>>(
+    expand_kernel<MODE_LIST, IDENT_KEY><<<nblk(n), TILE, sizeof(ExpandSmem2), st>>>(
         c->tmp_rec.as<Rec>(), n, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
         nullptr, 0, 0, nullptr, c->tmp_rec2.as<Rec>(), 0, c->d_ctr);
     unpack_rec_kernel<<<nblk(total), TILE, 0, st>>>(c->tmp_rec2.as<Rec>(), total, ck, ca, cl);
@@ -600,7 +620,7 @@ int32_t spl_dedup(spl_ctx *c, const spl_key *ck, const uint64_t *ca, int64_t n, 
     uint64_t tag;
     CKS(c, next_epoch(c, tag));
     CK(c, c->cand_slot.ensure((size_t)n * 4, 0, st));
-    probe_list_kernel<<<nblk(n), TILE, 0, st>>>(ck, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+    probe_list_kernel<IDENT_KEY><<<nblk(n), TILE, 0, st>>>(ck, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
     ++c->launches;
     CK(c, cudaGetLastError());
     CKS(c, read_ctr(c, st));
@@ -715,7 +735,7 @@ int32_t spl_expand_rows(spl_ctx *c, const void *front_rows, int64_t n, int64_t r
     *n_out = total;
     if (total > cap) return fail(c, SPL_E_CAPACITY, "spl_expand_rows: %lld successors, capacity %lld", (long long)total, (long long)cap);
     if (total == 0) return SPL_OK;
-    expand_kernel<MODE_LIST><<<nblk(n), TILE, sizeof(ExpandSmem2), st>>>(
+    expand_kernel<MODE_LIST, IDENT_KEY><<<nblk(n), TILE, sizeof(ExpandSmem2), st>>>(
         reinterpret_cast<const Rec *>(front_rows), n, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(),
         (uint32_t)total, nullptr, 0, 0, nullptr, reinterpret_cast<Rec *>(out_rows), rank_base, c->d_ctr);
     ++c->launches;
@@ -789,7 +809,7 @@ int32_t spl_dedup_flags(spl_ctx *c, const spl_key *keys, int64_t n, uint8_t *fla
     uint64_t tag;
     CKS(c, next_epoch(c, tag));
     CK(c, c->cand_slot.ensure((size_t)n * 4, 0, st));
-    probe_list_kernel<<<nblk(n), TILE, 0, st>>>(keys, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+    probe_list_kernel<IDENT_KEY><<<nblk(n), TILE, 0, st>>>(keys, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
     win_flags_kernel<<<nblk(n), TILE, 0, st>>>(c->cand_slot.as<uint32_t>(), c->table, n, flags);
     c->launches += 2;
     CK(c, cudaGetLastError());
@@ -1138,7 +1158,7 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
         CKS(c, next_epoch(c, tag));
         CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
         CKS(c, zero_ctr(c, st));
-        probe_list_kernel<<<nblk(total), TILE, 0, st>>>(c->rkeys.as<spl_key>(), total, c->table, c->cap, tag,
+        probe_list_kernel<IDENT_KEY><<<nblk(total), TILE, 0, st>>>(c->rkeys.as<spl_key>(), total, c->table, c->cap, tag,
                                                         c->cand_slot.as<uint32_t>(), c->d_ctr);
         ++c->launches;
         CK(c, cudaGetLastError());
@@ -1252,8 +1272,12 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
             cudaError_t e = c->cand_slot.ensure(4, 0, st);
             if (e != cudaSuccess) rc = fail(c, SPL_E_NOMEM, "cand_slot alloc");
             else {
-                probe_list_kernel<<<1, TILE, 0, st>>>(reinterpret_cast<const spl_key *>(s->front.p), 1, c->table, c->cap, tag,
-                                                      c->cand_slot.as<uint32_t>(), c->d_ctr);
+                if (c->identity == IDENT_PYHASH)
+                    probe_list_kernel<IDENT_PYHASH><<<1, TILE, 0, st>>>(reinterpret_cast<const spl_key *>(s->front.p), 1, c->table,
+                                                                        c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+                else
+                    probe_list_kernel<IDENT_KEY><<<1, TILE, 0, st>>>(reinterpret_cast<const spl_key *>(s->front.p), 1, c->table,
+                                                                     c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
                 ++c->launches;
                 c->occupied = 1;
             }
@@ -1322,9 +1346,14 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         CKS(c, next_epoch(c, tag));
         CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
         CK(c, cudaEventRecord(c->ev[7], st));
-        expand_kernel<MODE_PROBE><<<nt, TILE, sizeof(ExpandSmem2), st>>>(
-            front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
-            c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
+        if (c->identity == IDENT_PYHASH)
+            expand_kernel<MODE_PROBE, IDENT_PYHASH><<<nt, TILE, sizeof(ExpandSmem2), st>>>(
+                front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
+                c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
+        else
+            expand_kernel<MODE_PROBE, IDENT_KEY><<<nt, TILE, sizeof(ExpandSmem2), st>>>(
+                front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
+                c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
         ++c->launches;
         CK(c, cudaGetLastError());
         CK(c, cudaEventRecord(c->ev[1], st));
@@ -1459,7 +1488,7 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
         rc = next_epoch(c, tag);
         if (rc == SPL_OK) {
             r_root_key_kernel<<<1, 1, 0, st>>>(s->front.as<RRec>(), c->rcfg.as<RConfigDev>(), c->rkeys.as<spl_key>());
-            probe_list_kernel<<<1, TILE, 0, st>>>(c->rkeys.as<spl_key>(), 1, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+            probe_list_kernel<IDENT_KEY><<<1, TILE, 0, st>>>(c->rkeys.as<spl_key>(), 1, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
             c->launches += 2;
             c->occupied = 1;
         }

@@ -11,6 +11,7 @@ from ._lib import Config, Key, LevelInfo, check, lib
 
 HEURISTIC_IDS = {'simple': 0, 'balanced': 1, 'aggressive': 2, 'efficiency': 3, 'competitive': 1}
 TIE_IDS = {'stable': 0, 'det': 1, 'key': 1}
+IDENTITY_IDS = {'key': 0, 'pyhash': 1}
 NOISE_IDS = {'const': 0, 'hash': 1, 'mt': 2}
 
 M64 = (1 << 64) - 1
@@ -165,6 +166,17 @@ class Engine:
     def reset_visited(self):
         check(lib.spl_reset_visited(self._h, self._stream()), self._h)
 
+    def set_identity(self, identity: str = 'key'):
+        """Identity of the speedrun solver's visited set: 'key' = exact (cards, gems); 'pyhash' = the reference's
+        own State.hash = hash((cards, gems)) (src/solver.py:316, :335-336), collisions merge as in its dict."""
+        check(lib.spl_set_identity(self._h, IDENTITY_IDS[identity]), self._h)
+
+    def pyhash(self, keys: torch.Tensor) -> torch.Tensor:
+        """hash((cards, gems)) per key (src/solver.py:316), int64 view of CPython's value"""
+        out = torch.empty(keys.shape[0], dtype=torch.int64, device=self.tdev)
+        check(lib.spl_pyhash(self._h, keys.data_ptr(), keys.shape[0], out.data_ptr(), self._stream()), self._h)
+        return out
+
     def visited_count(self) -> int:
         n = C.c_int64()
         check(lib.spl_visited_count(self._h, C.byref(n)), self._h)
@@ -250,7 +262,8 @@ class Engine:
 
     # -------------------------------------------------------------- fused solver
     def solver(self, root_key: int, root_aux: int, goal_pts: int, use_heuristic: bool, heuristic: str, beam_width: int,
-               tie: str = 'stable', noise: str = 'const', keep_links: bool = True) -> 'LevelSolver':
+               tie: str = 'stable', noise: str = 'const', keep_links: bool = True, identity: str = 'key') -> 'LevelSolver':
+        self.set_identity(identity)
         return LevelSolver(self, root_key, root_aux, goal_pts, use_heuristic, heuristic, beam_width, tie, noise,
                            keep_links)
 

@@ -159,12 +159,16 @@ class State:
         device: int | None = None,
         engine: Engine | None = None,
         stats: list | None = None,
+        identity: str = 'key',
     ) -> list['State']:
         """BFS / beam search on the GPU; same arguments and return value as src/solver.py:390-464.
 
         Extra keyword-only arguments (all optional): `tie_policy` ('stable' | 'det'), `noise`
-        ('const' | 'hash'), `device`, `engine` (a pre-built Engine, e.g. with a larger visited
-        table) and `stats` (a list that receives one dict of counters per level).
+        ('const' | 'hash' | 'mt'), `device`, `engine` (a pre-built Engine, e.g. with a larger visited
+        table), `stats` (a list that receives one dict of counters per level) and `identity`
+        ('key' = exact (cards, gems); 'pyhash' = dedup on the reference's own 64-bit
+        hash((cards, gems)), src/solver.py:316, so that even hash collisions merge as they do there;
+        single GPU only).
         """
         tie_policy = tie_policy or DEFAULT_TIE_POLICY
         noise = noise or DEFAULT_NOISE
@@ -187,6 +191,8 @@ class State:
             # one process per GPU (torchrun): every rank calls solve() collectively; the frontier is
             # sharded by key hash and each level is bit-identical to the single-GPU search
             from .sharded import Comm, CudaBackend, ShardedSolver
+            if identity != 'key':
+                raise ValueError("identity='pyhash' is a single-GPU option")
             sh = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), k, a, goal_pts, use_heuristic, heuristic_name,
                                beam_width, tie_policy, noise)
             for info in sh.run():
@@ -199,7 +205,7 @@ class State:
             for o in ordinals:
                 path.append(path[-1]._successors(eng)[o])
             return path
-        sol = eng.solver(k, a, goal_pts, use_heuristic, heuristic_name, beam_width, tie_policy, noise)
+        sol = eng.solver(k, a, goal_pts, use_heuristic, heuristic_name, beam_width, tie_policy, noise, identity=identity)
         try:
             turn = 0
             max_pts = 0

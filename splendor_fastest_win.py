@@ -23,7 +23,10 @@ def cli():
     ap.add_argument('-q', '--quiet', action='store_true')
     ap.add_argument('--gpu', action='store_true', help='(always on) run the search on the GPU')
     ap.add_argument('--tie', default='stable', choices=['stable', 'det'], help='score tie-break: arrival order | key')
-    ap.add_argument('--noise', default='const', choices=['const', 'hash'], help='deterministic stand-in for randint noise')
+    ap.add_argument('--noise', default='const', choices=['const', 'hash', 'mt'],
+                    help="randint noise: deterministic stand-ins, or 'mt' = Python's own seeded stream")
+    ap.add_argument('--identity', default='key', choices=['key', 'pyhash'],
+                    help="visited-set identity: exact (cards, gems) key | the reference's 64-bit hash((cards, gems))")
     ap.add_argument('--device', type=int, default=None)
     ap.add_argument('--realistic', action='store_true', help='realistic multi-player mode (gem pool, 12 visible cards)')
     ap.add_argument('--players', type=int, default=2, help='number of players for realistic mode')
@@ -62,7 +65,7 @@ def cli():
     try:
         solution = State.newgame().solve(goal_pts=a.goal_pts, use_heuristic=a.use_heuristic, heuristic_name=a.heuristic,
                                          beam_width=a.beam_width, verbose=not a.quiet and rank0, tie_policy=a.tie,
-                                         noise=a.noise, device=local if world > 1 else a.device)
+                                         noise=a.noise, device=local if world > 1 else a.device, identity=a.identity)
         if rank0:
             print('\nSolution:')
             print(f'({", ".join(c.name.title() for c in Color)}) Cards')

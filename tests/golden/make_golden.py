@@ -482,6 +482,22 @@ def main():
         finally:
             ref_solver.randint = NOISE
 
+    if want('pyhash'):
+        # the reference's identity: State.hash = hash((cards, gems)) (src/solver.py:316), as an unsigned 64-bit
+        # value, for a spread of reachable states (shallow BFS states + card-rich states of a beam search)
+        NOISE.mode = 'const'
+        _, lv = stepper(10**9, False, 'simple', 0, max_levels=6, keep_levels=True)
+        sample = [State.newgame()]
+        for states in lv:
+            sample += states[::max(1, len(states) // 300)]
+        _, lv = stepper(15, True, 'aggressive@stable', 400, keep_levels=True)
+        for states in lv[6:]:
+            sample += states[::max(1, len(states) // 60)]
+        rows = [[str(key_int(x)), str(x.hash & M64)] for x in sample]
+        json.dump(dict(note='[canonical 128-bit key, hash((cards, gems)) & (2**64-1)] per state', rows=rows),
+                  open(out / 'pyhash.json', 'w'))
+        print(f'pyhash: {len(rows)} states, max cards {max(len(x.cards) for x in sample)}', file=sys.stderr)
+
     if want('verbose'):
         # stdout of the reference's own solve(verbose=True) (noise const, ties by arrival order)
         import contextlib

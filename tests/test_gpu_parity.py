@@ -420,3 +420,32 @@ def test_table_growth_during_beam_search(golden):
     assert gi['ended'] and gi['table_slots'] > 4096 * 256
     sol.close()
     eng2.close()
+
+
+# ------------------------------------------------------------------ the reference's own identity
+def test_pyhash_kernel_matches_reference(eng, golden):
+    """spl_pyhash == hash((cards, gems)) of the reference (src/solver.py:316) on 2236 reachable states, bit for bit."""
+    rows = golden['pyhash']['rows']
+    keys = np.array([[int(k) & ((1 << 64) - 1), int(k) >> 64] for k, _ in rows], dtype=np.uint64)
+    want = np.array([int(h) for _, h in rows], dtype=np.uint64)
+    dk, _ = eng.to_device(keys, np.zeros(len(rows), np.uint64))
+    assert np.array_equal(_host(eng.pyhash(dk)), want)
+
+
+@pytest.mark.parametrize('use_h,beam,goal', [(True, 20_000, 12), (False, 0, 255)])
+def test_solver_identity_pyhash(eng, use_h, beam, goal):
+    """Visited set keyed by the reference's 64-bit hash: every level equals the oracle run with the same identity
+    (which in turn equals the exact-key run: no collisions at this scale)."""
+    k, a = S.State.newgame().record()
+    sol = eng.solver(k, a, goal, use_h, 'aggressive', beam, 'stable', 'const', identity='pyhash')
+    orc = oracle.Solver(goal, use_heuristic=use_h, heuristic_name='aggressive', beam_width=beam, identity='pyhash')
+    try:
+        for _ in range(7 if not use_h else 99):
+            gi, oi = sol.step(), orc.step()
+            _check_level(sol, orc, gi, oi, None, f'pyhash identity level {gi["level"]}')
+            if gi['ended']:
+                break
+    finally:
+        sol.close()
+        orc.close()
+        eng.set_identity('key')
