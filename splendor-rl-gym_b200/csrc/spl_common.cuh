@@ -2,7 +2,8 @@
 //
 // Data layout in HBM:
 //   frontier record  : 32 B AoS {lo, hi, aux, link}  -> one 256-bit load per parent
-//   visited-table slot: 32 B AoS {lo, hi|tag<<41, ~t, spare}, 32 B aligned = one L2 sector
+//   visited-table bucket: 64 B = one DRAM burst = three slots: sector 0 {lo0, hi0|tag, ~t0 ~t1 ~t2 (u32), spare},
+//                         sector 1 {lo1, hi1|tag, lo2, hi2|tag}
 //   candidate slot id : u32 per generated successor, in (parent rank, ordinal) order
 #pragma once
 #include <cuda_runtime.h>
@@ -50,11 +51,22 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(a) : "l"(p));
     return a;
 }
-// whole 32 B visited-table slot in one request (LDG.E.256.STRONG.GPU): {lo, hi|tag, ~t, spare}
-__device__ __forceinline__ void ld_slot(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &v) {
-    uint64_t spare;
-    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(v), "=l"(spare) : "l"(p));
-    (void)spare;
+// one 32-byte sector of a visited-table bucket in one request (LDG.E.256.STRONG.GPU)
+__device__ __forceinline__ void ld_u64x4_cg(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+// the {lo, hi|tag} words of slot j of bucket B (16-byte aligned: the operand of the 128-bit CAS)
+template <typename T>
+__device__ __forceinline__ T *bucket_key(T *B, int j) { return B + (j ? 2 + 2 * j : 0); }
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
+    uint32_t a;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(a) : "l"(p));
+    return a;
+}
+constexpr int BUCKET_SLOTS = 3;
+// candidate verdict / slot id = bucket << 2 | slot-in-bucket (buckets < 2^30); the slot's ~t word
+__device__ __forceinline__ const uint32_t *slot_tword(const uint64_t *table, uint32_t sid) {
+    return reinterpret_cast<const uint32_t *>(table + ((uint64_t)(sid >> 2) << 3) + 2) + (sid & 3);
 }
 __device__ __forceinline__ void ld_rec(const Rec *p, Rec &r) {  // 256-bit load (LDG.E.256 on sm_100)
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];"
@@ -90,19 +102,8 @@ __device__ __host__ __forceinline__ uint64_t hash_key(uint64_t lo, uint64_t hi) 
     x ^= x >> 32;
     return x;
 }
-// Home slot: always the EVEN slot of a 64-byte pair.  The DRAM access granule on B200 is 64 B
-// (ncu: ~2 sectors read per probe miss), so the first linear-probing step stays in the line
-// that the home probe already fetched.
-#ifndef SPL_PAIR
-#define SPL_PAIR 0   // measured: pairing adds clustering and is 5% slower (profiles/README.md r1b)
-#endif
-__device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t cap) {
-#if SPL_PAIR
-    return __umul64hi(h, cap >> 1) << 1;
-#else
-    return __umul64hi(h, cap);
-#endif
-}
+// home bucket of a key among `nb` buckets
+__device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t nb) { return __umul64hi(h, nb); }
 
 // splitmix64 finaliser over the folded key: noise policy `hash`
 __device__ __host__ __forceinline__ uint64_t mix64(uint64_t lo, uint64_t hi) {

@@ -106,42 +106,69 @@ __device__ __forceinline__ void make_child(const SmemTabs &s, const uint16_t *__
 }
 
 // ------------------------------------------------------------------ visited table probe
-// Returns the slot index the candidate resolved to (new insert, or same-epoch duplicate that may
-// still be the first arrival), or DEAD if the key was inserted in an earlier epoch or an EARLIER
-// arrival of this epoch already holds the slot.  `tinv` = ~t, t = arrival index in this epoch:
-// atomicMax(~t) keeps the FIRST arrival (src/solver.py:447-450) regardless of thread order.
-// `i` is the home slot (slot_of(hash_key())), usually prefetched into L2 a few iterations ago.
-__device__ __forceinline__ uint32_t probe_at(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t i,
+// The table is an array of 64-byte buckets of three slots (one DRAM burst per bucket); buckets are
+// probed linearly, slots inside a bucket in order.  A key is inserted into the first empty slot of
+// its probe sequence with one 128-bit CAS; slots never become empty again, so every later probe of
+// the same key meets that slot before it meets an empty one.
+// Returns the slot id (bucket << 2 | slot) the candidate resolved to (new insert, or same-epoch
+// duplicate that may still be the first arrival), or DEAD if the key was inserted in an earlier epoch
+// or an EARLIER arrival of this epoch already holds the slot.  `tinv` = ~t, t = arrival index in this
+// epoch (< 2^32 - 1): atomicMax(~t) keeps the FIRST arrival (src/solver.py:447-450) regardless of
+// thread order.  `b` is the home bucket (slot_of(hash_key())).
+constexpr uint32_t PROBE_NEXT = 0xFFFFFFFEu;  // slot holds another key: keep probing (not a slot id: slot-in-bucket < 3)
+// one slot of bucket B whose key words were read as (a, h) and whose arrival word was read as v
+// (v may be stale: it only grows, so "v > tinv" stays true once seen)
+__device__ __forceinline__ uint32_t probe_slot(uint64_t *B, uint64_t b, int j, uint64_t a, uint64_t h, uint32_t v,
+                                               uint64_t tag, uint64_t klo, uint64_t khi, uint64_t want_hi,
+                                               uint32_t tinv32, uint32_t &n_new) {
+    unsigned int *tword = reinterpret_cast<unsigned int *>(B + 2) + j;
+    const uint32_t id = (uint32_t)(b << 2) | (uint32_t)j;
+    bool mine = false;
+    if ((a | h) == 0) {  // empty: claim with one 128-bit CAS
+        cas128(bucket_key(B, j), 0, 0, klo, want_hi, a, h);
+        if ((a | h) == 0) {
+            a = klo;
+            h = want_hi;
+            mine = true;
+            ++n_new;
+        }
+        v = 0;  // a competing claim: its arrival word is ordered by the atomicMax below
+    }
+    if (a != klo || (h & HI_KEY_MASK) != khi) return PROBE_NEXT;
+    if (!mine) {
+        if ((h >> TAG_SHIFT) != tag) return DEAD;
+        if (v > tinv32) return DEAD;  // an earlier arrival is already registered (~t only grows)
+    }
+    atomicMax(tword, tinv32);
+    return id;
+}
+// Sector 0 of a bucket = slot 0 and the three arrival words, sector 1 = slots 1 and 2.  At the load
+// factors of a search most keys live in slot 0, so most probes read one 32-byte sector, as a plain
+// one-slot-per-sector table would, while a full bucket still costs a single DRAM burst.
+__device__ __forceinline__ uint32_t probe_at(uint64_t *__restrict__ table, uint64_t nb, uint64_t tag, uint64_t b,
                                              uint64_t klo, uint64_t khi, uint64_t tinv, uint32_t &n_new,
                                              unsigned int *error) {
     const uint64_t want_hi = khi | (tag << TAG_SHIFT);
+    const uint32_t tinv32 = (uint32_t)tinv;
     for (int probes = 0; probes < MAX_PROBE; ++probes) {
-        uint64_t *slot = table + (i << 2);
-        uint64_t a, b, v;
-        ld_slot(slot, a, b, v);
-        if ((a | b) == 0) {  // empty: claim with one 128-bit CAS
-            cas128(slot, 0, 0, klo, want_hi, a, b);
-            if ((a | b) == 0) {
-                atomicMax(reinterpret_cast<unsigned long long *>(slot + 2), (unsigned long long)tinv);
-                ++n_new;
-                return (uint32_t)i;
-            }
-            v = 0;
-        }
-        if (a == klo && (b & HI_KEY_MASK) == khi) {
-            if ((b >> TAG_SHIFT) != tag) return DEAD;
-            if (v > tinv) return DEAD;  // an earlier arrival is already registered (~t only grows)
-            atomicMax(reinterpret_cast<unsigned long long *>(slot + 2), (unsigned long long)tinv);
-            return (uint32_t)i;
-        }
-        if (++i == cap) i = 0;
+        uint64_t *B = table + (b << 3);
+        uint64_t a0, h0, t01, t2, a1, h1, a2, h2;
+        ld_u64x4_cg(B, a0, h0, t01, t2);
+        uint32_t r = probe_slot(B, b, 0, a0, h0, (uint32_t)t01, tag, klo, khi, want_hi, tinv32, n_new);
+        if (r != PROBE_NEXT) return r;
+        ld_u64x4_cg(B + 4, a1, h1, a2, h2);
+        r = probe_slot(B, b, 1, a1, h1, (uint32_t)(t01 >> 32), tag, klo, khi, want_hi, tinv32, n_new);
+        if (r != PROBE_NEXT) return r;
+        r = probe_slot(B, b, 2, a2, h2, (uint32_t)t2, tag, klo, khi, want_hi, tinv32, n_new);
+        if (r != PROBE_NEXT) return r;
+        if (++b == nb) b = 0;
     }
     atomicExch(error, 1u);
     return DEAD;
 }
-__device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, uint64_t cap, uint64_t tag, uint64_t klo,
+__device__ __forceinline__ uint32_t probe_insert(uint64_t *__restrict__ table, uint64_t nb, uint64_t tag, uint64_t klo,
                                                  uint64_t khi, uint64_t tinv, uint32_t &n_new, unsigned int *error) {
-    return probe_at(table, cap, tag, slot_of(hash_key(klo, khi), cap), klo, khi, tinv, n_new, error);
+    return probe_at(table, nb, tag, slot_of(hash_key(klo, khi), nb), klo, khi, tinv, n_new, error);
 }
 
 // ------------------------------------------------------------------ the reference's own identity (optional)
@@ -526,19 +553,18 @@ __global__ void __launch_bounds__(TILE) resolve_kernel(const Rec *__restrict__ f
     const uint32_t nwords = (ncand + 31) >> 5;
     uint32_t mywins = 0;
     for (uint32_t i0 = 0; i0 < ncand; i0 += 4 * TILE) {
-        uint32_t sidx[4];
-        uint64_t v[4];
+        uint32_t sidx[4], v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t i = i0 + k * TILE + threadIdx.x;
             sidx[k] = i < ncand ? cand_slot[c0 + i] : DEAD;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = sidx[k] != DEAD ? ld_cg_u64(table + ((uint64_t)sidx[k] << 2) + 2) : 0;
+        for (int k = 0; k < 4; ++k) v[k] = sidx[k] != DEAD ? ld_cg_u32(slot_tword(table, sidx[k])) : 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t i = i0 + k * TILE + threadIdx.x;
-            const bool win = sidx[k] != DEAD && (~v[k]) == (uint64_t)(c0 + i);
+            const bool win = sidx[k] != DEAD && ~v[k] == c0 + i;
             const uint32_t bal = __ballot_sync(0xffffffffu, win);
             if ((threadIdx.x & 31) == 0 && (i >> 5) < nwords) {
                 S.win[i >> 5] = bal;
@@ -1211,7 +1237,7 @@ __global__ void __launch_bounds__(TILE) win_flags_kernel(const uint32_t *__restr
     const int64_t t = (int64_t)blockIdx.x * TILE + threadIdx.x;
     if (t < n) {
         const uint32_t s = cand_slot[t];
-        flags[t] = s != DEAD && ~ld_cg_u64(table + ((uint64_t)s << 2) + 2) == (uint64_t)t;
+        flags[t] = s != DEAD && ~ld_cg_u32(slot_tword(table, s)) == (uint32_t)t;
     }
 }
 __global__ void __launch_bounds__(TILE) scatter_flags_kernel(const uint8_t *__restrict__ part, const uint32_t *__restrict__ idx,
@@ -1434,19 +1460,21 @@ __global__ void __launch_bounds__(TILE) owner_scatter_kernel(const Rec *__restri
 }
 
 // move every occupied slot of an old table into a larger one (tags preserved)
-__global__ void __launch_bounds__(TILE) rehash_kernel(const uint64_t *__restrict__ old_table, uint64_t old_cap,
-                                                      uint64_t *__restrict__ table, uint64_t cap, Counters *ctr) {
-    const uint64_t s = (uint64_t)blockIdx.x * TILE + threadIdx.x;
-    if (s >= old_cap) return;
-    uint64_t a, b;
-    ld_cg_u64x2(old_table + (s << 2), a, b);
-    if ((a | b) == 0) return;
-    uint64_t i = slot_of(hash_key(a, b & HI_KEY_MASK), cap);
+__global__ void __launch_bounds__(TILE) rehash_kernel(const uint64_t *__restrict__ old_table, uint64_t old_nb,
+                                                      uint64_t *__restrict__ table, uint64_t nb, Counters *ctr) {
+    const uint64_t s = (uint64_t)blockIdx.x * TILE + threadIdx.x;  // one thread per old slot
+    if (s >= old_nb * BUCKET_SLOTS) return;
+    uint64_t a, h;
+    ld_cg_u64x2(bucket_key(old_table + ((s / BUCKET_SLOTS) << 3), (int)(s % BUCKET_SLOTS)), a, h);
+    if ((a | h) == 0) return;
+    uint64_t b = slot_of(hash_key(a, h & HI_KEY_MASK), nb);
     for (int probes = 0; probes < MAX_PROBE; ++probes) {
-        uint64_t oa, ob;
-        cas128(table + (i << 2), 0, 0, a, b, oa, ob);
-        if ((oa | ob) == 0) return;
-        if (++i == cap) i = 0;
+        for (int j = 0; j < BUCKET_SLOTS; ++j) {
+            uint64_t oa, oh;
+            cas128(bucket_key(table + (b << 3), j), 0, 0, a, h, oa, oh);
+            if ((oa | oh) == 0) return;
+        }
+        if (++b == nb) b = 0;
     }
     atomicExch(&ctr->error, 1u);
 }

@@ -60,7 +60,7 @@ struct spl_ctx {
     std::string err;
     // visited table
     uint64_t *table = nullptr;
-    uint64_t cap = 0, max_table_bytes = 0, occupied = 0;
+    uint64_t cap = 0 /* slots = 3 * nb */, nb = 0 /* 64-byte buckets */, max_table_bytes = 0, occupied = 0;
     uint32_t epoch = 0;
     uint64_t chunk_parents = 0;
     // constant tables
@@ -158,12 +158,17 @@ int32_t spl_host_buys(const uint8_t key[5], uint8_t out[90]) {
 }
 
 // ------------------------------------------------------------------ context
+// The table is sized in slots (3 per 64-byte bucket); slot ids are u32 (bucket << 2 | slot), so at most 2^30 buckets.
+constexpr uint64_t MAX_BUCKETS = 1ull << 30;
+static uint64_t buckets_for(uint64_t slots) {
+    return std::min<uint64_t>(std::max<uint64_t>(slots / BUCKET_SLOTS, 16), MAX_BUCKETS);
+}
 static int alloc_table(spl_ctx *c, uint64_t slots, cudaStream_t st) {
-    if (slots >= 0xFFFFFFFEull) slots = 0xFFFFFFFEull;
-    slots &= ~1ull;  // whole 64-byte slot pairs
-    CK(c, cudaMalloc(&c->table, slots * 32));
-    CK(c, cudaMemsetAsync(c->table, 0, slots * 32, st));
-    c->cap = slots;
+    const uint64_t nb = buckets_for(slots);
+    CK(c, cudaMalloc(&c->table, nb * 64));
+    CK(c, cudaMemsetAsync(c->table, 0, nb * 64, st));
+    c->nb = nb;
+    c->cap = nb * BUCKET_SLOTS;
     return SPL_OK;
 }
 
@@ -228,7 +233,7 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE, IDENT_PYHASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST, IDENT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     uint64_t slots = cfg->table_slots ? cfg->table_slots : (1ull << 22);
-    slots = std::min<uint64_t>(slots, c->max_table_bytes / 32);
+    slots = std::min<uint64_t>(slots, c->max_table_bytes / 64 * BUCKET_SLOTS);
     slots = std::max<uint64_t>(slots, 1024);
     if (alloc_table(c, slots, 0) != SPL_OK) {
         g_create_error = c->err;
@@ -257,7 +262,7 @@ int32_t spl_destroy(spl_ctx *c) {
 int32_t spl_reset_visited(spl_ctx *c, void *stream) {
     if (!c) return SPL_E_INVALID;
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaMemsetAsync(c->table, 0, c->cap * 32, (cudaStream_t)stream));
+    CK(c, cudaMemsetAsync(c->table, 0, c->nb * 64, (cudaStream_t)stream));
     c->occupied = 0;
     c->epoch = 0;
     return SPL_OK;
@@ -331,22 +336,21 @@ static int prep_status(spl_ctx *c, int which, size_t ntiles, cudaStream_t st) {
 // grow the visited table so that `need` more inserts keep the load factor <= 0.7 (if memory allows)
 static int ensure_table(spl_ctx *c, uint64_t need, cudaStream_t st) {
     while ((double)(c->occupied + need) > 0.7 * (double)c->cap) {
-        uint64_t ncap = c->cap * 2;
-        if (ncap >= 0xFFFFFFFEull) ncap = 0xFFFFFFFEull;
-        if (ncap * 32 > c->max_table_bytes) ncap = c->max_table_bytes / 32;
-        ncap &= ~1ull;
-        if (ncap <= c->cap + c->cap / 8) break;  // cannot grow meaningfully
+        uint64_t nnb = std::min<uint64_t>(c->nb * 2, MAX_BUCKETS);
+        if (nnb * 64 > c->max_table_bytes) nnb = c->max_table_bytes / 64;
+        if (nnb <= c->nb + c->nb / 8) break;  // cannot grow meaningfully
         uint64_t *nt = nullptr;
-        cudaError_t e = cudaMalloc(&nt, ncap * 32);
+        cudaError_t e = cudaMalloc(&nt, nnb * 64);
         if (e != cudaSuccess) { cudaGetLastError(); break; }
-        CK(c, cudaMemsetAsync(nt, 0, ncap * 32, st));
-        rehash_kernel<<<nblk((int64_t)c->cap), TILE, 0, st>>>(c->table, c->cap, nt, ncap, c->d_ctr);
+        CK(c, cudaMemsetAsync(nt, 0, nnb * 64, st));
+        rehash_kernel<<<nblk((int64_t)c->cap), TILE, 0, st>>>(c->table, c->nb, nt, nnb, c->d_ctr);
         ++c->launches;
         CK(c, cudaGetLastError());
         CK(c, cudaStreamSynchronize(st));
         cudaFree(c->table);
         c->table = nt;
-        c->cap = ncap;
+        c->nb = nnb;
+        c->cap = nnb * BUCKET_SLOTS;
     }
     if (c->occupied + need / 8 > c->cap - c->cap / 16)
         return fail(c, SPL_E_TABLE_FULL, "visited table full: %llu occupied + %llu candidates vs %llu slots (max_table_bytes=%llu)",
@@ -620,7 +624,7 @@ int32_t spl_dedup(spl_ctx *c, const spl_key *ck, const uint64_t *ca, int64_t n, 
     uint64_t tag;
     CKS(c, next_epoch(c, tag));
     CK(c, c->cand_slot.ensure((size_t)n * 4, 0, st));
-    probe_list_kernel<IDENT_KEY><<<nblk(n), TILE, 0, st>>>(ck, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+    probe_list_kernel<IDENT_KEY><<<nblk(n), TILE, 0, st>>>(ck, n, c->table, c->nb, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
     ++c->launches;
     CK(c, cudaGetLastError());
     CKS(c, read_ctr(c, st));
@@ -809,7 +813,7 @@ int32_t spl_dedup_flags(spl_ctx *c, const spl_key *keys, int64_t n, uint8_t *fla
     uint64_t tag;
     CKS(c, next_epoch(c, tag));
     CK(c, c->cand_slot.ensure((size_t)n * 4, 0, st));
-    probe_list_kernel<IDENT_KEY><<<nblk(n), TILE, 0, st>>>(keys, n, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+    probe_list_kernel<IDENT_KEY><<<nblk(n), TILE, 0, st>>>(keys, n, c->table, c->nb, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
     win_flags_kernel<<<nblk(n), TILE, 0, st>>>(c->cand_slot.as<uint32_t>(), c->table, n, flags);
     c->launches += 2;
     CK(c, cudaGetLastError());
@@ -1158,7 +1162,7 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
         CKS(c, next_epoch(c, tag));
         CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
         CKS(c, zero_ctr(c, st));
-        probe_list_kernel<IDENT_KEY><<<nblk(total), TILE, 0, st>>>(c->rkeys.as<spl_key>(), total, c->table, c->cap, tag,
+        probe_list_kernel<IDENT_KEY><<<nblk(total), TILE, 0, st>>>(c->rkeys.as<spl_key>(), total, c->table, c->nb, tag,
                                                         c->cand_slot.as<uint32_t>(), c->d_ctr);
         ++c->launches;
         CK(c, cudaGetLastError());
@@ -1274,10 +1278,10 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
             else {
                 if (c->identity == IDENT_PYHASH)
                     probe_list_kernel<IDENT_PYHASH><<<1, TILE, 0, st>>>(reinterpret_cast<const spl_key *>(s->front.p), 1, c->table,
-                                                                        c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+                                                                        c->nb, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
                 else
                     probe_list_kernel<IDENT_KEY><<<1, TILE, 0, st>>>(reinterpret_cast<const spl_key *>(s->front.p), 1, c->table,
-                                                                     c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+                                                                     c->nb, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
                 ++c->launches;
                 c->occupied = 1;
             }
@@ -1349,11 +1353,11 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         if (c->identity == IDENT_PYHASH)
             expand_kernel<MODE_PROBE, IDENT_PYHASH><<<nt, TILE, sizeof(ExpandSmem2), st>>>(
                 front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
-                c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
+                c->table, c->nb, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
         else
             expand_kernel<MODE_PROBE, IDENT_KEY><<<nt, TILE, sizeof(ExpandSmem2), st>>>(
                 front + p0, np, c->d_tabs, c->d_takes_idx, c->d_takes_edges, c->off.as<uint32_t>(), (uint32_t)total,
-                c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
+                c->table, c->nb, tag, c->cand_slot.as<uint32_t>(), nullptr, p0, c->d_ctr);
         ++c->launches;
         CK(c, cudaGetLastError());
         CK(c, cudaEventRecord(c->ev[1], st));
@@ -1488,7 +1492,7 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
         rc = next_epoch(c, tag);
         if (rc == SPL_OK) {
             r_root_key_kernel<<<1, 1, 0, st>>>(s->front.as<RRec>(), c->rcfg.as<RConfigDev>(), c->rkeys.as<spl_key>());
-            probe_list_kernel<IDENT_KEY><<<1, TILE, 0, st>>>(c->rkeys.as<spl_key>(), 1, c->table, c->cap, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
+            probe_list_kernel<IDENT_KEY><<<1, TILE, 0, st>>>(c->rkeys.as<spl_key>(), 1, c->table, c->nb, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
             c->launches += 2;
             c->occupied = 1;
         }
