@@ -146,10 +146,10 @@ def run_b200(a):
         if a.beam == 30_000_000:  # default: keep the per-GPU queue fixed (weak scaling)
             a.beam = SHARDED_BEAM_PER_GPU * world
     # visited table sized for the whole search up front (about 85 visited states per beam slot at
-    # goal 15) so the timed region never rehashes; capped by the 32-bit slot index.
-    # Capped at 2.2 G slots (70 GB): beyond ~75 GB the random probes fall out of the GPU's TLB reach and
-    # every probe pays a page walk (measured: 3.48 G slots -> 626 ms per solve, 2.2 G slots -> 394 ms).
-    slots = int(min(2_200_000_000, max(1 << 22, a.beam * 72 / 0.62 / world)))
+    # goal 15) so the timed region never rehashes.  Three slots per 64-byte bucket; capped at
+    # 2^30 buckets = 3.22 G slots = 68.7 GB (u32 slot ids), which also keeps the table inside the GPU's TLB
+    # reach: beyond ~75 GB every random probe pays a page walk (profiles/README.md, r1c).
+    slots = int(min(3 << 30, max(1 << 22, a.beam * 72 / 0.62 / world)))
     eng = S.Engine(local, table_slots=slots, max_table_bytes=int(150e9))
     k, aux = S.State.newgame().record()
     comm = Comm(eng.tdev)
@@ -242,7 +242,7 @@ def run_b200(a):
             'config': {'workload': f'C3 (BASELINE configs[2]): speedrun goal {a.goal} -u -H {a.heuristic}, beam {a.beam} '
                                    f'(= {a.beam // world} per GPU), noise={a.noise}, ties={a.tie}; frontier sharded by key hash, '
                                    f'NCCL all-to-all routing; one step = one full solve',
-                       'l2': 'working set (visited table %.1f GB per GPU) >> 126 MB L2; no flush needed' % (slots * 32 / 1e9),
+                       'l2': 'working set (visited table %.1f GB per GPU) >> 126 MB L2; no flush needed' % (slots // 3 * 64 / 1e9),
                        'beam': a.beam, 'goal': a.goal, 'heuristic': a.heuristic, 'parallelism': f'hash-sharded x{world}'},
             'time_to_solve_goal15_s': ms / a.steps * 1e-3, 'levels': len(infos),
             'expanded_per_step': sum(i['expanded'] for i in lv), 'generated_per_step': sum(i['generated'] for i in lv),
@@ -287,7 +287,7 @@ def run_b200(a):
         'data': 'synthetic',
         'config': {'workload': f'C3 (BASELINE configs[2]): speedrun goal {a.goal} -u -H {a.heuristic}, beam {a.beam}, '
                                f'noise={a.noise}, ties={a.tie}; one step = one full solve from the root state',
-                   'l2': 'working set (visited table %.1f GB) >> 126 MB L2; no flush needed' % (slots * 32 / 1e9),
+                   'l2': 'working set (visited table %.1f GB) >> 126 MB L2; no flush needed' % (slots // 3 * 64 / 1e9),
                    'beam': a.beam, 'goal': a.goal, 'heuristic': a.heuristic, 'parallelism': 'single GPU, fused expand+probe kernels'},
         'time_to_solve_goal15_s': ms / a.steps * 1e-3,
         'generated_per_s': float(gen) * a.steps / (ms * 1e-3) if world == 1 else None,

@@ -19,7 +19,7 @@ ap.add_argument('--chunk', type=int, default=0)
 ap.add_argument('--reps', type=int, default=2)
 a = ap.parse_args()
 
-slots = a.slots or max(1 << 22, int(a.beam * 110 / 0.6))
+slots = a.slots or min(3 << 30, max(1 << 22, int(a.beam * 110 / 0.6)))
 eng = S.Engine(0, table_slots=slots, chunk_parents=a.chunk)
 k, aux = S.State.newgame().record()
 for rep in range(a.reps):
