@@ -74,7 +74,10 @@ enum {
 };
 
 /* tie-break policy of the beam cut `sorted(next_queue, key=h, reverse=True)[:beam]` (:452-456) */
-enum { SPL_TIE_STABLE = 0 /* arrival order, as Python's stable sort */, SPL_TIE_KEY = 1 /* key descending */ };
+enum { SPL_TIE_STABLE = 0 /* arrival order, as Python's stable sort */, SPL_TIE_KEY = 1 /* key descending */,
+       /* spl_dtopk_cut only: threshold by key as SPL_TIE_KEY, and the caller guarantees that the local keys are already in
+        * descending order by index (the sharded driver's arrival keys), so the local rank sort orders by score alone */
+       SPL_TIE_KEY_ORDERED = 2 };
 /* what makes two speedrun states "the same" for the visited set (spl_set_identity) */
 enum { SPL_IDENT_KEY = 0 /* exact 105-bit (cards, gems) key */, SPL_IDENT_PYHASH = 1 /* the reference's hash((cards, gems)) */ };
 

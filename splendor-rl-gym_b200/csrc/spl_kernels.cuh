@@ -1134,6 +1134,18 @@ __global__ void __launch_bounds__(TILE) sort_scatter_kernel(const uint64_t *__re
     }
 }
 
+// inverted key words of the kept elements in their final order (SPL_TIE_KEY_ORDERED: the sort moved only (y, idx))
+__global__ void __launch_bounds__(TILE) key_words_kernel(const uint32_t *__restrict__ idx, int64_t n,
+                                                         const uint64_t *__restrict__ kb, int ks,
+                                                         uint64_t *__restrict__ klo, uint64_t *__restrict__ khi) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i < n) {
+        const uint64_t s = idx[i];
+        klo[i] = ~kb[s * ks];
+        khi[i] = ~kb[s * ks + 1] & HI_KEY_MASK;
+    }
+}
+
 // frontier[rank] = uniq[idx[rank]]
 __global__ void __launch_bounds__(TILE) gather_rec_kernel(const Rec *__restrict__ src, const uint32_t *__restrict__ idx,
                                                           int64_t n, Rec *__restrict__ dst) {

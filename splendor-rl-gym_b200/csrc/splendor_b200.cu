@@ -533,9 +533,11 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
                                                         c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
         ++c->launches;
         CK(c, cudaGetLastError());
-        CKS(c, read_ctr(c, st));
-        vary_lo = c->h_ctr->key_or[0] ^ c->h_ctr->key_and[0];
-        vary_hi = (c->h_ctr->key_or[1] ^ c->h_ctr->key_and[1]) & HI_KEY_MASK;
+        if (det == 1) {  // which key bits vary among the survivors (constant digits need no sort pass)
+            CKS(c, read_ctr(c, st));
+            vary_lo = c->h_ctr->key_or[0] ^ c->h_ctr->key_and[0];
+            vary_hi = (c->h_ctr->key_or[1] ^ c->h_ctr->key_and[1]) & HI_KEY_MASK;
+        }
     } else {
         if (use_dict)
             cut_kernel<true><<<ct, TILE, 0, st>>>(sk, n, sk_min, sk_max, keep_all, c->d_sel, c->d_dict, c->y[0].as<uint64_t>(),
@@ -568,16 +570,22 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
         const size_t msz = (size_t)SORT_BINS * nt;
         CK(c, c->matrix.ensure(msz * 4, 0, st));
         CK(c, c->matrix2.ensure(msz * 4, 0, st));
-        if (det) {  // least significant first: key.lo, key.hi, then the score
+        if (det == 1) {  // least significant first: key.lo, key.hi, then the score
             for (int shift = 0; shift < 64; shift += SORT_BITS)
                 if ((vary_lo >> shift) & 0xff) { CKS(c, sort_pass(c, 1, cur, c->kl[cur].as<uint64_t>(), kept, shift, nt, msz, st)); cur ^= 1; }
             for (int shift = 0; shift < 41; shift += SORT_BITS)
                 if ((vary_hi >> shift) & 0xff) { CKS(c, sort_pass(c, 1, cur, c->kh[cur].as<uint64_t>(), kept, shift, nt, msz, st)); cur ^= 1; }
         }
         for (int shift = 0; shift < nbits; shift += SORT_BITS) {
-            CKS(c, sort_pass(c, det, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
+            CKS(c, sort_pass(c, det == 1, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
             cur ^= 1;
         }
+    }
+    if (det == 2 && kept > 0) {  // keys were in rank order already: the stable score sort kept them so; rebuild the key words
+        key_words_kernel<<<nblk(kept), TILE, 0, st>>>(c->idx[cur].as<uint32_t>(), kept, kb, ks, c->kl[cur].as<uint64_t>(),
+                                                       c->kh[cur].as<uint64_t>());
+        ++c->launches;
+        CK(c, cudaGetLastError());
     }
     *which = cur;
     *kept_out = kept;
@@ -953,7 +961,7 @@ int32_t spl_dtopk_cut(spl_ctx *c, int32_t tie_policy, int32_t keep_all, int32_t 
     const int64_t n = c->dtopk_n;
     *kept_host = 0;
     if (n == 0) return SPL_OK;
-    const int det = tie_policy == SPL_TIE_KEY;
+    const int det = tie_policy == SPL_TIE_KEY ? 1 : tie_policy == SPL_TIE_KEY_ORDERED ? 2 : 0;
     if (det && !c->dtopk_recs) return fail(c, SPL_E_STATE, "spl_dtopk_cut: det policy needs keys in spl_dtopk_begin");
     int which = 0;
     int64_t kept = 0;

@@ -10,7 +10,7 @@ import torch
 from ._lib import Config, Key, LevelInfo, check, lib
 
 HEURISTIC_IDS = {'simple': 0, 'balanced': 1, 'aggressive': 2, 'efficiency': 3, 'competitive': 1}
-TIE_IDS = {'stable': 0, 'det': 1, 'key': 1}
+TIE_IDS = {'stable': 0, 'det': 1, 'key': 1, 'det_ordered': 2}
 IDENTITY_IDS = {'key': 0, 'pyhash': 1}
 NOISE_IDS = {'const': 0, 'hash': 1, 'mt': 2}
 

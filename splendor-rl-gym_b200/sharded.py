@@ -212,7 +212,7 @@ class CudaBackend:
         check(lib.spl_dtopk_set(self.eng._h, (C.c_uint64 * 6)(*state), self.eng._stream()), self.eng._h)
 
     def dtopk_cut(self, tie, keep_all, all_ties, smin, smax, n):
-        det = tie == 'det'
+        det = tie in ('det', 'det_ordered')
         idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
         y = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
         kl = torch.empty(max(n, 1) if det else 1, dtype=torch.int64, device=self.device)
@@ -467,7 +467,8 @@ class ShardedSolver:
                         first = False
                         top = shift
         t0 = _tick('bc_select', t0)
-        idx, y, kl, kh = b.dtopk_cut('det', keep_all, all_ties, smin, smax, u_local)
+        # stable: the synthetic arrival keys fall with the local index, so the local sort only needs the score
+        idx, y, kl, kh = b.dtopk_cut('det' if self.tie == 'det' else 'det_ordered', keep_all, all_ties, smin, smax, u_local)
         t0 = _tick('bc_cut_sort', t0)
         # global rank of every local survivor: local index + #smaller composites on the other ranks
         k_local = idx.shape[0]

@@ -164,12 +164,12 @@ class FakeBackend:
     def dtopk_cut(self, tie, keep_all, all_ties, smin, smax, n):
         if n == 0:
             e = torch.empty(0, dtype=torch.int64)
-            return e, e, (e if tie == 'det' else None), (e if tie == 'det' else None)
+            return e, e, (e if tie != 'stable' else None), (e if tie != 'stable' else None)
         x = self.sk - np.uint64(smin)
         T = np.uint64(self.sel[0])
         if keep_all:
             keep = np.ones(n, bool)
-        elif tie == 'det':
+        elif tie in ('det', 'det_ordered'):
             keep = x > T
             t = x == T
             if all_ties:
@@ -183,9 +183,15 @@ class FakeBackend:
             keep[ties[:self.sel[1]]] = True
         idx = np.nonzero(keep)[0]
         y = np.uint64(smax - smin) - x[idx]
-        if tie == 'det':
+        if tie in ('det', 'det_ordered'):
             kl, kh = ~self.keys[idx, 0], ~self.keys[idx, 1] & np.uint64((1 << 41) - 1)
             order = np.lexsort((kl, kh, y))
+            if tie == 'det_ordered':
+                # SPL_TIE_KEY_ORDERED: the device sorts by score only (stable) and relies on the caller's promise that
+                # the keys already fall with the index -- check the promise, then do what the device does
+                stable = np.argsort(y, kind='stable')
+                assert np.array_equal(order, stable), 'det_ordered: local keys are not in descending order by index'
+                order = stable
             f = lambda a: torch.from_numpy(a[order].view(np.int64).copy())  # noqa: E731
             return torch.from_numpy(idx[order].astype(np.int64)), f(y), f(kl), f(kh)
         order = np.argsort(y, kind='stable')
