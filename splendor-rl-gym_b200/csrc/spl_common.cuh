@@ -46,11 +46,6 @@ struct ScoreLuts {  // x ** e for every integer argument the heuristics can see 
 __device__ __forceinline__ void ld_cg_u64x2(const uint64_t *p, uint64_t &a, uint64_t &b) {
     asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
-__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
-    uint64_t a;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(a) : "l"(p));
-    return a;
-}
 // one 32-byte sector of a visited-table bucket in one request (LDG.E.256.STRONG.GPU)
 __device__ __forceinline__ void ld_u64x4_cg(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
     asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
