@@ -84,7 +84,8 @@ enum { SPL_IDENT_KEY = 0 /* exact 105-bit (cards, gems) key */, SPL_IDENT_PYHASH
 typedef struct {
     int32_t device;            /* CUDA device ordinal */
     int32_t reserved0;
-    uint64_t table_slots;      /* initial visited-table capacity in 32-byte slots (0 = default 2^22) */
+    uint64_t table_slots;      /* initial visited-table capacity in slots: three per 64-byte bucket, at most
+                                * 3 * 2^30 (0 = default 2^22) */
     uint64_t max_table_bytes;  /* growth ceiling for the visited table (0 = 60% of free device memory) */
     uint64_t chunk_parents;    /* parents expanded per launch pair (0 = default 4 Mi; max 16 Mi) */
 } spl_config;
