@@ -148,3 +148,18 @@ def test_buys_cache_files_are_reference_compatible(tmp_path, golden):
     export_buys_to_txt(tmp_path / 'buys.txt')
     first = open(tmp_path / 'buys.txt').readline()
     assert first == '(0, 0, 0, 0, 0): ()\n'
+
+
+def test_python_ids_match_header_enums():
+    """The name -> id tables of the host mirror are the enum values include/splendor_b200.h declares."""
+    from splendor_rl_gym_b200 import engine
+    header = (ROOT / 'include' / 'splendor_b200.h').read_text()
+    enum = {k: int(v) for k, v in re.findall(r'\b(SPL_[A-Z_]+)\s*=\s*(-?\d+)', header)}
+    assert engine.HEURISTIC_IDS == {'simple': enum['SPL_H_SIMPLE'], 'balanced': enum['SPL_H_BALANCED'],
+                                    'aggressive': enum['SPL_H_AGGRESSIVE'], 'efficiency': enum['SPL_H_EFFICIENCY'],
+                                    'competitive': enum['SPL_H_BALANCED']}  # alias, src/solver.py:289-296
+    assert engine.NOISE_IDS == {'const': enum['SPL_NOISE_CONST'], 'hash': enum['SPL_NOISE_HASH'],
+                                'mt': enum['SPL_NOISE_EXTERNAL']}
+    assert engine.TIE_IDS == {'stable': enum['SPL_TIE_STABLE'], 'det': enum['SPL_TIE_KEY'], 'key': enum['SPL_TIE_KEY'],
+                              'det_ordered': enum['SPL_TIE_KEY_ORDERED']}
+    assert engine.IDENTITY_IDS == {'key': enum['SPL_IDENT_KEY'], 'pyhash': enum['SPL_IDENT_PYHASH']}
