@@ -886,7 +886,10 @@ __global__ void __launch_bounds__(1024) dict_rank_kernel(ScoreDict *d, uint64_t 
 // arrival order, src/solver.py:453).  Emits (y = sk_max - sk, src index) pairs for the rank sort.
 // status_keep carries the running count of elements ABOVE the threshold, status_tie the running count
 // of ties: survivors in total = above + min(ties, quota) (read back by the host from the last tile).
-constexpr int CUT_ITEMS = 32;  // 8192 elements per tile: 4x fewer look-back hops than 8 (0.30 -> see profiles)
+#ifndef SPL_CUT_ITEMS
+#define SPL_CUT_ITEMS 32
+#endif
+constexpr int CUT_ITEMS = SPL_CUT_ITEMS;  // 8192 elements per tile (measured: 16 items per thread is no faster, 8 is slower)
 // DICT: y = descending rank of the score among the level's distinct scores (ScoreDict)
 template <bool DICT>
 __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ sk, int64_t n, uint64_t sk_min,
