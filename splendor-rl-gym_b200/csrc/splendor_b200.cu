@@ -86,6 +86,8 @@ struct spl_ctx {
     long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     int64_t dtopk_n = 0;       // distributed top-k: elements staged by spl_dtopk_begin
     int64_t route_n = -1;      // candidates of the last spl_route_keys (its permutation lives in idx[1])
+    const void *active = nullptr;  // the live spl_solver: it owns the visited set, the pool buffers and the scratch
+    bool rcfg_dirty = false;       // a stage operator re-uploaded the realistic config since the live solver's upload
     bool dtopk_recs = false;
     const uint64_t *dtopk_keys = nullptr;  // caller-owned [n][2] key array of the distributed top-k
 };
@@ -99,6 +101,11 @@ static int fail(spl_ctx *c, int code, const char *fmt, ...) {
     if (c) c->err = buf; else g_create_error = buf;
     return code;
 }
+// stage operators that rewrite the visited set / identity must not run under a live solver
+#define NO_LIVE_SOLVER(c, what)                                                                                   \
+    do {                                                                                                          \
+        if ((c)->active) return fail(c, SPL_E_STATE, what ": a solver is open on this context (destroy it first)"); \
+    } while (0)
 #define CK(c, call)                                                                             \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \
@@ -259,18 +266,24 @@ int32_t spl_destroy(spl_ctx *c) {
     return SPL_OK;
 }
 
-int32_t spl_reset_visited(spl_ctx *c, void *stream) {
-    if (!c) return SPL_E_INVALID;
+static int reset_visited(spl_ctx *c, cudaStream_t st) {
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaMemsetAsync(c->table, 0, c->nb * 64, (cudaStream_t)stream));
+    CK(c, cudaMemsetAsync(c->table, 0, c->nb * 64, st));
     c->occupied = 0;
     c->epoch = 0;
     return SPL_OK;
 }
 
+int32_t spl_reset_visited(spl_ctx *c, void *stream) {
+    if (!c) return SPL_E_INVALID;
+    NO_LIVE_SOLVER(c, "spl_reset_visited");
+    return reset_visited(c, (cudaStream_t)stream);
+}
+
 int32_t spl_set_identity(spl_ctx *c, int32_t identity) {
     if (!c) return SPL_E_INVALID;
     if (identity != SPL_IDENT_KEY && identity != SPL_IDENT_PYHASH) return fail(c, SPL_E_INVALID, "spl_set_identity: unknown identity %d", identity);
+    NO_LIVE_SOLVER(c, "spl_set_identity");
     c->identity = identity == SPL_IDENT_PYHASH ? IDENT_PYHASH : IDENT_KEY;
     return SPL_OK;
 }
@@ -346,7 +359,13 @@ static int ensure_table(spl_ctx *c, uint64_t need, cudaStream_t st) {
         rehash_kernel<<<nblk((int64_t)c->cap), TILE, 0, st>>>(c->table, c->nb, nt, nnb, c->d_ctr);
         ++c->launches;
         CK(c, cudaGetLastError());
+        unsigned int rehash_err = 0;  // read the flag now: callers zero the counters before their own launches
+        CK(c, cudaMemcpyAsync(&rehash_err, &c->d_ctr->error, 4, cudaMemcpyDeviceToHost, st));
         CK(c, cudaStreamSynchronize(st));
+        if (rehash_err) {
+            cudaFree(nt);
+            return fail(c, SPL_E_TABLE_FULL, "rehash into %llu buckets overflowed a probe sequence", (unsigned long long)nnb);
+        }
         cudaFree(c->table);
         c->table = nt;
         c->nb = nnb;
@@ -623,6 +642,7 @@ int32_t spl_expand(spl_ctx *c, const spl_key *keys, const uint64_t *aux, int64_t
 int32_t spl_dedup(spl_ctx *c, const spl_key *ck, const uint64_t *ca, int64_t n, spl_key *uk, uint64_t *ua, int64_t *usrc,
                   int64_t *n_out, void *stream) {
     if (!c || !n_out || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dedup: bad arguments");
+    NO_LIVE_SOLVER(c, "spl_dedup");
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
     *n_out = 0;
@@ -813,6 +833,7 @@ int32_t spl_route_keys(spl_ctx *c, const void *cand_rows, int64_t n, int32_t n_r
 
 int32_t spl_dedup_flags(spl_ctx *c, const spl_key *keys, int64_t n, uint8_t *flags, void *stream) {
     if (!c || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dedup_flags: bad arguments");
+    NO_LIVE_SOLVER(c, "spl_dedup_flags");
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, cudaSetDevice(c->device));
     if (n == 0) return SPL_OK;
@@ -1014,6 +1035,7 @@ struct spl_solver {
     std::vector<DevBuf *> links;   // per level: link column of the queue (device, 8 B per state)
     std::vector<int64_t> level_n;
     ~spl_solver() {
+        if (c->active == this) c->active = nullptr;
         c->pool_front.swap(front);
         c->pool_uniq.swap(uniq);
         for (auto *b : links) c->pool_links.push_back(b);
@@ -1060,22 +1082,20 @@ static int speedrun_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t 
         info->ms_select = t;  // select + cut + sort
         cudaEventElapsedTime(&t, c->ev[5], c->ev[6]);
         info->ms_sort = t;    // gather into rank order
-    } else {
+    } else if (kept > 0) {
         s->front.swap(s->uniq);
     }
-    s->n_front = kept;
-    s->level += 1;
     info->kept = kept;
     info->visited = (int64_t)c->occupied;
     info->table_slots = c->cap;
-    if (kept == 0) {  // frontier exhausted: `puzzle` is the last dequeued state (src/solver.py:438,459)
-        s->ended = true;
+    if (kept == 0) {  // frontier exhausted: `puzzle` is the last dequeued state (src/solver.py:438,459);
+        s->ended = true;  // s->front still holds the level that was just expanded
         s->goal_rank = n - 1;
-        s->n_front = n;
-        s->level -= 1;
         info->ended = 1;
         return SPL_OK;
     }
+    s->n_front = kept;
+    s->level += 1;
     CKS(c, save_links(s, st));
     CK(c, cudaStreamSynchronize(st));
     return SPL_OK;
@@ -1101,6 +1121,7 @@ static int upload_rconfig(spl_ctx *c, const spl_rconfig *cfg, cudaStream_t st) {
         h.card[i] = T.dev.card[i];
     }
     CK(c, c->rcfg.ensure(sizeof h, 0, st));
+    c->rcfg_dirty = true;
     CK(c, cudaMemcpyAsync(c->rcfg.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
     CK(c, cudaStreamSynchronize(st));  // h is a stack object
     c->h2d_bytes += sizeof h;
@@ -1142,17 +1163,21 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
     info->goal_rank = -1;
     const int64_t n = s->n_front;
     const RRec *front = s->front.as<RRec>();
+    if (c->rcfg_dirty) {  // spl_rscore / spl_rexpand / spl_rmaxpts ran with their own GameConfig in between
+        CKS(c, upload_rconfig(c, &s->rcfg, st));
+        c->rcfg_dirty = false;
+    }
     // game over on dequeue (src/solver.py:827-829)
     CKS(c, zero_ctr(c, st));
     r_goal_kernel<<<nblk(n), TILE, 0, st>>>(front, n, c->rcfg.as<RConfigDev>(), c->d_ctr);
     ++c->launches;
     CK(c, cudaGetLastError());
     CKS(c, read_ctr(c, st));
-    if (c->h_ctr->goal_rank != 0x7fffffffffffffffll || s->level > 1000) {  // turn limit, :849-852
+    if (c->h_ctr->goal_rank != 0x7fffffffffffffffll) {
         s->ended = true;
-        s->goal_rank = c->h_ctr->goal_rank != 0x7fffffffffffffffll ? c->h_ctr->goal_rank : n - 1;
+        s->goal_rank = c->h_ctr->goal_rank;
         info->ended = 1;
-        info->goal_rank = c->h_ctr->goal_rank != 0x7fffffffffffffffll ? s->goal_rank : -1;
+        info->goal_rank = s->goal_rank;
         info->visited = (int64_t)c->occupied;
         info->table_slots = c->cap;
         return SPL_OK;
@@ -1225,9 +1250,11 @@ static int realistic_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t
         const uint64_t smin = c->h_ctr->sk_min, smax = c->h_ctr->sk_max;
         int which = 0;
         CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), nullptr, n_new, s->beam, smin, smax, 0, &which, &kept, st));
-        CK(c, s->front.ensure((size_t)kept * 96, 0, st));
-        r_gather_kernel<uint32_t><<<nblk(kept), TILE, 0, st>>>(s->uniq.as<RRec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<RRec>());
-        ++c->launches;
+        if (s->level < 1000) {  // at the turn limit the queue just expanded stays in place (see below)
+            CK(c, s->front.ensure((size_t)kept * 96, 0, st));
+            r_gather_kernel<uint32_t><<<nblk(kept), TILE, 0, st>>>(s->uniq.as<RRec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<RRec>());
+            ++c->launches;
+        }
         CK(c, cudaGetLastError());
         CK(c, cudaEventRecord(c->ev[3], st));
         CK(c, cudaStreamSynchronize(st));
@@ -1238,7 +1265,9 @@ static int realistic_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t
     info->kept = kept;
     info->visited = (int64_t)c->occupied;
     info->table_slots = c->cap;
-    if (kept == 0) {  // queue exhausted: `puzzle` is the last dequeued state
+    // queue exhausted, or the turn limit: the reference leaves its loop after the iteration with turn == 1000
+    // (src/solver.py:846-852), so `puzzle` is the last state dequeued from THAT queue and the path has 1001 states
+    if (kept == 0 || s->level >= 1000) {
         s->ended = true;
         s->goal_rank = n - 1;
         info->ended = 1;
@@ -1260,6 +1289,7 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
     if (use_h && beam < 1) return fail(c, SPL_E_INVALID, "spl_solver_create: beam_width must be >= 1");
     if (use_h && tie != SPL_TIE_STABLE && tie != SPL_TIE_KEY) return fail(c, SPL_E_INVALID, "spl_solver_create: unknown tie policy %d", tie);
     if (noise < 0 || noise > SPL_NOISE_EXTERNAL) return fail(c, SPL_E_INVALID, "spl_solver_create: unknown noise policy %d", noise);
+    NO_LIVE_SOLVER(c, "spl_solver_create");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t st = 0;
     spl_solver *s = new spl_solver();
@@ -1268,7 +1298,7 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
     s->front.swap(c->pool_front);
     s->uniq.swap(c->pool_uniq);
     std::sort(c->pool_links.begin(), c->pool_links.end(), [](DevBuf *a, DevBuf *b) { return a->cap > b->cap; });
-    int rc = spl_reset_visited(c, st);
+    int rc = reset_visited(c, st);
     if (rc == SPL_OK) {
         Rec r{root_key->lo, root_key->hi & HI_KEY_MASK, root_aux, ~0ull};
         cudaError_t e = s->front.ensure(32, 0, st);
@@ -1299,6 +1329,7 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
     if (rc == SPL_OK) rc = save_links(s, st);
     if (rc == SPL_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(c, SPL_E_CUDA, "solver create sync failed");
     if (rc != SPL_OK) { delete s; return rc; }
+    c->active = s;
     *out = s;
     return SPL_OK;
 }
@@ -1472,6 +1503,7 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
                            spl_solver **out) {
     if (!c || !cfg || !root_rec_host || !out) return fail(c, SPL_E_INVALID, "spl_rsolver_create: null argument");
     if (beam < 1) return fail(c, SPL_E_INVALID, "spl_rsolver_create: beam_width must be >= 1");
+    NO_LIVE_SOLVER(c, "spl_rsolver_create");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t st = 0;
     CKS(c, upload_rconfig(c, cfg, st));
@@ -1480,7 +1512,8 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
     s->goal = cfg->target_points;
     s->front.swap(c->pool_front);
     s->uniq.swap(c->pool_uniq);
-    int rc = spl_reset_visited(c, st);
+    c->rcfg_dirty = false;
+    int rc = reset_visited(c, st);
     if (rc == SPL_OK) {
         cudaError_t e = s->front.ensure(96, 0, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->front.p, root_rec_host, 96, cudaMemcpyHostToDevice, st);
@@ -1508,6 +1541,7 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
     if (rc == SPL_OK) rc = save_links(s, st);
     if (rc == SPL_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(c, SPL_E_CUDA, "rsolver create sync failed");
     if (rc != SPL_OK) { delete s; return rc; }
+    c->active = s;
     *out = s;
     return SPL_OK;
 }

@@ -39,7 +39,19 @@ DEFAULT_DEVICE = 0
 
 
 def _engine(device=None) -> Engine:
-    return Engine.get(DEFAULT_DEVICE if device is None else device)
+    """The context solve()/__iter__/HEURISTICS run on.  Under torch.distributed (one process per GPU) the
+    default is this rank's own GPU -- LOCAL_RANK, or torch's current device once the launcher has set it --
+    never cuda:0 on every rank: NCCL cannot run two ranks on one device."""
+    if device is None:
+        device = DEFAULT_DEVICE
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            import os
+            device = int(os.environ['LOCAL_RANK']) if 'LOCAL_RANK' in os.environ else torch.cuda.current_device()
+            if torch.cuda.device_count() and device >= torch.cuda.device_count():
+                raise RuntimeError(f'rank {dist.get_rank()} maps to cuda:{device}, but only {torch.cuda.device_count()} '
+                                   f'devices are visible: run one process per GPU')
+    return Engine.get(device)
 
 
 def _score_one(name: str, state: 'State') -> float:

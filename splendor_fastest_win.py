@@ -47,20 +47,28 @@ def cli():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from splendor_rl_gym_b200 import Color, GameConfig, MultiPlayerState, State
     rank0 = int(os.environ.get('RANK', '0')) == 0
-    if a.realistic:  # reference CLI lines 95-129
-        cfg = GameConfig(num_players=a.players, target_points=a.goal_pts,
-                         gems_per_color={2: 4, 3: 5, 4: 7}.get(a.players, 4), infinite_resources=False)
-        solution = MultiPlayerState.newgame(config=cfg, shuffle_market=a.shuffle, seed=a.seed).solve(
-            use_heuristic=True, heuristic_name='competitive',
-            beam_width=a.beam_width if a.beam_width != 300_000 else 20_000, verbose=not a.quiet, device=a.device)
-        last = solution[-1]
-        print(f'\n{"=" * 60}')
-        print(f'Game Over! Winner: Player {last.get_winner()}')
-        print('Final Scores:')
-        for p in last.players:
-            print(f'  Player {p.player_id}: {p.pts} points, {len(p.cards)} cards')
-        print(f'Total moves: {last.turn_number}')
-        print(f'{"=" * 60}\n')
+    if a.realistic:  # reference CLI lines 95-129 (realistic mode is not sharded: under torchrun every rank solves
+        try:          # the same game on its own GPU and rank 0 reports)
+            cfg = GameConfig(num_players=a.players, target_points=a.goal_pts,
+                             gems_per_color={2: 4, 3: 5, 4: 7}.get(a.players, 4), infinite_resources=False)
+            solution = MultiPlayerState.newgame(config=cfg, shuffle_market=a.shuffle, seed=a.seed).solve(
+                use_heuristic=True, heuristic_name='competitive',
+                beam_width=a.beam_width if a.beam_width != 300_000 else 20_000, verbose=not a.quiet and rank0,
+                device=local if world > 1 else a.device)
+            last = solution[-1]
+            if rank0:
+                print(f'\n{"=" * 60}')
+                print(f'Game Over! Winner: Player {last.get_winner()}')
+                print('Final Scores:')
+                for p in last.players:
+                    print(f'  Player {p.player_id}: {p.pts} points, {len(p.cards)} cards')
+                print(f'Total moves: {last.turn_number}')
+                print(f'{"=" * 60}\n')
+        except KeyboardInterrupt:
+            print('Execution stopped by the user.')
+        finally:
+            if world > 1:
+                dist.destroy_process_group()
         return
     try:
         solution = State.newgame().solve(goal_pts=a.goal_pts, use_heuristic=a.use_heuristic, heuristic_name=a.heuristic,
