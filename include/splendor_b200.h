@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 1
+#define SPL_ABI_VERSION 2
 
 typedef struct spl_ctx spl_ctx;
 typedef struct spl_solver spl_solver;
@@ -87,7 +87,11 @@ typedef struct {
     uint64_t table_slots;      /* initial visited-table capacity in slots: three per 64-byte bucket, at most
                                 * 3 * 2^30 (0 = default 2^22) */
     uint64_t max_table_bytes;  /* growth ceiling for the visited table (0 = 60% of free device memory) */
-    uint64_t chunk_parents;    /* parents expanded per launch pair (0 = default 4 Mi; max 16 Mi) */
+    uint64_t chunk_parents;    /* parents expanded per round (0 = default: 4 Mi on the key-table level, 16 Mi on the
+                                * card-set-grouped level; max 16 Mi) */
+    uint64_t node_slots;       /* initial capacity of the card-set node table (384-byte nodes) used by the beam-search
+                                * level (0 = default 2^12; grows by rehash) */
+    uint64_t max_node_bytes;   /* growth ceiling of the node table (0 = 50% of free device memory) */
 } spl_config;
 
 /* per-level counters (the reference prints none of these; they feed parity tests and the roofline) */

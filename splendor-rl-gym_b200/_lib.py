@@ -27,7 +27,8 @@ class Key(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [('device', C.c_int32), ('reserved0', C.c_int32), ('table_slots', C.c_uint64),
-                ('max_table_bytes', C.c_uint64), ('chunk_parents', C.c_uint64)]
+                ('max_table_bytes', C.c_uint64), ('chunk_parents', C.c_uint64), ('node_slots', C.c_uint64),
+                ('max_node_bytes', C.c_uint64)]
 
 
 class LevelInfo(C.Structure):

@@ -24,6 +24,10 @@ struct Counters {            // device-resident scalars, zeroed per use by the h
     unsigned int error;               // 1 = probe overflow (table full)
     unsigned int ticket[4];           // dynamic tile tickets
     unsigned long long key_or[2], key_and[2];  // OR / AND of the kept keys (det policy: which key bits vary)
+    // card-set-grouped level (spl_m2.cuh): total_cands counts the round's gem takes there
+    unsigned long long n_buys;        // buy records of the round
+    unsigned int n_runs, n_big;       // equal-hash runs of the round; runs queued for the CTA kernel
+    unsigned int n_new_nodes, pad0;   // nodes (card sets) created in the round
 };
 
 struct SelState {            // radix-select state (device)
@@ -657,6 +661,16 @@ __global__ void __launch_bounds__(TILE) goal_kernel(const Rec *__restrict__ fron
 constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS;
 
+// Tie key of element i among equal scores.  link_top == 0: the canonical state key (det policy, larger first).
+// link_top > 0: the arrival order carried by the record's link word (= parent rank << 8 | ordinal < 2^link_top),
+// mapped to lo = 2^link_top - 1 - link so that "larger first" == "earlier arrival first" (stable policy on
+// unordered input, spl_m2.cuh).
+__device__ __forceinline__ void load_tie_key(const uint64_t *__restrict__ kb, int ks, int64_t i, int link_top, uint64_t &lo,
+                                             uint64_t &hi) {
+    if (link_top) { lo = ((1ull << link_top) - 1) - kb[i * ks + 3]; hi = 0; }
+    else { lo = kb[i * ks]; hi = kb[i * ks + 1]; }
+}
+
 // histogram of digit (x >> shift) & (2^bits - 1) over elements whose higher bits equal the prefix.
 // WORD 0: x = sk - sk_min (score).  WORD 1 / 2 (det policy): key.hi / key.lo of the elements whose
 // score equals the score threshold (and, for WORD 2, whose key.hi equals the hi threshold).
@@ -664,7 +678,7 @@ template <int WORD>
 // keys are read as kb[i * ks] (lo) and kb[i * ks + 1] (hi): ks = 4 for 32-byte records, 2 for a plain key array
 __global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restrict__ sk, const uint64_t *__restrict__ kb,
                                                         int ks, int64_t n, uint64_t sk_min, int shift, int bits, int first,
-                                                        const SelState *st, uint32_t *__restrict__ hist) {
+                                                        const SelState *st, uint32_t *__restrict__ hist, int link_top = 0) {
     __shared__ uint32_t sh[SEL_BINS];
     for (int i = threadIdx.x; i < SEL_BINS; i += TILE) sh[i] = 0;
     __syncthreads();
@@ -681,9 +695,10 @@ __global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restri
             if (WORD > 0) {
                 match = x == T;
                 if (match) {
-                    const uint64_t hi = kb[i * ks + 1];
+                    uint64_t lo, hi;
+                    load_tie_key(kb, ks, i, link_top, lo, hi);
                     if (WORD == 1) x = hi;
-                    else { match = hi == Thi; x = kb[i * ks]; }
+                    else { match = hi == Thi; x = lo; }
                 }
             }
             match = match && (first || hs >= 64 || (x >> hs) == (prefix >> hs));
@@ -957,6 +972,8 @@ __global__ void __launch_bounds__(TILE) cut_kernel(const uint64_t *__restrict__ 
 // the key threshold found by the WORD 1/2 select passes (or every tie when `all_ties`).  Order of
 // emission is irrelevant here (the composite sort below fixes the ranks); also accumulates the
 // OR / AND of the kept keys so that sort passes over constant key digits can be skipped.
+// link_top > 0: tie key = arrival order (load_tie_key).  pack (needs DICT and link_top): emit ONE sort word
+// y = score rank << link_top | link (ascending == better first) instead of (y, ~key.lo, ~key.hi).
 template <bool DICT>
 __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restrict__ sk, const uint64_t *__restrict__ kb,
                                                        int ks, int64_t n, uint64_t sk_min, uint64_t sk_max, int keep_all,
@@ -964,7 +981,7 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
                                                        const ScoreDict *__restrict__ dict, uint64_t *__restrict__ out_y,
                                                        uint64_t *__restrict__ out_klo, uint64_t *__restrict__ out_khi,
                                                        uint32_t *__restrict__ out_idx, uint64_t *status_keep,
-                                                       Counters *ctr, int ticket_id) {
+                                                       Counters *ctr, int ticket_id, int link_top = 0, int pack = 0) {
     __shared__ uint32_t warp_sums[TILE / 32 + 1];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_keep_base;
@@ -981,8 +998,7 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
         bool k = false;
         if (b0 + q < n) {
             x[q] = sk[b0 + q] - sk_min;
-            lo[q] = kb[(b0 + q) * ks];
-            hi[q] = kb[(b0 + q) * ks + 1];
+            load_tie_key(kb, ks, b0 + q, link_top, lo[q], hi[q]);
             if (keep_all || x[q] > T) k = true;
             else if (x[q] == T) k = all_ties || hi[q] > Thi || (hi[q] == Thi && lo[q] >= Tlo);
             if (k) { or_lo |= lo[q]; or_hi |= hi[q]; and_lo &= lo[q]; and_hi &= hi[q]; }
@@ -1001,9 +1017,14 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
 #pragma unroll
     for (int q = 0; q < CUT_ITEMS; ++q)
         if (keepmask >> q & 1) {
-            out_y[pos] = DICT ? (uint64_t)dict_rank_of(dict, x[q] + sk_min) : (sk_max - sk_min) - x[q];
-            out_klo[pos] = ~lo[q];                 // ascending sort of ~key == descending key
-            out_khi[pos] = ~hi[q] & HI_KEY_MASK;
+            const uint64_t y = DICT ? (uint64_t)dict_rank_of(dict, x[q] + sk_min) : (sk_max - sk_min) - x[q];
+            if (pack) {
+                out_y[pos] = (y << link_top) | (((1ull << link_top) - 1) - lo[q]);
+            } else {
+                out_y[pos] = y;
+                out_klo[pos] = ~lo[q];                 // ascending sort of ~key == descending key
+                out_khi[pos] = ~hi[q] & HI_KEY_MASK;
+            }
             out_idx[pos] = (uint32_t)(b0 + q);
             ++pos;
         }

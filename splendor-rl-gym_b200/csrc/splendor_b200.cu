@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "spl_kernels.cuh"
+#include "spl_m2.cuh"
 #include "spl_realistic.cuh"
 #include "spl_tables.cuh"
 
@@ -63,6 +64,13 @@ struct spl_ctx {
     uint64_t cap = 0 /* slots = 3 * nb */, nb = 0 /* 64-byte buckets */, max_table_bytes = 0, occupied = 0;
     uint32_t epoch = 0;
     uint64_t chunk_parents = 0;
+    bool chunk_user = false;  // chunk_parents was set by the caller (spl_config), not the default
+    // card-set node table of the grouped level (spl_m2.cuh)
+    uint64_t *nodes = nullptr;
+    uint64_t nn = 0, node_occ = 0, max_node_bytes = 0;
+    uint16_t *d_gemrank = nullptr;
+    DevBuf brec, ntk8, boff2, run_start, run_wpre, big_list;
+    int tie_link_top = 0;  // > 0: the beam cut breaks score ties on the records' link words (arrival order)
     // constant tables
     DevTables *d_tabs = nullptr;
     uint32_t *d_takes_idx = nullptr;
@@ -121,6 +129,13 @@ static int fail(spl_ctx *c, int code, const char *fmt, ...) {
         if (s_ != SPL_OK) return s_; \
     } while (0)
 
+// every entry point: select the context's device and drop any stale non-sticky error another library left in this
+// thread's runtime state (the launch checks below read cudaGetLastError, which would otherwise report it as ours)
+static inline cudaError_t enter_device(spl_ctx *c) {
+    const cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) cudaGetLastError();
+    return e;
+}
 static inline unsigned nblk(int64_t n, int per = TILE) { return (unsigned)((n + per - 1) / per); }
 static inline int bitlen(uint64_t x) { return x ? 64 - __builtin_clzll(x) : 0; }
 
@@ -210,6 +225,7 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     size_t free_b = 0, total_b = 0;
     CKC(cudaMemGetInfo(&free_b, &total_b));
     c->max_table_bytes = cfg->max_table_bytes ? cfg->max_table_bytes : (uint64_t)(free_b * 0.6);
+    c->chunk_user = cfg->chunk_parents != 0;
     c->chunk_parents = cfg->chunk_parents ? std::min<uint64_t>(cfg->chunk_parents, 16ull << 20) : (4ull << 20);
     c->chunk_parents = std::max<uint64_t>(c->chunk_parents, TILE);
     const HostTables &T = host_tables();
@@ -228,6 +244,8 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     c->luts.pts = c->d_lut;
     c->luts.saved = c->d_lut + T.lut_pts.size();
     c->luts.small = c->d_lut + T.lut_pts.size() + T.lut_saved.size();
+    CKC(cudaMalloc(&c->d_gemrank, T.gemrank.size() * 2));
+    CKC(cudaMemcpy(c->d_gemrank, T.gemrank.data(), T.gemrank.size() * 2, cudaMemcpyHostToDevice));
     CKC(cudaMalloc(&c->d_ctr, sizeof(Counters)));
     CKC(cudaMallocHost(&c->h_ctr, sizeof(Counters)));
     CKC(cudaMalloc(&c->d_sel, sizeof(SelState)));
@@ -239,6 +257,17 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE, IDENT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE, IDENT_PYHASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST, IDENT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
+    CKC(cudaFuncSetAttribute(m2_buys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuySmem)));
+    CKC(cudaFuncSetAttribute(m2_group_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+    CKC(cudaFuncSetAttribute(m2_group_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
+    {
+        c->max_node_bytes = cfg->max_node_bytes ? cfg->max_node_bytes : (uint64_t)(free_b * 0.5);
+        uint64_t nn = cfg->node_slots ? cfg->node_slots : (1ull << 12);
+        nn = std::max<uint64_t>(std::min<uint64_t>(nn, c->max_node_bytes / (NODE_WORDS * 8)), 64);
+        CKC(cudaMalloc(&c->nodes, nn * NODE_WORDS * 8));
+        CKC(cudaMemset(c->nodes, 0, nn * NODE_WORDS * 8));
+        c->nn = nn;
+    }
     uint64_t slots = cfg->table_slots ? cfg->table_slots : (1ull << 22);
     slots = std::min<uint64_t>(slots, c->max_table_bytes / 64 * BUCKET_SLOTS);
     slots = std::max<uint64_t>(slots, 1024);
@@ -259,7 +288,7 @@ int32_t spl_destroy(spl_ctx *c) {
     cudaDeviceSynchronize();
     cudaFree(c->table); cudaFree(c->d_tabs); cudaFree(c->d_takes_idx); cudaFree(c->d_takes_edges);
     cudaFree(c->d_lut); cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr); cudaFree(c->d_sel); cudaFreeHost(c->h_sel);
-    cudaFree(c->d_hist); cudaFree(c->d_dict);
+    cudaFree(c->d_hist); cudaFree(c->d_dict); cudaFree(c->nodes); cudaFree(c->d_gemrank);
     for (auto *b : c->pool_links) delete b;
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     delete c;
@@ -267,9 +296,11 @@ int32_t spl_destroy(spl_ctx *c) {
 }
 
 static int reset_visited(spl_ctx *c, cudaStream_t st) {
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     CK(c, cudaMemsetAsync(c->table, 0, c->nb * 64, st));
+    if (c->node_occ) CK(c, cudaMemsetAsync(c->nodes, 0, c->nn * NODE_WORDS * 8, st));
     c->occupied = 0;
+    c->node_occ = 0;
     c->epoch = 0;
     return SPL_OK;
 }
@@ -291,7 +322,7 @@ int32_t spl_set_identity(spl_ctx *c, int32_t identity) {
 int32_t spl_pyhash(spl_ctx *c, const spl_key *keys, int64_t n, uint64_t *out, void *stream) {
     if (!c || n < 0 || (n && (!keys || !out))) return fail(c, SPL_E_INVALID, "spl_pyhash: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (n == 0) return SPL_OK;
     pyhash_kernel<<<nblk(n), TILE, 0, st>>>(keys, n, out);
     ++c->launches;
@@ -401,12 +432,13 @@ static int run_count(spl_ctx *c, const Rec *front, int64_t n, cudaStream_t st) {
 static int select_ties_by_key(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t k,
                               uint64_t sk_min, cudaStream_t st) {
     const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
-    for (int word = 1; word <= 2; ++word) {
-        int top = word == 1 ? 41 : 64, first = 1;
+    const int lt = c->tie_link_top;  // arrival-order ties: one word of lt bits, the high word is constant 0
+    for (int word = lt ? 2 : 1; word <= 2; ++word) {
+        int top = word == 1 ? 41 : (lt ? lt : 64), first = 1;
         while (top > 0) {
             const int bits = std::min(SEL_BITS, top), shift = top - bits;
-            if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
-            else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+            if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist, lt);
+            else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist, lt);
             sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, 0, (uint64_t)k, c->d_sel);
             c->launches += 2;
             first = 0;
@@ -540,19 +572,21 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
     CKS(c, prep_status(c, 2, ct, st));
     CKS(c, reset_ticket(c, 1, st));
     uint64_t vary_lo = 0, vary_hi = 0;
+    const int lt = det == 1 ? c->tie_link_top : 0;
+    const int pack = lt && use_dict;  // one sort word: score rank << lt | link
     if (det) {
         CKS(c, zero_ctr(c, st));
         if (use_dict)
             cut_det_kernel<true><<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->d_dict,
                                                        c->y[0].as<uint64_t>(), c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(),
-                                                       c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
+                                                       c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1, lt, pack);
         else
             cut_det_kernel<false><<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, nullptr,
                                                         c->y[0].as<uint64_t>(), c->kl[0].as<uint64_t>(), c->kh[0].as<uint64_t>(),
-                                                        c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
+                                                        c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1, lt, 0);
         ++c->launches;
         CK(c, cudaGetLastError());
-        if (det == 1) {  // which key bits vary among the survivors (constant digits need no sort pass)
+        if (det == 1 && !pack) {  // which key bits vary among the survivors (constant digits need no sort pass)
             CKS(c, read_ctr(c, st));
             vary_lo = c->h_ctr->key_or[0] ^ c->h_ctr->key_and[0];
             vary_hi = (c->h_ctr->key_or[1] ^ c->h_ctr->key_and[1]) & HI_KEY_MASK;
@@ -582,21 +616,21 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
         if (kept > cap_kept) return fail(c, SPL_E_CUDA, "internal: cut kept %lld > capacity %lld", (long long)kept, (long long)cap_kept);
     }
     // y = sk_max - sk in [0, sk_max - sk_min - T], or (dictionary) the score's descending rank in [0, rank_t]
-    const int nbits = use_dict ? bitlen(c->h_sel->rank_t) : bitlen((sk_max - sk_min) - T);
+    const int nbits = (use_dict ? bitlen(c->h_sel->rank_t) : bitlen((sk_max - sk_min) - T)) + (pack ? lt : 0);
     int cur = 0;
     const unsigned nt = nblk(kept, SORT_TILE);
     if (kept > 1 && (nbits > 0 || vary_lo || vary_hi)) {
         const size_t msz = (size_t)SORT_BINS * nt;
         CK(c, c->matrix.ensure(msz * 4, 0, st));
         CK(c, c->matrix2.ensure(msz * 4, 0, st));
-        if (det == 1) {  // least significant first: key.lo, key.hi, then the score
+        if (det == 1 && !pack) {  // least significant first: key.lo, key.hi, then the score
             for (int shift = 0; shift < 64; shift += SORT_BITS)
                 if ((vary_lo >> shift) & 0xff) { CKS(c, sort_pass(c, 1, cur, c->kl[cur].as<uint64_t>(), kept, shift, nt, msz, st)); cur ^= 1; }
             for (int shift = 0; shift < 41; shift += SORT_BITS)
                 if ((vary_hi >> shift) & 0xff) { CKS(c, sort_pass(c, 1, cur, c->kh[cur].as<uint64_t>(), kept, shift, nt, msz, st)); cur ^= 1; }
         }
         for (int shift = 0; shift < nbits; shift += SORT_BITS) {
-            CKS(c, sort_pass(c, det == 1, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
+            CKS(c, sort_pass(c, det == 1 && !pack, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
             cur ^= 1;
         }
     }
@@ -616,7 +650,7 @@ int32_t spl_expand(spl_ctx *c, const spl_key *keys, const uint64_t *aux, int64_t
                    uint64_t *cl, int64_t cap, int64_t *n_out, void *stream) {
     if (!c || !n_out || n < 0 || n > (16ll << 20)) return fail(c, SPL_E_INVALID, "spl_expand: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     *n_out = 0;
     if (n == 0) return SPL_OK;
     CK(c, c->tmp_rec.ensure((size_t)n * 32, 0, st));
@@ -644,7 +678,7 @@ int32_t spl_dedup(spl_ctx *c, const spl_key *ck, const uint64_t *ca, int64_t n, 
     if (!c || !n_out || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dedup: bad arguments");
     NO_LIVE_SOLVER(c, "spl_dedup");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     *n_out = 0;
     if (n == 0) return SPL_OK;
     CKS(c, zero_ctr(c, st));
@@ -680,7 +714,7 @@ int32_t spl_score(spl_ctx *c, int32_t heuristic, int32_t noise, const spl_key *k
                   double *scores, void *stream) {
     if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_score: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (n == 0) return SPL_OK;
     score_kernel<<<nblk(n), TILE, 0, st>>>(keys, aux, n, heuristic, noise, c->luts, scores);
     ++c->launches;
@@ -694,7 +728,7 @@ int32_t spl_topk(spl_ctx *c, const double *scores, const spl_key *keys, int64_t 
     if (tie_policy != SPL_TIE_STABLE && tie_policy != SPL_TIE_KEY) return fail(c, SPL_E_INVALID, "spl_topk: unknown tie policy %d", tie_policy);
     if (tie_policy == SPL_TIE_KEY && !keys) return fail(c, SPL_E_INVALID, "spl_topk: SPL_TIE_KEY needs keys");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     *n_out = 0;
     if (n == 0 || k == 0) return SPL_OK;
     CKS(c, zero_ctr(c, st));
@@ -727,7 +761,7 @@ int32_t spl_owner_partition(spl_ctx *c, const spl_key *keys, int64_t n, int32_t 
     if (!c || !counts_host || n < 0 || n >= (1ll << 32) || n_ranks < 1 || n_ranks > 256)
         return fail(c, SPL_E_INVALID, "spl_owner_partition: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     for (int g = 0; g < n_ranks; ++g) counts_host[g] = 0;
     if (n == 0) return SPL_OK;
     for (int b = 0; b < 2; ++b) {
@@ -758,7 +792,7 @@ int32_t spl_expand_rows(spl_ctx *c, const void *front_rows, int64_t n, int64_t r
                         int64_t *n_out, void *stream) {
     if (!c || !n_out || n < 0 || n > (16ll << 20)) return fail(c, SPL_E_INVALID, "spl_expand_rows: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     *n_out = 0;
     if (n == 0) return SPL_OK;
     CKS(c, zero_ctr(c, st));
@@ -780,7 +814,7 @@ int32_t spl_route_keys(spl_ctx *c, const void *cand_rows, int64_t n, int32_t n_r
     if (!c || !counts_host || n < 0 || n >= (1ll << 32) || n_ranks < 1 || n_ranks > 255)
         return fail(c, SPL_E_INVALID, "spl_route_keys: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     for (int g = 0; g < n_ranks; ++g) counts_host[g] = 0;
     c->route_n = n;
     if (n == 0) return SPL_OK;
@@ -835,7 +869,7 @@ int32_t spl_dedup_flags(spl_ctx *c, const spl_key *keys, int64_t n, uint8_t *fla
     if (!c || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dedup_flags: bad arguments");
     NO_LIVE_SOLVER(c, "spl_dedup_flags");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (n == 0) return SPL_OK;
     CKS(c, zero_ctr(c, st));
     CKS(c, ensure_table(c, (uint64_t)n, st));
@@ -856,7 +890,7 @@ int32_t spl_compact_winners(spl_ctx *c, const void *cand_rows, int64_t n, const 
                             int64_t *n_out, void *stream) {
     if (!c || !n_out || n < 0 || n != c->route_n) return fail(c, SPL_E_STATE, "spl_compact_winners: must follow spl_route_keys on the same candidates");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     *n_out = 0;
     if (n == 0) return SPL_OK;
     CK(c, c->rtmp.ensure((size_t)n + 8, 0, st));
@@ -877,7 +911,7 @@ int32_t spl_score_rows(spl_ctx *c, int32_t heuristic, int32_t noise, const void 
                        const uint8_t *draws, void *stream) {
     if (!c || n < 0 || (noise == SPL_NOISE_EXTERNAL && !draws)) return fail(c, SPL_E_INVALID, "spl_score_rows: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (n == 0) return SPL_OK;
     score_rows_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const Rec *>(rows), n, heuristic, noise, c->luts, scores, draws);
     ++c->launches;
@@ -888,7 +922,7 @@ int32_t spl_score_rows(spl_ctx *c, int32_t heuristic, int32_t noise, const void 
 int32_t spl_move_rows(spl_ctx *c, const void *rows, const int64_t *idx, int64_t n, void *out_rows, int32_t scatter, void *stream) {
     if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_move_rows: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (n == 0) return SPL_OK;
     move_rows_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const Rec *>(rows), idx, n, reinterpret_cast<Rec *>(out_rows), scatter);
     ++c->launches;
@@ -900,7 +934,7 @@ int32_t spl_dtopk_begin(spl_ctx *c, const double *scores, const spl_key *keys, i
                         uint64_t *sk_max_host, void *stream) {
     if (!c || !sk_min_host || !sk_max_host || n < 0 || n >= (1ll << 32)) return fail(c, SPL_E_INVALID, "spl_dtopk_begin: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     c->dtopk_n = n;
     c->dtopk_recs = false;
     *sk_min_host = ~0ull;
@@ -925,7 +959,7 @@ int32_t spl_dtopk_hist(spl_ctx *c, int32_t word, int32_t shift, int32_t bits, in
     if (!c || !hist_dev_out || word < 0 || word > 2 || bits < 1 || bits > SEL_BITS) return fail(c, SPL_E_INVALID, "spl_dtopk_hist: bad arguments");
     if (word > 0 && !c->dtopk_recs && c->dtopk_n) return fail(c, SPL_E_STATE, "spl_dtopk_hist: key passes need keys in spl_dtopk_begin");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     const int64_t n = c->dtopk_n;
     *hist_dev_out = c->d_hist;
     if (n == 0) return SPL_OK;
@@ -943,7 +977,7 @@ int32_t spl_dtopk_hist(spl_ctx *c, int32_t word, int32_t shift, int32_t bits, in
 int32_t spl_dtopk_pick(spl_ctx *c, int32_t word, int32_t shift, int32_t first, int32_t init_k, int64_t k, void *stream) {
     if (!c) return SPL_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, init_k, (uint64_t)k, c->d_sel);
     ++c->launches;
     CK(c, cudaGetLastError());
@@ -953,7 +987,7 @@ int32_t spl_dtopk_pick(spl_ctx *c, int32_t word, int32_t shift, int32_t first, i
 int32_t spl_dtopk_get(spl_ctx *c, uint64_t state_host[6], void *stream) {
     if (!c || !state_host) return SPL_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     c->d2h_bytes += sizeof(SelState);
@@ -964,7 +998,7 @@ int32_t spl_dtopk_get(spl_ctx *c, uint64_t state_host[6], void *stream) {
 int32_t spl_dtopk_set(spl_ctx *c, const uint64_t state_host[6], void *stream) {
     if (!c || !state_host) return SPL_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     memcpy(c->h_sel, state_host, 6 * sizeof(uint64_t));
     c->h_sel->rank_t = ~0ull;
     CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
@@ -978,7 +1012,7 @@ int32_t spl_dtopk_cut(spl_ctx *c, int32_t tie_policy, int32_t keep_all, int32_t 
                       int64_t *kept_host, void *stream) {
     if (!c || !kept_host) return SPL_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     const int64_t n = c->dtopk_n;
     *kept_host = 0;
     if (n == 0) return SPL_OK;
@@ -1006,7 +1040,7 @@ int32_t spl_count_less(spl_ctx *c, int32_t words, int32_t inclusive, const uint6
                        int64_t nb, int64_t *out, int32_t accumulate, int32_t sorted_a, void *stream) {
     if (!c || (words != 1 && words != 3) || na < 0 || nb < 0) return fail(c, SPL_E_INVALID, "spl_count_less: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (na == 0) return SPL_OK;
     count_less_kernel<<<nblk(na), TILE, 0, st>>>(words, inclusive, ay, akl, akh, na, by, bkl, bkh, nb, out, accumulate, sorted_a);
     ++c->launches;
@@ -1021,6 +1055,7 @@ struct spl_solver {
     spl_ctx *c = nullptr;
     int goal = 15, use_h = 0, heuristic = 0, tie = 0, noise = 0, keep_links = 1;
     bool realistic = false;
+    bool grouped = false;  // beam search on the card-set-grouped level (spl_m2.cuh); otherwise the key-table level
     spl_rconfig rcfg{};
     // external-noise mode: the level is split in two calls (expand+dedup | score+cut)
     bool pending = false;
@@ -1060,6 +1095,161 @@ static int save_links(spl_solver *s, cudaStream_t st) {
     return SPL_OK;
 }
 
+// ------------------------------------------------------------------ card-set-grouped level (spl_m2.cuh)
+// grow the node table so that `need` more card sets keep its load factor <= 0.6 (if memory allows)
+static int ensure_nodes(spl_ctx *c, uint64_t need, cudaStream_t st) {
+    while ((double)(c->node_occ + need) > 0.6 * (double)c->nn) {
+        uint64_t nnn = c->nn * 2;
+        if (nnn * NODE_WORDS * 8 > c->max_node_bytes) nnn = c->max_node_bytes / (NODE_WORDS * 8);
+        if (nnn <= c->nn + c->nn / 8) break;
+        uint64_t *nt = nullptr;
+        cudaError_t e = cudaMalloc(&nt, nnn * NODE_WORDS * 8);
+        if (e != cudaSuccess) { cudaGetLastError(); break; }
+        CK(c, cudaMemsetAsync(nt, 0, nnn * NODE_WORDS * 8, st));
+        m2_rehash_kernel<<<nblk((int64_t)c->nn * 32), TILE, 0, st>>>(c->nodes, c->nn, nt, nnn, c->d_ctr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        unsigned int err = 0;
+        CK(c, cudaMemcpyAsync(&err, &c->d_ctr->error, 4, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        if (err) { cudaFree(nt); return fail(c, SPL_E_TABLE_FULL, "node rehash into %llu slots overflowed a probe sequence", (unsigned long long)nnn); }
+        cudaFree(c->nodes);
+        c->nodes = nt;
+        c->nn = nnn;
+    }
+    if (c->node_occ + need > c->nn - c->nn / 16)
+        return fail(c, SPL_E_TABLE_FULL, "card-set table full: %llu nodes + %llu new vs %llu slots (max_node_bytes=%llu)",
+                    (unsigned long long)c->node_occ, (unsigned long long)need, (unsigned long long)c->nn,
+                    (unsigned long long)c->max_node_bytes);
+    return SPL_OK;
+}
+
+// expand + dedup (+ score) of the whole queue `front[0..n)` in rounds of parents; winners are appended to
+// s->uniq / c->sk in no particular order (their link words carry the arrival order)
+static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n_uniq_out, int64_t *generated_out,
+                          uint64_t *sk_min_out, uint64_t *sk_max_out, float ms[5], cudaStream_t st) {
+    spl_ctx *c = s->c;
+    const int64_t chunk = c->chunk_user ? (int64_t)c->chunk_parents : (16ll << 20);
+    int64_t n_uniq = 0, generated = 0;
+    uint64_t sk_min = ~0ull, sk_max = 0;
+    const bool score = s->use_h && s->noise != SPL_NOISE_EXTERNAL;
+    for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+        const int64_t np = std::min<int64_t>(chunk, n - p0);
+        const unsigned nt = nblk(np);
+        // ---- 1. fan-out: buys offsets, take counts, sort keys of the parents
+        CKS(c, zero_ctr(c, st));
+        CK(c, cudaEventRecord(c->ev[0], st));
+        CK(c, c->boff2.ensure((size_t)np * 4 + 4, 0, st));
+        CK(c, c->ntk8.ensure((size_t)np + 8, 0, st));
+        // items of the round = parents + buy records; their number is known after the count, so the key / id
+        // arrays are sized for the parents first and grown (contents kept) once the buys are counted
+        CK(c, c->y[0].ensure((size_t)np * 8 + 8, 0, st));
+        CK(c, c->idx[0].ensure((size_t)np * 4 + 4, 0, st));
+        CKS(c, prep_status(c, 0, nt, st));
+        m2_count_kernel<<<nt, TILE, 0, st>>>(front + p0, np, c->d_tabs, c->d_takes_idx, c->boff2.as<uint32_t>(),
+                                              c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>(), c->ntk8.as<uint8_t>(),
+                                              c->status[0].as<uint64_t>(), c->d_ctr, 0);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CKS(c, read_ctr(c, st));
+        const uint64_t n_takes = c->h_ctr->total_cands, n_buys = c->h_ctr->n_buys, total = n_takes + n_buys;
+        generated += (int64_t)total;
+        if (total == 0) continue;
+        const int64_t n_items = np + (int64_t)n_buys;
+        if (total >= 0xFFFFFFFFull || (uint64_t)n_items >= 0xFFFFFFFFull)
+            return fail(c, SPL_E_INVALID, "round produced %llu candidates (>= 2^32): lower spl_config.chunk_parents", (unsigned long long)total);
+        CK(c, c->y[0].ensure((size_t)n_items * 8 + 8, (size_t)np * 8, st));
+        CK(c, c->idx[0].ensure((size_t)n_items * 4 + 4, (size_t)np * 4, st));
+        CK(c, c->y[1].ensure((size_t)n_items * 8 + 8, 0, st));
+        CK(c, c->idx[1].ensure((size_t)n_items * 4 + 4, 0, st));
+        CK(c, c->brec.ensure((size_t)n_buys * 32 + 32, 0, st));
+        if (n_buys) {
+            m2_buys_kernel<<<nt, TILE, sizeof(BuySmem), st>>>(front + p0, np, c->d_tabs, c->d_takes_idx, c->boff2.as<uint32_t>(), p0,
+                                                               c->brec.as<Rec>(), c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>());
+            ++c->launches;
+            CK(c, cudaGetLastError());
+        }
+        CK(c, cudaEventRecord(c->ev[7], st));
+        // ---- 2. stable LSD sort of the items by the high half of their card-set hash
+        int cur = 0;
+        {
+            const unsigned snt = nblk(n_items, SORT_TILE);
+            const size_t msz = (size_t)SORT_BINS * snt;
+            CK(c, c->matrix.ensure(msz * 4, 0, st));
+            CK(c, c->matrix2.ensure(msz * 4, 0, st));
+            if (n_items > 1)
+                for (int shift = 0; shift < 32; shift += SORT_BITS) {
+                    CKS(c, sort_pass(c, 0, cur, c->y[cur].as<uint64_t>(), n_items, shift, snt, msz, st));
+                    cur ^= 1;
+                }
+        }
+        // ---- 3. runs of equal key + candidate-weight prefix
+        const unsigned rt = nblk(n_items, TILE * RUN_ITEMS);
+        CK(c, c->run_start.ensure((size_t)n_items * 4 + 8, 0, st));
+        CK(c, c->run_wpre.ensure((size_t)n_items * 4 + 8, 0, st));
+        CKS(c, prep_status(c, 1, rt, st));
+        CKS(c, prep_status(c, 2, rt, st));
+        CKS(c, reset_ticket(c, 1, st));
+        m2_runs_kernel<<<rt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), c->idx[cur].as<uint32_t>(), n_items, (uint32_t)np,
+                                             c->ntk8.as<uint8_t>(), c->run_start.as<uint32_t>(), c->run_wpre.as<uint32_t>(),
+                                             c->status[1].as<uint64_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev[1], st));
+        CKS(c, read_ctr(c, st));
+        const uint64_t n_runs = c->h_ctr->n_runs;
+        // every run holds at least one card set; more than one only when two sets share a 32-bit key
+        CKS(c, ensure_nodes(c, n_runs + n_runs / 8 + 64, st));
+        CK(c, c->big_list.ensure((size_t)n_runs * 4 + 4, 0, st));
+        CK(c, s->uniq.ensure((size_t)(n_uniq + (int64_t)total) * 32, (size_t)n_uniq * 32, st));
+        if (s->use_h) CK(c, c->sk.ensure((size_t)(n_uniq + (int64_t)total) * 8, (size_t)n_uniq * 8, st));
+        // ---- 4. per-run dedup: warp kernel, then the CTA kernel over the runs it queued
+        GroupArgs A;
+        A.front = front + p0; A.brec = c->brec.as<Rec>(); A.ik = c->y[cur].as<uint64_t>(); A.iidx = c->idx[cur].as<uint32_t>();
+        A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
+        A.np = (uint32_t)np; A.rank_base = p0; A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges;
+        A.gemrank = c->d_gemrank; A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>();
+        A.out_sk = score ? c->sk.as<uint64_t>() : nullptr; A.out_base = (uint64_t)n_uniq; A.big_list = c->big_list.as<uint32_t>();
+        A.h = s->heuristic; A.noise_mode = s->noise; A.L = c->luts; A.ctr = c->d_ctr;
+        CK(c, cudaEventRecord(c->ev[2], st));
+        const unsigned gs = (unsigned)std::min<uint64_t>((n_runs + M2_WARPS - 1) / M2_WARPS, 148 * 6);
+        m2_group_small_kernel<<<gs, TILE, sizeof(SmallSmem), st>>>(A);
+        CK(c, cudaEventRecord(c->ev[4], st));
+        m2_group_big_kernel<<<148 * 8, TILE, sizeof(BigSmem), st>>>(A);
+        c->launches += 2;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev[3], st));
+        CKS(c, read_ctr(c, st));
+        if (c->h_ctr->error)
+            return fail(c, c->h_ctr->error == 3 ? SPL_E_CUDA : SPL_E_TABLE_FULL,
+                        c->h_ctr->error == 3 ? "internal: more than %d card sets share one sort key (level %d)" : "card-set table full during level %d (code %d)",
+                        c->h_ctr->error == 3 ? BIG_DONE : s->level, c->h_ctr->error == 3 ? s->level : (int)c->h_ctr->error);
+        const int64_t n_new = (int64_t)c->h_ctr->n_emitted;
+        c->node_occ += c->h_ctr->n_new_nodes;
+        c->occupied += n_new;
+        if (score && n_new) { sk_min = std::min<uint64_t>(sk_min, c->h_ctr->sk_min); sk_max = std::max<uint64_t>(sk_max, c->h_ctr->sk_max); }
+        n_uniq += n_new;
+        float t;
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[7]); ms[0] += t;   // fan-out + buy records
+        cudaEventElapsedTime(&t, c->ev[7], c->ev[1]); ms[2] += t;   // item sort + runs (grouping)
+        cudaEventElapsedTime(&t, c->ev[2], c->ev[3]); ms[1] += t;   // per-run dedup + emit + score (the dominant stage)
+        if (getenv("SPL_DEBUG")) {
+            float ts = 0, tb = 0;
+            cudaEventElapsedTime(&ts, c->ev[2], c->ev[4]);
+            cudaEventElapsedTime(&tb, c->ev[4], c->ev[3]);
+            fprintf(stderr, "[grouped] level %d round p0=%lld np=%lld takes=%llu buys=%llu runs=%llu big=%u new_nodes=%u winners=%lld  small %.3f ms  big %.3f ms  nodes %llu/%llu\n",
+                    s->level, (long long)p0, (long long)np, (unsigned long long)n_takes, (unsigned long long)n_buys,
+                    (unsigned long long)n_runs, c->h_ctr->n_big, c->h_ctr->n_new_nodes, (long long)n_new, ts, tb,
+                    (unsigned long long)c->node_occ, (unsigned long long)c->nn);
+        }
+    }
+    *n_uniq_out = n_uniq;
+    *generated_out = generated;
+    *sk_min_out = sk_min;
+    *sk_max_out = sk_max;
+    return SPL_OK;
+}
+
 // ------------------------------------------------------------------ second half of a speedrun level
 // beam cut (src/solver.py:452-456) or plain BFS hand-over, then bookkeeping
 static int speedrun_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t n_uniq, uint64_t sk_min, uint64_t sk_max,
@@ -1069,7 +1259,13 @@ static int speedrun_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t 
     if (s->use_h && n_uniq > 0) {
         int which = 0;
         CK(c, cudaEventRecord(c->ev[4], st));
-        CKS(c, run_cut_sort(c, c->sk.as<uint64_t>(), s->uniq.as<Rec>(), n_uniq, s->beam, sk_min, sk_max, s->tie == SPL_TIE_KEY, &which, &kept, st));
+        // grouped level: the winners are unordered, so `stable` ties are broken on the link words (arrival order)
+        const bool link_ties = s->grouped && s->tie == SPL_TIE_STABLE;
+        c->tie_link_top = link_ties ? 8 + bitlen((uint64_t)n) : 0;
+        const int rc_cut = run_cut_sort(c, c->sk.as<uint64_t>(), s->uniq.as<Rec>(), n_uniq, s->beam, sk_min, sk_max,
+                                        s->tie == SPL_TIE_KEY || link_ties, &which, &kept, st);
+        c->tie_link_top = 0;
+        CKS(c, rc_cut);
         CK(c, cudaEventRecord(c->ev[5], st));
         CK(c, s->front.ensure((size_t)kept * 32, 0, st));
         gather_rec_kernel<<<nblk(kept), TILE, 0, st>>>(s->uniq.as<Rec>(), c->idx[which].as<uint32_t>(), kept, s->front.as<Rec>());
@@ -1087,7 +1283,7 @@ static int speedrun_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t 
     }
     info->kept = kept;
     info->visited = (int64_t)c->occupied;
-    info->table_slots = c->cap;
+    info->table_slots = s->grouped ? c->nn : c->cap;
     if (kept == 0) {  // frontier exhausted: `puzzle` is the last dequeued state (src/solver.py:438,459);
         s->ended = true;  // s->front still holds the level that was just expanded
         s->goal_rank = n - 1;
@@ -1290,11 +1486,14 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
     if (use_h && tie != SPL_TIE_STABLE && tie != SPL_TIE_KEY) return fail(c, SPL_E_INVALID, "spl_solver_create: unknown tie policy %d", tie);
     if (noise < 0 || noise > SPL_NOISE_EXTERNAL) return fail(c, SPL_E_INVALID, "spl_solver_create: unknown noise policy %d", noise);
     NO_LIVE_SOLVER(c, "spl_solver_create");
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     cudaStream_t st = 0;
     spl_solver *s = new spl_solver();
     s->c = c; s->goal = goal; s->use_h = use_h; s->heuristic = heuristic; s->beam = beam; s->tie = tie;
     s->noise = noise; s->keep_links = keep_links;
+    // beam search with on-device scoring runs on the card-set-grouped level; exhaustive BFS (queue order == arrival
+    // order), the reference's hash identity and externally drawn noise (arrival-ordered draws) on the key table
+    s->grouped = use_h && noise != SPL_NOISE_EXTERNAL && c->identity == IDENT_KEY && !getenv("SPL_NO_GROUPED");
     s->front.swap(c->pool_front);
     s->uniq.swap(c->pool_uniq);
     std::sort(c->pool_links.begin(), c->pool_links.end(), [](DevBuf *a, DevBuf *b) { return a->cap > b->cap; });
@@ -1313,7 +1512,12 @@ int32_t spl_solver_create(spl_ctx *c, const spl_key *root_key, uint64_t root_aux
         if (rc == SPL_OK) {
             cudaError_t e = c->cand_slot.ensure(4, 0, st);
             if (e != cudaSuccess) rc = fail(c, SPL_E_NOMEM, "cand_slot alloc");
-            else {
+            else if (s->grouped) {
+                m2_root_kernel<<<1, 1, 0, st>>>(c->nodes, c->nn, root_key->lo, root_key->hi & HI_KEY_MASK, c->d_gemrank, c->d_ctr);
+                ++c->launches;
+                c->occupied = 1;
+                c->node_occ = 1;
+            } else {
                 if (c->identity == IDENT_PYHASH)
                     probe_list_kernel<IDENT_PYHASH><<<1, TILE, 0, st>>>(reinterpret_cast<const spl_key *>(s->front.p), 1, c->table,
                                                                         c->nb, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
@@ -1345,7 +1549,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     if (s->ended) return fail(c, SPL_E_STATE, "spl_solver_step: the search has already ended");
     if (s->pending) return fail(c, SPL_E_STATE, "spl_solver_step: the previous level still waits for spl_solver_cut");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (s->realistic) return rsolver_step(s, info, st);
     memset(info, 0, sizeof *info);
     info->level = s->level;
@@ -1367,12 +1571,20 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         info->ended = 1;
         info->goal_rank = s->goal_rank;
         info->visited = (int64_t)c->occupied;
-        info->table_slots = c->cap;
+        info->table_slots = s->grouped ? c->nn : c->cap;
         return SPL_OK;
     }
     // ---- expand + dedup by chunks of parents
     int64_t n_uniq = 0, generated = 0;
     uint64_t sk_min = ~0ull, sk_max = 0;
+    if (s->grouped) {
+        CKS(c, grouped_expand(s, front, n, &n_uniq, &generated, &sk_min, &sk_max, ms, st));
+        info->expanded = n;
+        info->generated = generated;
+        info->unique = n_uniq;
+        info->ms_count = ms[0]; info->ms_expand = ms[1]; info->ms_resolve = ms[2];
+        return speedrun_cut(s, info, n, n_uniq, sk_min, sk_max, st);
+    }
     for (int64_t p0 = 0; p0 < n; p0 += (int64_t)c->chunk_parents) {
         const int64_t np = std::min<int64_t>((int64_t)c->chunk_parents, n - p0);
         const unsigned nt = nblk(np);
@@ -1461,7 +1673,7 @@ int32_t spl_rexpand(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_
                     int64_t *n_out, void *stream) {
     if (!c || !n_out || n < 0 || n > (16ll << 20)) return fail(c, SPL_E_INVALID, "spl_rexpand: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     *n_out = 0;
     if (n == 0) return SPL_OK;
     CKS(c, upload_rconfig(c, cfg, st));
@@ -1477,7 +1689,7 @@ int32_t spl_rexpand(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_
 int32_t spl_rscore(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, double *scores, void *stream) {
     if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_rscore: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (n == 0) return SPL_OK;
     CKS(c, upload_rconfig(c, cfg, st));
     r_score_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const RRec *>(recs), n, c->rcfg.as<RConfigDev>(), c->luts,
@@ -1490,7 +1702,7 @@ int32_t spl_rscore(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t
 int32_t spl_rmaxpts(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, uint8_t *out, void *stream) {
     if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_rmaxpts: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     if (n == 0) return SPL_OK;
     CKS(c, upload_rconfig(c, cfg, st));
     r_maxpts_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const RRec *>(recs), n, c->rcfg.as<RConfigDev>(), out);
@@ -1504,7 +1716,7 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
     if (!c || !cfg || !root_rec_host || !out) return fail(c, SPL_E_INVALID, "spl_rsolver_create: null argument");
     if (beam < 1) return fail(c, SPL_E_INVALID, "spl_rsolver_create: beam_width must be >= 1");
     NO_LIVE_SOLVER(c, "spl_rsolver_create");
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     cudaStream_t st = 0;
     CKS(c, upload_rconfig(c, cfg, st));
     spl_solver *s = new spl_solver();
@@ -1559,7 +1771,7 @@ int32_t spl_solver_cut(spl_solver *s, const uint8_t *draws, int64_t n_draws, spl
     if (!s->pending) return fail(c, SPL_E_STATE, "spl_solver_cut: no level is waiting for draws");
     if (!draws || n_draws != s->pend_uniq) return fail(c, SPL_E_INVALID, "spl_solver_cut: need exactly %lld draws", (long long)s->pend_uniq);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     *info = s->pend_info;
     s->pending = false;
     if (s->realistic) return realistic_cut(s, info, s->pend_n, s->pend_uniq, draws, st);
@@ -1591,7 +1803,7 @@ int32_t spl_solver_path(spl_solver *s, int64_t *ranks, int32_t *ordinals, int32_
     if (!s->keep_links) return fail(c, SPL_E_STATE, "spl_solver_path: solver was created with keep_links = 0");
     const int L = s->level;  // level index of the final state
     if (L + 1 > cap) return fail(c, SPL_E_CAPACITY, "spl_solver_path: need %d entries", L + 1);
-    CK(c, cudaSetDevice(c->device));
+    CK(c, enter_device(c));
     int64_t r = s->goal_rank;
     for (int l = L; l >= 0; --l) {
         ranks[l] = r;

@@ -123,7 +123,8 @@ class Engine:
 
     _instances: dict = {}
 
-    def __init__(self, device: int = 0, table_slots: int = 0, max_table_bytes: int = 0, chunk_parents: int = 0):
+    def __init__(self, device: int = 0, table_slots: int = 0, max_table_bytes: int = 0, chunk_parents: int = 0,
+                 node_slots: int = 0, max_node_bytes: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError('splendor-rl-gym_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.device = device
@@ -131,7 +132,7 @@ class Engine:
         torch.cuda.init()
         with torch.cuda.device(device):
             torch.zeros(1, device=self.tdev)  # make sure the primary context exists
-        cfg = Config(device, 0, table_slots, max_table_bytes, chunk_parents)
+        cfg = Config(device, 0, table_slots, max_table_bytes, chunk_parents, node_slots, max_node_bytes)
         h = C.c_void_p()
         check(lib.spl_create(C.byref(cfg), C.byref(h)))
         self._h = h

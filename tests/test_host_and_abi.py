@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(raw, name), f'{name} declared in the header but not exported'
     assert declared == set(S.EXPORTS), declared ^ set(S.EXPORTS)
-    assert S.lib.spl_abi_version() == 1
+    assert S.lib.spl_abi_version() == 2
 
 
 def test_takes_table_matches_reference(golden):

@@ -17,10 +17,13 @@ ap.add_argument('--bfs', type=int, default=0, help='run pure BFS for this many l
 ap.add_argument('--slots', type=int, default=0)
 ap.add_argument('--chunk', type=int, default=0)
 ap.add_argument('--reps', type=int, default=2)
+ap.add_argument('--nodes', type=int, default=0, help='node-table slots of the grouped level (default 4 per beam slot)')
+ap.add_argument('--kv', action='store_true', help='size the key table as round 1 did (for SPL_NO_GROUPED=1 runs)')
 a = ap.parse_args()
 
-slots = a.slots or min(3 << 30, max(1 << 22, int(a.beam * 110 / 0.6)))
-eng = S.Engine(0, table_slots=slots, chunk_parents=a.chunk)
+slots = a.slots or (min(3 << 30, max(1 << 22, int(a.beam * 110 / 0.6))) if (a.kv or a.bfs) else 1 << 22)
+nodes = a.nodes or min(int(140e9 / 384), max(1 << 14, a.beam * 4))
+eng = S.Engine(0, table_slots=slots, chunk_parents=a.chunk, node_slots=0 if (a.kv or a.bfs) else nodes, max_node_bytes=int(150e9))
 k, aux = S.State.newgame().record()
 for rep in range(a.reps):
     torch.cuda.synchronize()
