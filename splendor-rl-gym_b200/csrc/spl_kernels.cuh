@@ -26,8 +26,9 @@ struct Counters {            // device-resident scalars, zeroed per use by the h
     unsigned long long key_or[2], key_and[2];  // OR / AND of the kept keys (det policy: which key bits vary)
     // card-set-grouped level (spl_m2.cuh): total_cands counts the round's gem takes there
     unsigned long long n_buys;        // buy records of the round
-    unsigned int n_runs, n_big;       // equal-hash runs of the round; runs queued for the CTA kernel
-    unsigned int n_new_nodes, pad0;   // nodes (card sets) created in the round
+    unsigned int n_runs, n_new_nodes; // equal-hash runs of the round; nodes (card sets) created in the round
+    unsigned int n_cls[8];            // runs per candidate-count class (m2_dispatch_kernel)
+    unsigned long long n_ties;        // tie_collect_kernel: arrival words collected
 };
 
 struct SelState {            // radix-select state (device)
@@ -683,16 +684,21 @@ __global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restri
     for (int i = threadIdx.x; i < SEL_BINS; i += TILE) sh[i] = 0;
     __syncthreads();
     const uint64_t prefix = first ? 0 : (WORD == 0 ? st->prefix : WORD == 1 ? st->khi : st->klo);
-    const uint64_t T = WORD == 0 ? 0 : st->prefix, Thi = WORD == 2 ? st->khi : 0;
+    const uint64_t T = (WORD == 0 || WORD == 3) ? 0 : st->prefix, Thi = WORD == 2 ? st->khi : 0;
     const int hs = shift + bits;  // bits above the digit must match the prefix
     const uint32_t dmask = (1u << bits) - 1;
     for (int64_t base = (int64_t)blockIdx.x * TILE; base < n; base += (int64_t)gridDim.x * TILE) {
         const int64_t i = base + threadIdx.x;
         bool match = i < n;
         uint64_t x = 0;
-        if (match) {
-            x = sk[i] - sk_min;
-            if (WORD > 0) {
+        if (match && WORD == 3) {
+            x = kb[i];  // compact list of the tie words of the threshold score (tie_collect_kernel)
+            match = first || hs >= 64 || (x >> hs) == (prefix >> hs);
+        } else if (match) {
+            x = sk[i];
+            match = x != 0;  // 0 = unused output slot
+            x -= sk_min;
+            if (WORD > 0 && match) {
                 match = x == T;
                 if (match) {
                     uint64_t lo, hi;
@@ -713,6 +719,31 @@ __global__ void __launch_bounds__(TILE) sel_hist_kernel(const uint64_t *__restri
     __syncthreads();
     for (int i = threadIdx.x; i < SEL_BINS; i += TILE)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// arrival-order ties (link_top > 0): gather the tie words of the elements whose score equals the threshold into a
+// compact list, so that the select passes over them read nothing else
+__global__ void __launch_bounds__(TILE) tie_collect_kernel(const uint64_t *__restrict__ sk, const uint64_t *__restrict__ kb, int ks,
+                                                           int64_t n, uint64_t sk_min, const SelState *st, int link_top,
+                                                           uint64_t *__restrict__ list, Counters *ctr) {
+    const uint64_t T = st->prefix;
+    const unsigned lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * TILE; base < n; base += (int64_t)gridDim.x * TILE) {
+        const int64_t i = base + threadIdx.x;
+        const uint64_t v = i < n ? sk[i] : 0;
+        const bool tie = v != 0 && v - sk_min == T;
+        const unsigned m = __ballot_sync(0xffffffffu, tie);
+        if (m) {
+            unsigned long long at = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) at = atomicAdd(&ctr->n_ties, (unsigned long long)__popc(m));
+            at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
+            if (tie) {
+                uint64_t lo, hi;
+                load_tie_key(kb, ks, i, link_top, lo, hi);
+                list[at + __popc(m & ((1u << lane) - 1))] = lo;
+            }
+        }
+    }
 }
 
 // choose the bucket holding the k_rem-th largest element; 1 CTA of 1024 threads, 2 bins each.
@@ -807,8 +838,8 @@ __global__ void __launch_bounds__(TILE) dict_build_kernel(const uint64_t *__rest
         if ((iter & 15) == 15 &&
             __any_sync(0xffffffffu, *reinterpret_cast<volatile unsigned int *>(&d->over) != 0)) break;
         const int64_t i = base + threadIdx.x;
-        const bool ok = i < n;
-        const unsigned long long v = ok ? sk[i] : 0;
+        const unsigned long long v = i < n ? sk[i] : 0;
+        const bool ok = v != 0;  // 0 = "no state" (unused output slot of the grouped level); flip_f64 never yields it
         const unsigned act = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const unsigned peers = __match_any_sync(act, v);
@@ -996,9 +1027,11 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
 #pragma unroll
     for (int q = 0; q < CUT_ITEMS; ++q) {
         bool k = false;
-        if (b0 + q < n) {
-            x[q] = sk[b0 + q] - sk_min;
-            load_tie_key(kb, ks, b0 + q, link_top, lo[q], hi[q]);
+        const uint64_t v = b0 + q < n ? sk[b0 + q] : 0;
+        if (v != 0) {  // 0 = unused output slot
+            x[q] = v - sk_min;
+            lo[q] = hi[q] = 0;
+            if (keep_all || x[q] >= T) load_tie_key(kb, ks, b0 + q, link_top, lo[q], hi[q]);  // states below the cut: score only
             if (keep_all || x[q] > T) k = true;
             else if (x[q] == T) k = all_ties || hi[q] > Thi || (hi[q] == Thi && lo[q] >= Tlo);
             if (k) { or_lo |= lo[q]; or_hi |= hi[q]; and_lo &= lo[q]; and_hi &= hi[q]; }

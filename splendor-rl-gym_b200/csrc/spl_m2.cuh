@@ -33,6 +33,9 @@ constexpr int SMALL_ITEMS = 32;        // runs handled by one warp: at most 32 i
 constexpr int SMALL_W = 128;
 constexpr int SM_TBL = 256;            // per-warp dedup slots (> SMALL_W, power of two)
 constexpr int SM_STAGE = 48;           // per-warp winner staging (flushed above 16 entries)
+struct GroupArgs;
+constexpr int NUM_CLS = 8;             // run classes; used: CLS_WARP (one warp per run), CLS_CTA (one CTA per run)
+constexpr int CLS_WARP = 6, CLS_CTA = 7;
 constexpr int M2_WARPS = TILE / 32;
 constexpr int BIG_DONE = 16;           // distinct card sets one equal-hash run of the CTA kernel may hold
 
@@ -107,8 +110,8 @@ __global__ void __launch_bounds__(TILE) m2_rehash_kernel(const uint64_t *__restr
 __global__ void __launch_bounds__(TILE) m2_count_kernel(const Rec *__restrict__ front, int64_t np,
                                                         const DevTables *__restrict__ tabs,
                                                         const uint32_t *__restrict__ takes_idx,
-                                                        uint32_t *__restrict__ boff, uint64_t *__restrict__ ik,
-                                                        uint32_t *__restrict__ iidx, uint8_t *__restrict__ ntk8,
+                                                        uint32_t *__restrict__ boff, uint64_t *__restrict__ iv,
+                                                        uint8_t *__restrict__ ntk8,
                                                         uint64_t *status, Counters *ctr, int ticket_id) {
     __shared__ SmemTabs s;
     __shared__ uint32_t warp_sums[TILE / 32 + 1];
@@ -128,8 +131,7 @@ __global__ void __launch_bounds__(TILE) m2_count_kernel(const Rec *__restrict__ 
         derive_parent(s, takes_idx, r.lo, r.hi, r.aux, bl, bh, nb, tk);
         ntk = tk & 0xff;
         mask_words(r.lo, r.hi, m0, m1);
-        ik[p] = mask_hash(m0, m1) >> 32;
-        iidx[p] = (uint32_t)p;
+        iv[p] = (mask_hash(m0, m1) & 0xFFFFFFFF00000000ull) | (uint64_t)p;  // item = sort key << 32 | item id
         ntk8[p] = (uint8_t)ntk;
     }
     uint32_t total, total_tk;
@@ -160,8 +162,7 @@ __global__ void __launch_bounds__(TILE) m2_buys_kernel(const Rec *__restrict__ f
                                                        const DevTables *__restrict__ tabs,
                                                        const uint32_t *__restrict__ takes_idx,
                                                        const uint32_t *__restrict__ boff, int64_t rank_base,
-                                                       Rec *__restrict__ brec, uint64_t *__restrict__ ik,
-                                                       uint32_t *__restrict__ iidx) {
+                                                       Rec *__restrict__ brec, uint64_t *__restrict__ iv) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BuySmem &S = *reinterpret_cast<BuySmem *>(smem_raw);
     const unsigned tid = threadIdx.x;
@@ -217,9 +218,77 @@ __global__ void __launch_bounds__(TILE) m2_buys_kernel(const Rec *__restrict__ f
             st_rec(brec + g, r);
             uint64_t m0, m1;
             mask_words(klo, khi, m0, m1);
-            ik[np + g] = mask_hash(m0, m1) >> 32;
-            iidx[np + g] = (uint32_t)(np + g);
+            iv[np + g] = (mask_hash(m0, m1) & 0xFFFFFFFF00000000ull) | (uint64_t)(np + g);
         }
+    }
+}
+
+// ------------------------------------------------------------------ 2. sort of the packed items
+// One stable LSD pass over 64-bit values (digit = bits shift..shift+7), tile = 4096 values per CTA.  Per-tile digit
+// counts come from sort_hist_kernel + scan_u32_kernel (digit-major matrix).  The tile is first ordered by digit
+// in shared memory, so that consecutive threads write consecutive addresses of each digit's output range (whole
+// sectors) instead of scattering single values.
+__global__ void __launch_bounds__(TILE) psort_scatter_kernel(const uint64_t *__restrict__ v_in, int64_t n, int shift,
+                                                             const uint32_t *__restrict__ matrix_scanned, uint32_t ntiles,
+                                                             uint64_t *__restrict__ v_out) {
+    __shared__ uint32_t whist[TILE / 32][SORT_BINS];
+    __shared__ uint32_t dbase[SORT_BINS], gbase[SORT_BINS];
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint64_t stage[SORT_TILE];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (TILE / 32) * SORT_BINS; i += TILE) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t tbase = (int64_t)blockIdx.x * SORT_TILE, wbase = tbase + (int64_t)w * (32 * SORT_ITEMS);
+    uint64_t v[SORT_ITEMS];
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS; ++q) {  // the warp's contiguous 512-value segment, 32 consecutive values per step
+        const int64_t i = wbase + q * 32 + lane;
+        const bool ok = i < n;
+        v[q] = ok ? v_in[i] : 0;
+        const uint32_t d = (uint32_t)(v[q] >> shift) & (SORT_BINS - 1);
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(act, d);
+            if (lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit d = threadIdx.x: exclusive over warps; tile-local start of the digit; its global base for this tile
+        const uint32_t d = threadIdx.x;
+        uint32_t run = 0;
+        for (int ww = 0; ww < TILE / 32; ++ww) {
+            const uint32_t c = whist[ww][d];
+            whist[ww][d] = run;
+            run += c;
+        }
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(run, warp_sums, tot);
+        dbase[d] = ex;
+        gbase[d] = matrix_scanned[(uint64_t)d * ntiles + blockIdx.x];
+        for (int ww = 0; ww < TILE / 32; ++ww) whist[ww][d] += ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS; ++q) {  // stable placement inside the tile
+        const int64_t i = wbase + q * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = (uint32_t)(v[q] >> shift) & (SORT_BINS - 1);
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(act, d);
+            stage[whist[w][d] + __popc(peers & ((1u << lane) - 1))] = v[q];
+            __syncwarp(peers);
+            if (lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    const uint32_t cnt = (uint32_t)min((int64_t)SORT_TILE, n - tbase);
+    for (uint32_t i = threadIdx.x; i < cnt; i += TILE) {
+        const uint64_t x = stage[i];
+        const uint32_t d = (uint32_t)(x >> shift) & (SORT_BINS - 1);
+        v_out[gbase[d] + (i - dbase[d])] = x;
     }
 }
 
@@ -227,8 +296,8 @@ __global__ void __launch_bounds__(TILE) m2_buys_kernel(const Rec *__restrict__ f
 // run_start[r] = first sorted item of run r, run_wpre[r] = candidates (takes of parents + buy records)
 // in the runs before r.  Two look-back chains (run count, weight) walked by two warps at once.
 constexpr int RUN_ITEMS = 8;
-__global__ void __launch_bounds__(TILE) m2_runs_kernel(const uint64_t *__restrict__ ik, const uint32_t *__restrict__ iidx,
-                                                       int64_t n_items, uint32_t np, const uint8_t *__restrict__ ntk8,
+__global__ void __launch_bounds__(TILE) m2_runs_kernel(const uint64_t *__restrict__ iv, int64_t n_items, uint32_t np,
+                                                       const uint8_t *__restrict__ ntk8,
                                                        uint32_t *__restrict__ run_start, uint32_t *__restrict__ run_wpre,
                                                        uint64_t *status_f, uint64_t *status_w, Counters *ctr, int ticket_id) {
     __shared__ uint32_t warp_sums[TILE / 32 + 1];
@@ -239,16 +308,16 @@ __global__ void __launch_bounds__(TILE) m2_runs_kernel(const uint64_t *__restric
     const uint32_t tile = s_tile;
     const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * RUN_ITEMS;
     uint32_t flags = 0, w[RUN_ITEMS], fsum = 0, wsum = 0;
-    uint64_t prev = (b0 > 0 && b0 - 1 < n_items) ? ik[b0 - 1] : 0;
+    uint64_t prev = (b0 > 0 && b0 - 1 < n_items) ? iv[b0 - 1] >> 32 : 0;
 #pragma unroll
     for (int q = 0; q < RUN_ITEMS; ++q) {
         const int64_t i = b0 + q;
         w[q] = 0;
         if (i < n_items) {
-            const uint64_t k = ik[i];
+            const uint64_t v = iv[i], k = v >> 32;
             if (i == 0 || k != prev) { flags |= 1u << q; ++fsum; }
             prev = k;
-            const uint32_t id = iidx[i];
+            const uint32_t id = (uint32_t)v;
             w[q] = id < np ? ntk8[id] : 1u;
             wsum += w[q];
         }
@@ -285,8 +354,7 @@ __global__ void __launch_bounds__(TILE) m2_runs_kernel(const uint64_t *__restric
 struct GroupArgs {
     const Rec *front;              // the round's parents (rank order)
     const Rec *brec;               // the round's buy records
-    const uint64_t *ik;            // sorted keys (unused by the kernels, kept for debugging)
-    const uint32_t *iidx;          // sorted item ids: < np parent, else np + buy index
+    const uint64_t *iv;            // sorted items: sort key << 32 | item id (id < np: parent, else np + buy index)
     const uint32_t *run_start, *run_wpre;
     uint32_t np;
     int64_t rank_base;             // global rank of parent 0 of the round
@@ -296,209 +364,389 @@ struct GroupArgs {
     const uint16_t *gemrank;
     uint64_t *nodes;
     uint64_t nn;
-    Rec *out;                      // winners (any order) ...
-    uint64_t *out_sk;              // ... and their order-preserving score keys (null: no scoring)
+    // Output: winners (any order; link carries the arrival order) and their order-preserving score keys, appended
+    // densely at out_base + ctr->n_emitted (reserved in batches: per CTA / per 17..48 staged records / per run)
+    Rec *out;
+    uint64_t *out_sk;
     uint64_t out_base;
-    uint32_t *big_list;
+    uint32_t *cls_list[NUM_CLS];   // run lists per candidate-count class (m2_dispatch_kernel)
     int h, noise_mode;
     ScoreLuts L;
     Counters *ctr;
 };
 
-struct SmallSmem {
-    SmemTabs tabs;
-    uint64_t tbl[M2_WARPS][SM_TBL];
-    uint64_t st[5][M2_WARPS][SM_STAGE];  // lo, hi, aux, link, sk
+// ---- warp kernel: one warp per run.  The candidates of a run are visited in ARRIVAL ORDER, so "first arrival
+// wins" (src/solver.py:447-450) needs nothing but the node's bitmap: a candidate whose bit is clear is the first
+// arrival of its gem hand (it sets the bit), every later one finds the bit set.  Arrival order inside a run:
+//   * the run's parents are in rank order and its buy records in (generating parent, ordinal) order -- the sort is
+//     stable and both were generated in that order;
+//   * all takes of a parent P carry t = P << 8 | ordinal, a buy record carries t = Q << 8 | ordinal of its
+//     generating parent Q, and Q != P for every parent P of the run (Q owns one card less than the run's card
+//     set), so merging the two lists by rank alone yields the arrival order.
+__device__ __forceinline__ uint32_t item_id(const GroupArgs &A, uint32_t i) { return (uint32_t)A.iv[i]; }
+
+// per-warp winner staging: records are collected in shared memory and written out 17..48 at a time behind one
+// global atomic (dense output, few same-address atomics)
+struct WarpStage {
+    uint64_t *lo, *hi, *aux, *link, *sk;  // [SM_STAGE] each (shared memory of this warp)
+    uint32_t cnt;                        // warp-uniform
+    uint64_t kmin, kmax;
 };
-
-__device__ __forceinline__ uint32_t sm_slot(uint32_t g) { return (g * 0x9E3779B1u) >> 24; }
-// entry = (gems + 1) << 48 | t : same gems share the high part, so atomicMin keeps the first arrival
-__device__ __forceinline__ void sm_insert(uint64_t *tbl, uint32_t g, uint64_t t) {
-    const uint64_t mine = ((uint64_t)(g + 1) << 48) | t;
-    uint32_t s = sm_slot(g);
-    for (;;) {
-        uint64_t cur = tbl[s];
-        if (cur == 0) {
-            cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tbl[s]), 0ull, (unsigned long long)mine);
-            if (cur == 0) return;
-        }
-        if ((cur >> 48) == (mine >> 48)) {
-            atomicMin(reinterpret_cast<unsigned long long *>(&tbl[s]), (unsigned long long)mine);
-            return;
-        }
-        s = (s + 1) & (SM_TBL - 1);
+__device__ __forceinline__ void stage_flush(const GroupArgs &A, WarpStage &W) {
+    const unsigned lane = threadIdx.x & 31;
+    __syncwarp();
+    uint64_t base = 0;
+    if (lane == 0) base = atomicAdd(&A.ctr->n_emitted, (unsigned long long)W.cnt);
+    base = __shfl_sync(0xffffffffu, base, 0) + A.out_base;
+    for (uint32_t i = lane; i < W.cnt; i += 32) {
+        Rec r{W.lo[i], W.hi[i], W.aux[i], W.link[i]};
+        st_rec(A.out + base + i, r);
+        if (A.out_sk) A.out_sk[base + i] = W.sk[i];
     }
-}
-__device__ __forceinline__ bool sm_is_first(const uint64_t *tbl, uint32_t g, uint64_t t) {
-    const uint64_t mine = ((uint64_t)(g + 1) << 48) | t;
-    uint32_t s = sm_slot(g);
-    for (;;) {
-        const uint64_t cur = tbl[s];
-        if (cur == 0) return false;
-        if ((cur >> 48) == (mine >> 48)) return cur == mine;
-        s = (s + 1) & (SM_TBL - 1);
-    }
+    W.cnt = 0;
+    __syncwarp();
 }
 
-// One warp per run of at most SMALL_ITEMS items / SMALL_W candidates (the vast majority of runs); larger
-// runs are queued for the CTA kernel.  Persistent grid: warp w takes runs w, w + W, ... so that at any
-// moment the grid works on a window of consecutive runs == consecutive nodes.
-__global__ void __launch_bounds__(TILE, 4) m2_group_small_kernel(GroupArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmallSmem &S = *reinterpret_cast<SmallSmem *>(smem_raw);
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    load_tabs(S.tabs, A.tabs);
-    __syncthreads();
-    uint64_t *tbl = S.tbl[w];
-    const uint32_t R = A.ctr->n_runs;
-    uint32_t cnt = 0, n_fresh = 0;  // staged winners (warp-uniform), nodes created (lane 0)
-    uint64_t kmin = ~0ull, kmax = 0;
-    auto flush = [&]() {
-        uint64_t base = 0;
-        if (lane == 0) base = atomicAdd(&A.ctr->n_emitted, (unsigned long long)cnt);
-        base = __shfl_sync(0xffffffffu, base, 0) + A.out_base;
-        for (uint32_t i = lane; i < cnt; i += 32) {
-            Rec r{S.st[0][w][i], S.st[1][w][i], S.st[2][w][i], S.st[3][w][i]};
-            st_rec(A.out + base + i, r);
-            if (A.out_sk) A.out_sk[base + i] = S.st[4][w][i];
+// Open the node of card set (M0, M1) for this warp: the whole 384-byte node at the home slot is fetched in one
+// round trip (header + bitmap, 48 words over the lanes); if the home slot holds the set, or is empty and this warp
+// claims it, nothing else is read.  bm[0..45] (shared memory of the warp) receives the bitmap.
+__device__ __forceinline__ uint64_t *node_open(const GroupArgs &A, uint64_t M0, uint64_t M1, uint64_t *bm, uint32_t &n_fresh) {
+    const unsigned lane = threadIdx.x & 31;
+    uint64_t i = __umul64hi(mask_hash(M0, M1), A.nn);
+    const uint64_t *H = A.nodes + i * NODE_WORDS;
+    uint64_t w0, w1 = 0;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(w0) : "l"(H + lane));
+    if (lane < 16) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(w1) : "l"(H + 32 + lane));
+    uint64_t h0 = __shfl_sync(0xffffffffu, w0, 0), h1 = __shfl_sync(0xffffffffu, w0, 1);
+    int state = 0;  // 0: another set lives here (probe on), 1: found, 2: claimed now (fresh)
+    if (lane == 0) {
+        if (h1 == 0) {
+            cas128(A.nodes + i * NODE_WORDS, 0, 0, M0, M1 | NODE_OCC, h0, h1);
+            if ((h0 | h1) == 0) state = 2;
         }
-        cnt = 0;
-        __syncwarp();
-    };
-    for (uint32_t r = blockIdx.x * M2_WARPS + w; r < R; r += gridDim.x * M2_WARPS) {
-        const uint32_t s = A.run_start[r], e = A.run_start[r + 1];
-        const uint32_t wgt = A.run_wpre[r + 1] - A.run_wpre[r];
-        if (e - s > SMALL_ITEMS || wgt > SMALL_W) {
-            if (lane == 0) A.big_list[atomicAdd(&A.ctr->n_big, 1u)] = r;
-            continue;
+        if (state == 0 && h0 == M0 && h1 == (M1 | NODE_OCC)) state = 1;
+    }
+    state = __shfl_sync(0xffffffffu, state, 0);
+    if (state == 0) {  // collision at the home slot: ordinary probe sequence, then fetch that node's bitmap
+        int fresh_i = 0;
+        if (lane == 0) {
+            bool fresh;
+            i = node_find_or_create(A.nodes, A.nn, M0, M1, fresh, &A.ctr->error);
+            fresh_i = fresh;
         }
-        // ---- one item per lane
-        const bool valid = s + lane < e;
-        Rec it{0, 0, 0, 0};
-        bool isP = false;
-        uint32_t nb = 0, tk = 0;
-        uint64_t grank = 0, m0 = 0, m1 = 0;
-        if (valid) {
-            const uint32_t id = A.iidx[s + lane];
-            isP = id < A.np;
-            if (isP) {
-                ld_rec(A.front + id, it);
-                uint64_t bl, bh;
-                derive_parent(S.tabs, A.takes_idx, it.lo, it.hi, it.aux, bl, bh, nb, tk);
-                grank = (uint64_t)(A.rank_base + id);
-            } else {
-                ld_rec(A.brec + (id - A.np), it);
-            }
-            mask_words(it.lo, it.hi, m0, m1);
-        }
-        unsigned pending = __ballot_sync(0xffffffffu, valid);
-        while (pending) {  // one iteration per distinct card set of the run (almost always one)
-            const int lead = __ffs(pending) - 1;
-            const uint64_t M0 = __shfl_sync(0xffffffffu, m0, lead), M1 = __shfl_sync(0xffffffffu, m1, lead);
-            const bool mine = valid && m0 == M0 && m1 == M1;
-            const unsigned grp = __ballot_sync(0xffffffffu, mine);
-            pending &= ~grp;
-            uint64_t node = 0;
-            int fresh_i = 0;
-            if (lane == 0) {
-                bool fresh;
-                node = node_find_or_create(A.nodes, A.nn, M0, M1, fresh, &A.ctr->error);
-                fresh_i = fresh;
-                n_fresh += fresh;
-            }
-            node = __shfl_sync(0xffffffffu, node, 0);
-            const bool fresh = __shfl_sync(0xffffffffu, fresh_i, 0);
-            uint64_t *N = A.nodes + node * NODE_WORDS;
-#pragma unroll
-            for (int i = 0; i < SM_TBL / 32; ++i) tbl[i * 32 + lane] = 0;
-            __syncwarp();
-            const unsigned pm = __ballot_sync(0xffffffffu, mine && isP);
-            for (int pass = 0; pass < 2; ++pass) {
-                // buy records of this card set: one candidate per lane
-                {
-                    const bool act = mine && !isP;
-                    const uint32_t g = (uint32_t)(it.lo & GEM_MASK);
-                    bool win = false;
-                    uint32_t rk = 0;
-                    if (act) {
-                        rk = __ldg(A.gemrank + g);
-                        if (pass == 0) { if (fresh || !node_bit(N, rk)) sm_insert(tbl, g, it.link); }
-                        else win = sm_is_first(tbl, g, it.link);
-                    }
-                    if (pass == 1) {
-                        const unsigned wb = __ballot_sync(0xffffffffu, win);
-                        if (win) {
-                            const uint32_t at = cnt + __popc(wb & ((1u << lane) - 1));
-                            S.st[0][w][at] = it.lo; S.st[1][w][at] = it.hi; S.st[2][w][at] = it.aux; S.st[3][w][at] = it.link;
-                            if (A.out_sk) {
-                                const uint64_t k = flip_f64((uint64_t)__double_as_longlong(
-                                    score_state(A.h, A.noise_mode, it.lo, it.hi & HI_KEY_MASK, it.aux, A.L)));
-                                S.st[4][w][at] = k;
-                                kmin = min(kmin, k); kmax = max(kmax, k);
-                            }
-                            atomicOr(reinterpret_cast<unsigned long long *>(N + 2 + (rk >> 6)), 1ull << (rk & 63));
-                        }
-                        cnt += __popc(wb);
-                        __syncwarp();
-                        if (cnt > SM_STAGE - 32) flush();
-                    }
-                }
-                // gem takes of this card set's parents (src/solver.py:381-388), 32 table edges at a time
-                for (unsigned rest = pm; rest; rest &= rest - 1) {
-                    const int P = __ffs(rest) - 1;
-                    const uint64_t plo = __shfl_sync(0xffffffffu, it.lo, P), phi = __shfl_sync(0xffffffffu, it.hi, P);
-                    const uint64_t paux = __shfl_sync(0xffffffffu, it.aux, P), pgr = __shfl_sync(0xffffffffu, grank, P);
-                    const uint32_t ptk = __shfl_sync(0xffffffffu, tk, P), pnb = __shfl_sync(0xffffffffu, nb, P);
-                    const uint32_t ntk = ptk & 0xff;
-                    for (uint32_t q0 = 0; q0 < ntk; q0 += 32) {
-                        const uint32_t q = q0 + lane;
-                        const bool act = q < ntk;
-                        uint32_t g = 0, rk = 0;
-                        uint64_t t = 0;
-                        bool win = false;
-                        if (act) {
-                            g = __ldg(A.takes_edges + (ptk >> 8) + q);
-                            rk = __ldg(A.gemrank + g);
-                            t = (pgr << 8) | (pnb + q);
-                            if (pass == 0) { if (fresh || !node_bit(N, rk)) sm_insert(tbl, g, t); }
-                            else win = sm_is_first(tbl, g, t);
-                        }
-                        if (pass == 1) {
-                            const unsigned wb = __ballot_sync(0xffffffffu, win);
-                            if (win) {
-                                const uint32_t at = cnt + __popc(wb & ((1u << lane) - 1));
-                                const uint64_t clo = (plo & ~GEM_MASK) | g;
-                                S.st[0][w][at] = clo; S.st[1][w][at] = phi; S.st[2][w][at] = paux; S.st[3][w][at] = t;
-                                if (A.out_sk) {
-                                    const uint64_t k = flip_f64((uint64_t)__double_as_longlong(
-                                        score_state(A.h, A.noise_mode, clo, phi & HI_KEY_MASK, paux, A.L)));
-                                    S.st[4][w][at] = k;
-                                    kmin = min(kmin, k); kmax = max(kmax, k);
-                                }
-                                atomicOr(reinterpret_cast<unsigned long long *>(N + 2 + (rk >> 6)), 1ull << (rk & 63));
-                            }
-                            cnt += __popc(wb);
-                            __syncwarp();
-                            if (cnt > SM_STAGE - 32) flush();
-                        }
-                    }
-                }
-                __syncwarp();  // pass 0 inserts (and bitmap reads) complete before pass 1 reads the table (and sets bits)
-            }
+        i = __shfl_sync(0xffffffffu, i, 0);
+        state = __shfl_sync(0xffffffffu, fresh_i, 0) ? 2 : 1;
+        if (state == 1) {
+            H = A.nodes + i * NODE_WORDS;
+            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(w0) : "l"(H + lane));
+            if (lane < 16) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(w1) : "l"(H + 32 + lane));
         }
     }
-    if (cnt) flush();
+    if (state == 2) { w0 = 0; w1 = 0; if (lane == 0) ++n_fresh; }
+    if (lane >= 2) bm[lane - 2] = w0;
+    if (lane < 16) bm[30 + lane] = w1;
+    __syncwarp();
+    return A.nodes + i * NODE_WORDS;
+}
+__device__ __forceinline__ void node_close(uint64_t *N, const uint64_t *bm) {
+    const unsigned lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane >= 2) N[lane] = bm[lane - 2];
+    if (lane < 16) N[32 + lane] = bm[30 + lane];
+}
+
+// One step of the arrival-ordered walk: up to 32 candidates (act lanes), EARLIER arrivals on lower lanes.  `dups`:
+// several lanes may carry the same gem hand (buy records of different parents), then the lowest lane speaks for it.
+// A candidate wins iff its bit was clear; winners are staged with their scores.  Called by all 32 lanes.
+__device__ __forceinline__ void bm_step(const GroupArgs &A, WarpStage &W, uint64_t *bm, bool act, bool dups, uint32_t g,
+                                        uint64_t t, uint64_t clo, uint64_t chi, uint64_t caux) {
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t rk = 0;
+    if (act) rk = __ldg(A.gemrank + g);
+    bool lead = act;
+    if (dups) {
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (act) lead = lane == (unsigned)(__ffs(__match_any_sync(m, rk)) - 1);
+    }
+    bool win = false;
+    if (lead) {
+        const unsigned long long bit = 1ull << (rk & 63);
+        win = !(atomicOr(reinterpret_cast<unsigned long long *>(&bm[rk >> 6]), bit) & bit);
+    }
+    const unsigned wb = __ballot_sync(0xffffffffu, win);
+    if (win) {
+        const uint32_t at = W.cnt + __popc(wb & ((1u << lane) - 1));
+        W.lo[at] = clo; W.hi[at] = chi; W.aux[at] = caux; W.link[at] = t;
+        if (A.out_sk) {
+            const uint64_t k = flip_f64((uint64_t)__double_as_longlong(score_state(A.h, A.noise_mode, clo, chi & HI_KEY_MASK, caux, A.L)));
+            W.sk[at] = k;
+            W.kmin = min(W.kmin, k); W.kmax = max(W.kmax, k);
+        }
+    }
+    W.cnt += __popc(wb);
+    if (W.cnt > SM_STAGE - 32) stage_flush(A, W);
+}
+// the gem takes (src/solver.py:381-388) of one parent (fields warp-uniform), 32 table edges per step
+__device__ __forceinline__ void take_steps(const GroupArgs &A, WarpStage &W, uint64_t *bm, uint64_t plo, uint64_t phi, uint64_t paux,
+                                           uint64_t pgr, uint32_t ptk, uint32_t pnb) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t ntk = ptk & 0xff;
+    for (uint32_t q0 = 0; q0 < ntk; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        const bool act = q < ntk;
+        const uint32_t g = act ? (uint32_t)__ldg(A.takes_edges + (ptk >> 8) + q) : 0u;
+        bm_step(A, W, bm, act, false, g, (pgr << 8) | (pnb + q), (plo & ~GEM_MASK) | g, phi, paux);
+    }
+}
+// item `i` of the sorted list -> record, parent fan-out, card-set words
+__device__ __forceinline__ void load_item(const GroupArgs &A, const SmemTabs &tabs, uint32_t i, Rec &it, bool &isP, uint32_t &nb,
+                                          uint32_t &tk, uint64_t &grank, uint64_t &m0, uint64_t &m1) {
+    const uint32_t id = item_id(A, i);
+    isP = id < A.np;
+    nb = tk = 0;
+    grank = 0;
+    if (isP) {
+        ld_rec(A.front + id, it);
+        uint64_t bl, bh;
+        derive_parent(tabs, A.takes_idx, it.lo, it.hi, it.aux, bl, bh, nb, tk);
+        grank = (uint64_t)(A.rank_base + id);
+    } else {
+        ld_rec(A.brec + (id - A.np), it);
+        grank = it.link >> 8;  // rank of the generating parent
+    }
+    mask_words(it.lo, it.hi, m0, m1);
+}
+__device__ __forceinline__ void warp_epilogue(const GroupArgs &A, WarpStage &W, uint32_t n_fresh) {
+    const unsigned lane = threadIdx.x & 31;
+    if (W.cnt) stage_flush(A, W);
     if (lane == 0 && n_fresh) atomicAdd(&A.ctr->n_new_nodes, n_fresh);
     if (A.out_sk) {
 #pragma unroll
         for (int d = 16; d; d >>= 1) {
-            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
-            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+            W.kmin = min(W.kmin, __shfl_xor_sync(0xffffffffu, W.kmin, d));
+            W.kmax = max(W.kmax, __shfl_xor_sync(0xffffffffu, W.kmax, d));
         }
-        if (lane == 0 && kmin <= kmax) {
-            atomicMin(&A.ctr->sk_min, (unsigned long long)kmin);
-            atomicMax(&A.ctr->sk_max, (unsigned long long)kmax);
+        if (lane == 0 && W.kmin <= W.kmax) {
+            atomicMin(&A.ctr->sk_min, (unsigned long long)W.kmin);
+            atomicMax(&A.ctr->sk_max, (unsigned long long)W.kmax);
         }
+    }
+}
+
+struct WarpSmem {
+    SmemTabs tabs;
+    uint64_t bm[M2_WARPS][NODE_BM_WORDS + 2];
+    uint64_t st[5][M2_WARPS][SM_STAGE];  // lo, hi, aux, link, sk
+};
+
+// Class CLS_WARP of the dispatch (THREAD_W < candidates <= WARP_W): one warp per run.  The run is streamed through a
+// parent window and a buy-record window of 32 lanes each, once per card set it holds (almost always one; several
+// only when two sets share a 32-bit sort key).  Persistent grid: warp w takes list entries w, w + W, ...
+constexpr int MAX_SETS = 4;  // card sets under one sort key that the thread / warp kernels can tell apart
+__global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem &S = *reinterpret_cast<WarpSmem *>(smem_raw);
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    load_tabs(S.tabs, A.tabs);
+    __syncthreads();
+    uint64_t *bm = S.bm[w];
+    WarpStage W{S.st[0][w], S.st[1][w], S.st[2][w], S.st[3][w], S.st[4][w], 0, ~0ull, 0};
+    const uint32_t n_list = A.ctr->n_cls[CLS_WARP];
+    uint32_t n_fresh = 0;
+    for (uint32_t j = blockIdx.x * M2_WARPS + w; j < n_list; j += gridDim.x * M2_WARPS) {
+        const uint32_t r = A.cls_list[CLS_WARP][j];
+        const uint32_t s = A.run_start[r], e = A.run_start[r + 1];
+        // parents [s, pe), buy records [pe, e)
+        uint32_t pe = s;
+        for (uint32_t b0 = s; b0 < e; b0 += 32) {
+            const unsigned pm = __ballot_sync(0xffffffffu, b0 + lane < e && item_id(A, b0 + lane) < A.np);
+            pe += __popc(pm);
+            if (pm != 0xffffffffu) break;
+        }
+        uint64_t d0[MAX_SETS], d1[MAX_SETS];  // card sets done so far
+        int n_done = 0;
+        uint32_t lead = s;
+        while (lead != 0xFFFFFFFFu) {
+            uint64_t M0 = 0, M1 = 0;
+            if (lane == 0) {
+                const uint32_t id = item_id(A, lead);
+                const Rec *src = id < A.np ? A.front + id : A.brec + (id - A.np);
+                mask_words(src->lo, src->hi, M0, M1);
+            }
+            M0 = __shfl_sync(0xffffffffu, M0, 0); M1 = __shfl_sync(0xffffffffu, M1, 0);
+            uint64_t *N = node_open(A, M0, M1, bm, n_fresh);
+            uint32_t next_lead = 0xFFFFFFFFu;
+            Rec it{0, 0, 0, 0}, bt{0, 0, 0, 0};
+            uint32_t nb = 0, tk = 0;
+            uint64_t grank = 0, brank = 0;
+            uint32_t bnext = pe, pnext = s;   // first item not loaded into a window yet
+            unsigned bmask = 0, pmask = 0;
+            for (;;) {
+                if (!pmask && pnext < pe) {  // refill the parent window
+                    const bool valid = pnext + lane < pe;
+                    bool p_;
+                    uint64_t m0 = 0, m1 = 0;
+                    if (valid) load_item(A, S.tabs, pnext + lane, it, p_, nb, tk, grank, m0, m1);
+                    const bool ok = valid && m0 == M0 && m1 == M1;
+                    bool other = valid && !ok;  // a card set not walked yet?
+#pragma unroll
+                    for (int d = 0; d < MAX_SETS; ++d) other = other && !(d < n_done && d0[d] == m0 && d1[d] == m1);
+                    const unsigned om = __ballot_sync(0xffffffffu, other);
+                    if (om) next_lead = min(next_lead, pnext + (uint32_t)__ffs(om) - 1);
+                    pmask = __ballot_sync(0xffffffffu, ok);
+                    pnext += 32;
+                    continue;
+                }
+                if (!bmask && bnext < e) {  // refill the buy window
+                    const bool valid = bnext + lane < e;
+                    uint64_t m0 = 0, m1 = 0;
+                    if (valid) {
+                        ld_rec(A.brec + (item_id(A, bnext + lane) - A.np), bt);
+                        mask_words(bt.lo, bt.hi, m0, m1);
+                        brank = bt.link >> 8;
+                    }
+                    const bool ok = valid && m0 == M0 && m1 == M1;
+                    bool other = valid && !ok;
+#pragma unroll
+                    for (int d = 0; d < MAX_SETS; ++d) other = other && !(d < n_done && d0[d] == m0 && d1[d] == m1);
+                    const unsigned om = __ballot_sync(0xffffffffu, other);
+                    if (om) next_lead = min(next_lead, bnext + (uint32_t)__ffs(om) - 1);
+                    bmask = __ballot_sync(0xffffffffu, ok);
+                    bnext += 32;
+                    continue;
+                }
+                if (!pmask && !bmask) break;
+                const uint64_t X = pmask ? __shfl_sync(0xffffffffu, grank, __ffs(pmask) - 1) : ~0ull;
+                const unsigned m = bmask & __ballot_sync(0xffffffffu, brank < X);
+                if (m) {  // the buy records of the window that arrive before the next parent
+                    bm_step(A, W, bm, (m >> lane) & 1, true, (uint32_t)(bt.lo & GEM_MASK), bt.link, bt.lo, bt.hi, bt.aux);
+                    bmask &= ~m;
+                } else {  // pmask != 0 here: every record left in the window arrives after parent X
+                    const int P = __ffs(pmask) - 1;
+                    pmask &= pmask - 1;
+                    take_steps(A, W, bm, __shfl_sync(0xffffffffu, it.lo, P), __shfl_sync(0xffffffffu, it.hi, P),
+                               __shfl_sync(0xffffffffu, it.aux, P), X, __shfl_sync(0xffffffffu, tk, P), __shfl_sync(0xffffffffu, nb, P));
+                }
+            }
+            node_close(N, bm);
+            if (next_lead != 0xFFFFFFFFu) {
+                if (n_done == MAX_SETS) { if (lane == 0) atomicExch(&A.ctr->error, 3u); break; }
+#pragma unroll
+                for (int d = 0; d < MAX_SETS; ++d)
+                    if (d == n_done) { d0[d] = M0; d1[d] = M1; }
+                ++n_done;
+            }
+            lead = next_lead;
+        }
+    }
+    warp_epilogue(A, W, n_fresh);
+}
+
+// ---- dispatch + thread kernel.  One thread per run: buy-only runs of at most TINY_ITEMS records of a single card
+// set (most runs: card sets that only pruned states ever reach) are finished right here -- the records of a run
+// are in arrival order (stable sort of records generated in (parent, ordinal) order), so the first occurrence of
+// a gem hand wins; every other run is appended to the list of its class (warp kernel up to BIG_W candidates, CTA
+// kernel beyond: one warp on a heavy run would keep the whole grid waiting).
+constexpr int TINY_ITEMS = 16;
+#ifndef SPL_BIG_W
+#define SPL_BIG_W 512
+#endif
+constexpr uint32_t BIG_W = SPL_BIG_W;
+__global__ void __launch_bounds__(TILE) m2_group_tiny_kernel(GroupArgs A, uint32_t n_runs) {
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint64_t s_base;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * TILE + threadIdx.x;
+    int cls = -1;  // -1 none, 0 handled here, CLS_WARP / CLS_CTA queued
+    uint32_t s = 0, cnt = 0, winmask = 0;
+    uint64_t *N = nullptr;
+    uint32_t n_fresh = 0;
+    uint64_t kmin = ~0ull, kmax = 0;
+    if (r < n_runs) {
+        s = A.run_start[r];
+        cnt = A.run_start[r + 1] - s;
+        const uint32_t id0 = item_id(A, s);
+        const uint32_t wgt = A.run_wpre[r + 1] - A.run_wpre[r];
+        if (cnt <= TINY_ITEMS && id0 >= A.np) cls = 0;
+        else cls = wgt <= BIG_W ? CLS_WARP : CLS_CTA;
+        if (cls == 0) {
+            uint64_t lo0, hi0, M0, M1;
+            ld_cg_u64x2(reinterpret_cast<const uint64_t *>(A.brec + (id0 - A.np)), lo0, hi0);
+            mask_words(lo0, hi0, M0, M1);
+            uint32_t gp[TINY_ITEMS / 2];  // gem hands, two per word
+#pragma unroll
+            for (int q = 0; q < TINY_ITEMS / 2; ++q) gp[q] = 0;
+            gp[0] = (uint32_t)(lo0 & GEM_MASK);
+            bool same = true;
+#pragma unroll
+            for (int j = 1; j < TINY_ITEMS; ++j) {
+                if (j < (int)cnt) {
+                    uint64_t lo, hi, m0, m1;
+                    ld_cg_u64x2(reinterpret_cast<const uint64_t *>(A.brec + (item_id(A, s + j) - A.np)), lo, hi);
+                    mask_words(lo, hi, m0, m1);
+                    same = same && m0 == M0 && m1 == M1;
+                    gp[j >> 1] |= (uint32_t)(lo & GEM_MASK) << (16 * (j & 1));
+                }
+            }
+            if (!same) {
+                cls = CLS_WARP;  // several card sets under one sort key: the warp kernel sorts that out
+            } else {
+                bool fresh;
+                const uint64_t node = node_find_or_create(A.nodes, A.nn, M0, M1, fresh, &A.ctr->error);
+                n_fresh = fresh;
+                N = A.nodes + node * NODE_WORDS;
+#pragma unroll
+                for (int j = 0; j < TINY_ITEMS; ++j) {
+                    if (j < (int)cnt) {
+                        const uint32_t g = (gp[j >> 1] >> (16 * (j & 1))) & 0x7fffu;
+                        bool dup = false;
+#pragma unroll
+                        for (int i = 0; i < j; ++i) dup = dup || ((gp[i >> 1] >> (16 * (i & 1))) & 0x7fffu) == g;
+                        if (!dup && (fresh || !node_bit(N, __ldg(A.gemrank + g)))) winmask |= 1u << j;
+                    }
+                }
+            }
+        }
+    }
+    // queue the runs of the other classes (one atomic per warp and class)
+#pragma unroll
+    for (int k = CLS_WARP; k <= CLS_CTA; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&A.ctr->n_cls[k], (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (cls == k) A.cls_list[k][base + __popc(m & ((1u << lane) - 1))] = r;
+        }
+    }
+    // winners of the runs finished here: one output reservation per CTA
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(__popc(winmask), warp_sums, tot);
+    if (threadIdx.x == 0 && tot) s_base = A.out_base + atomicAdd(&A.ctr->n_emitted, (unsigned long long)tot);
+    __syncthreads();
+    uint64_t pos = s_base + ex;
+    for (uint32_t m = winmask; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        Rec it;
+        ld_rec(A.brec + (item_id(A, s + j) - A.np), it);
+        st_rec(A.out + pos, it);
+        const uint64_t k = flip_f64((uint64_t)__double_as_longlong(score_state(A.h, A.noise_mode, it.lo, it.hi & HI_KEY_MASK, it.aux, A.L)));
+        A.out_sk[pos] = k;
+        kmin = min(kmin, k); kmax = max(kmax, k);
+        const uint32_t rk = __ldg(A.gemrank + (uint32_t)(it.lo & GEM_MASK));
+        atomicOr(reinterpret_cast<unsigned long long *>(N + 2 + (rk >> 6)), 1ull << (rk & 63));
+        ++pos;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        n_fresh += __shfl_xor_sync(0xffffffffu, n_fresh, d);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+    }
+    if (lane == 0 && n_fresh) atomicAdd(&A.ctr->n_new_nodes, n_fresh);
+    if (lane == 0 && kmin <= kmax) {
+        atomicMin(&A.ctr->sk_min, (unsigned long long)kmin);
+        atomicMax(&A.ctr->sk_max, (unsigned long long)kmax);
     }
 }
 
@@ -518,7 +766,7 @@ template <class F>
 __device__ __forceinline__ void big_enumerate(const GroupArgs &A, BigSmem &S, uint32_t s, uint32_t e, uint64_t M0, uint64_t M1,
                                               bool note_others, F &&f) {
     for (uint32_t i = s + threadIdx.x; i < e; i += TILE) {
-        const uint32_t id = A.iidx[i];
+        const uint32_t id = item_id(A, i);
         Rec it;
         const bool isP = id < A.np;
         if (isP) ld_rec(A.front + id, it); else ld_rec(A.brec + (id - A.np), it);
@@ -554,7 +802,7 @@ __global__ void __launch_bounds__(TILE) m2_group_big_kernel(GroupArgs A) {
     BigSmem &S = *reinterpret_cast<BigSmem *>(smem_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31;
     load_tabs(S.tabs, A.tabs);
-    const uint32_t n_big = A.ctr->n_big;
+    const uint32_t n_big = A.ctr->n_cls[CLS_CTA];
     uint32_t n_fresh = 0;
     uint64_t kmin = ~0ull, kmax = 0;
     for (;;) {
@@ -562,7 +810,7 @@ __global__ void __launch_bounds__(TILE) m2_group_big_kernel(GroupArgs A) {
         if (tid == 0) S.job = atomicAdd(&A.ctr->ticket[3], 1u);
         __syncthreads();
         if (S.job >= n_big) break;
-        const uint32_t r = A.big_list[S.job];
+        const uint32_t r = A.cls_list[CLS_CTA][S.job];
         const uint32_t s = A.run_start[r], e = A.run_start[r + 1];
         if (tid == 0) { S.n_done = 0; S.next = s; }
         __syncthreads();
@@ -570,7 +818,7 @@ __global__ void __launch_bounds__(TILE) m2_group_big_kernel(GroupArgs A) {
             const uint32_t lead = S.next;
             __syncthreads();
             if (tid == 0) {
-                const uint32_t id = A.iidx[lead];
+                const uint32_t id = item_id(A, lead);
                 const Rec *src = id < A.np ? A.front + id : A.brec + (id - A.np);
                 mask_words(src->lo, src->hi, S.m0, S.m1);
                 bool fresh;

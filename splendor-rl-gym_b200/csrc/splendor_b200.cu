@@ -69,7 +69,7 @@ struct spl_ctx {
     uint64_t *nodes = nullptr;
     uint64_t nn = 0, node_occ = 0, max_node_bytes = 0;
     uint16_t *d_gemrank = nullptr;
-    DevBuf brec, ntk8, boff2, run_start, run_wpre, big_list;
+    DevBuf brec, ntk8, boff2, run_start, run_wpre, cls_list;
     int tie_link_top = 0;  // > 0: the beam cut breaks score ties on the records' link words (arrival order)
     // constant tables
     DevTables *d_tabs = nullptr;
@@ -258,7 +258,7 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE, IDENT_PYHASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST, IDENT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(m2_buys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuySmem)));
-    CKC(cudaFuncSetAttribute(m2_group_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+    CKC(cudaFuncSetAttribute(m2_group_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
     CKC(cudaFuncSetAttribute(m2_group_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
     {
         c->max_node_bytes = cfg->max_node_bytes ? cfg->max_node_bytes : (uint64_t)(free_b * 0.5);
@@ -432,13 +432,31 @@ static int run_count(spl_ctx *c, const Rec *front, int64_t n, cudaStream_t st) {
 static int select_ties_by_key(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t k,
                               uint64_t sk_min, cudaStream_t st) {
     const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
-    const int lt = c->tie_link_top;  // arrival-order ties: one word of lt bits, the high word is constant 0
-    for (int word = lt ? 2 : 1; word <= 2; ++word) {
-        int top = word == 1 ? 41 : (lt ? lt : 64), first = 1;
+    const int lt = c->tie_link_top;
+    if (lt) {
+        // arrival-order ties: collect the tie words (2^lt - 1 - link) of the threshold score once, then select among them
+        const int64_t ntie = (int64_t)c->h_sel->tie_count;
+        CK(c, c->rtmp.ensure((size_t)ntie * 8 + 8, 0, st));
+        CK(c, cudaMemsetAsync(&c->d_ctr->n_ties, 0, 8, st));
+        tie_collect_kernel<<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, c->d_sel, lt, c->rtmp.as<uint64_t>(), c->d_ctr);
+        ++c->launches;
+        const unsigned tgrid = std::min<unsigned>(nblk(ntie), 148 * 8);
+        int top = lt, first = 1;
         while (top > 0) {
             const int bits = std::min(SEL_BITS, top), shift = top - bits;
-            if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist, lt);
-            else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist, lt);
+            sel_hist_kernel<3><<<tgrid, TILE, 0, st>>>(nullptr, c->rtmp.as<uint64_t>(), 1, ntie, 0, shift, bits, first, c->d_sel, c->d_hist);
+            sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, 2, shift, first, 0, (uint64_t)k, c->d_sel);
+            c->launches += 2;
+            first = 0;
+            top = shift;
+        }
+    } else
+    for (int word = 1; word <= 2; ++word) {
+        int top = word == 1 ? 41 : 64, first = 1;
+        while (top > 0) {
+            const int bits = std::min(SEL_BITS, top), shift = top - bits;
+            if (word == 1) sel_hist_kernel<1><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
+            else sel_hist_kernel<2><<<grid, TILE, 0, st>>>(sk, kb, ks, n, sk_min, shift, bits, first, c->d_sel, c->d_hist);
             sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, word, shift, first, 0, (uint64_t)k, c->d_sel);
             c->launches += 2;
             first = 0;
@@ -482,7 +500,8 @@ static int run_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks
 // element.  Leaves d_sel / h_sel as run_select does plus rank_t; *used = 0 when the level has more
 // than DICT_MAX distinct scores (nothing decided: the caller falls back to the radix select).
 static int run_dict_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int ks, int64_t n, int64_t k,
-                           uint64_t sk_min, int det, int *used, cudaStream_t st) {
+                           uint64_t sk_min, int det, int *used, cudaStream_t st, int keep_all = -1) {
+    if (keep_all < 0) keep_all = k >= n;
     *used = 0;
     if (c->dict_skip > 0) { --c->dict_skip; return SPL_OK; }
     const unsigned grid = std::min<unsigned>(nblk(n), 148 * 8);
@@ -503,7 +522,7 @@ static int run_dict_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, i
         return SPL_OK;
     }
     *used = 1;
-    if (det && k < n && c->h_sel->k_rem < c->h_sel->tie_count) CKS(c, select_ties_by_key(c, sk, kb, ks, n, k, sk_min, st));
+    if (det && !keep_all && c->h_sel->k_rem < c->h_sel->tie_count) CKS(c, select_ties_by_key(c, sk, kb, ks, n, k, sk_min, st));
     return SPL_OK;
 }
 
@@ -537,18 +556,20 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
                        int all_ties, uint64_t sk_min, uint64_t sk_max, int det, int use_dict, int *which, int64_t *kept_out,
                        cudaStream_t st);
 
+// n = elements of sk / recs; n_valid of them are states (the rest are unused slots, sk == 0)
 static int run_cut_sort(spl_ctx *c, const uint64_t *sk, const Rec *recs, int64_t n, int64_t k, uint64_t sk_min,
-                        uint64_t sk_max, int det, int *which, int64_t *kept_out, cudaStream_t st) {
-    const int keep_all = n <= k;
+                        uint64_t sk_max, int det, int *which, int64_t *kept_out, cudaStream_t st, int64_t n_valid = -1) {
+    if (n_valid < 0) n_valid = n;
+    const int keep_all = n_valid <= k;
     const uint64_t *kb = reinterpret_cast<const uint64_t *>(recs);
     const int ks = 4;
     int use_dict = 0;
-    CKS(c, run_dict_select(c, sk, kb, ks, n, std::min(n, k), sk_min, det, &use_dict, st));
+    CKS(c, run_dict_select(c, sk, kb, ks, n, std::min(n_valid, k), sk_min, det, &use_dict, st, keep_all));
     if (!keep_all && !use_dict) CKS(c, run_select(c, sk, kb, ks, n, k, sk_min, sk_max, det, st));
     const int all_ties = keep_all || c->h_sel->tie_count != ~0ull;
-    CKS(c, do_cut_sort(c, sk, kb, ks, n, std::min(n, k), keep_all, all_ties, sk_min, sk_max, det, use_dict, which, kept_out, st));
-    if (*kept_out != std::min(n, k))
-        return fail(c, SPL_E_CUDA, "internal: cut kept %lld states, expected %lld", (long long)*kept_out, (long long)std::min(n, k));
+    CKS(c, do_cut_sort(c, sk, kb, ks, n, std::min(n_valid, k), keep_all, all_ties, sk_min, sk_max, det, use_dict, which, kept_out, st));
+    if (*kept_out != std::min(n_valid, k))
+        return fail(c, SPL_E_CUDA, "internal: cut kept %lld states, expected %lld", (long long)*kept_out, (long long)std::min(n_valid, k));
     return SPL_OK;
 }
 
@@ -1126,13 +1147,12 @@ static int ensure_nodes(spl_ctx *c, uint64_t need, cudaStream_t st) {
 
 // expand + dedup (+ score) of the whole queue `front[0..n)` in rounds of parents; winners are appended to
 // s->uniq / c->sk in no particular order (their link words carry the arrival order)
-static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n_uniq_out, int64_t *generated_out,
+static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n_uniq_out, int64_t *n_slots_out, int64_t *generated_out,
                           uint64_t *sk_min_out, uint64_t *sk_max_out, float ms[5], cudaStream_t st) {
     spl_ctx *c = s->c;
     const int64_t chunk = c->chunk_user ? (int64_t)c->chunk_parents : (16ll << 20);
-    int64_t n_uniq = 0, generated = 0;
+    int64_t n_uniq = 0, n_slots = 0, generated = 0;
     uint64_t sk_min = ~0ull, sk_max = 0;
-    const bool score = s->use_h && s->noise != SPL_NOISE_EXTERNAL;
     for (int64_t p0 = 0; p0 < n; p0 += chunk) {
         const int64_t np = std::min<int64_t>(chunk, n - p0);
         const unsigned nt = nblk(np);
@@ -1141,14 +1161,12 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         CK(c, cudaEventRecord(c->ev[0], st));
         CK(c, c->boff2.ensure((size_t)np * 4 + 4, 0, st));
         CK(c, c->ntk8.ensure((size_t)np + 8, 0, st));
-        // items of the round = parents + buy records; their number is known after the count, so the key / id
-        // arrays are sized for the parents first and grown (contents kept) once the buys are counted
+        // items of the round = parents + buy records (packed: sort key << 32 | item id); the array is sized for the
+        // parents first and grown (contents kept) once the buys are counted
         CK(c, c->y[0].ensure((size_t)np * 8 + 8, 0, st));
-        CK(c, c->idx[0].ensure((size_t)np * 4 + 4, 0, st));
         CKS(c, prep_status(c, 0, nt, st));
         m2_count_kernel<<<nt, TILE, 0, st>>>(front + p0, np, c->d_tabs, c->d_takes_idx, c->boff2.as<uint32_t>(),
-                                              c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>(), c->ntk8.as<uint8_t>(),
-                                              c->status[0].as<uint64_t>(), c->d_ctr, 0);
+                                              c->y[0].as<uint64_t>(), c->ntk8.as<uint8_t>(), c->status[0].as<uint64_t>(), c->d_ctr, 0);
         ++c->launches;
         CK(c, cudaGetLastError());
         CKS(c, read_ctr(c, st));
@@ -1159,13 +1177,11 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         if (total >= 0xFFFFFFFFull || (uint64_t)n_items >= 0xFFFFFFFFull)
             return fail(c, SPL_E_INVALID, "round produced %llu candidates (>= 2^32): lower spl_config.chunk_parents", (unsigned long long)total);
         CK(c, c->y[0].ensure((size_t)n_items * 8 + 8, (size_t)np * 8, st));
-        CK(c, c->idx[0].ensure((size_t)n_items * 4 + 4, (size_t)np * 4, st));
         CK(c, c->y[1].ensure((size_t)n_items * 8 + 8, 0, st));
-        CK(c, c->idx[1].ensure((size_t)n_items * 4 + 4, 0, st));
         CK(c, c->brec.ensure((size_t)n_buys * 32 + 32, 0, st));
         if (n_buys) {
             m2_buys_kernel<<<nt, TILE, sizeof(BuySmem), st>>>(front + p0, np, c->d_tabs, c->d_takes_idx, c->boff2.as<uint32_t>(), p0,
-                                                               c->brec.as<Rec>(), c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>());
+                                                               c->brec.as<Rec>(), c->y[0].as<uint64_t>());
             ++c->launches;
             CK(c, cudaGetLastError());
         }
@@ -1177,9 +1193,18 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
             const size_t msz = (size_t)SORT_BINS * snt;
             CK(c, c->matrix.ensure(msz * 4, 0, st));
             CK(c, c->matrix2.ensure(msz * 4, 0, st));
+            const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
             if (n_items > 1)
-                for (int shift = 0; shift < 32; shift += SORT_BITS) {
-                    CKS(c, sort_pass(c, 0, cur, c->y[cur].as<uint64_t>(), n_items, shift, snt, msz, st));
+                for (int shift = 32; shift < 64; shift += SORT_BITS) {
+                    sort_hist_kernel<<<snt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), n_items, shift, c->matrix.as<uint32_t>(), snt);
+                    CKS(c, prep_status(c, 1, st_tiles, st));
+                    CKS(c, reset_ticket(c, 2, st));
+                    scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
+                                                                c->status[1].as<uint64_t>(), c->d_ctr, 2);
+                    psort_scatter_kernel<<<snt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), n_items, shift, c->matrix2.as<uint32_t>(), snt,
+                                                                c->y[cur ^ 1].as<uint64_t>());
+                    c->launches += 3;
+                    CK(c, cudaGetLastError());
                     cur ^= 1;
                 }
         }
@@ -1190,7 +1215,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         CKS(c, prep_status(c, 1, rt, st));
         CKS(c, prep_status(c, 2, rt, st));
         CKS(c, reset_ticket(c, 1, st));
-        m2_runs_kernel<<<rt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), c->idx[cur].as<uint32_t>(), n_items, (uint32_t)np,
+        m2_runs_kernel<<<rt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), n_items, (uint32_t)np,
                                              c->ntk8.as<uint8_t>(), c->run_start.as<uint32_t>(), c->run_wpre.as<uint32_t>(),
                                              c->status[1].as<uint64_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
         ++c->launches;
@@ -1200,23 +1225,29 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         const uint64_t n_runs = c->h_ctr->n_runs;
         // every run holds at least one card set; more than one only when two sets share a 32-bit key
         CKS(c, ensure_nodes(c, n_runs + n_runs / 8 + 64, st));
-        CK(c, c->big_list.ensure((size_t)n_runs * 4 + 4, 0, st));
-        CK(c, s->uniq.ensure((size_t)(n_uniq + (int64_t)total) * 32, (size_t)n_uniq * 32, st));
-        if (s->use_h) CK(c, c->sk.ensure((size_t)(n_uniq + (int64_t)total) * 8, (size_t)n_uniq * 8, st));
+        CK(c, c->cls_list.ensure((size_t)n_runs * 8 + 16, 0, st));
+        CK(c, s->uniq.ensure((size_t)(n_slots + (int64_t)total) * 32, (size_t)n_slots * 32, st));
+        CK(c, c->sk.ensure((size_t)(n_slots + (int64_t)total) * 8, (size_t)n_slots * 8, st));
         // ---- 4. per-run dedup: warp kernel, then the CTA kernel over the runs it queued
         GroupArgs A;
-        A.front = front + p0; A.brec = c->brec.as<Rec>(); A.ik = c->y[cur].as<uint64_t>(); A.iidx = c->idx[cur].as<uint32_t>();
+        A.front = front + p0; A.brec = c->brec.as<Rec>(); A.iv = c->y[cur].as<uint64_t>();
         A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
         A.np = (uint32_t)np; A.rank_base = p0; A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges;
         A.gemrank = c->d_gemrank; A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>();
-        A.out_sk = score ? c->sk.as<uint64_t>() : nullptr; A.out_base = (uint64_t)n_uniq; A.big_list = c->big_list.as<uint32_t>();
+        A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)n_slots;
+        for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
+        A.cls_list[CLS_WARP] = c->cls_list.as<uint32_t>();
+        A.cls_list[CLS_CTA] = c->cls_list.as<uint32_t>() + n_runs;
         A.h = s->heuristic; A.noise_mode = s->noise; A.L = c->luts; A.ctr = c->d_ctr;
         CK(c, cudaEventRecord(c->ev[2], st));
-        const unsigned gs = (unsigned)std::min<uint64_t>((n_runs + M2_WARPS - 1) / M2_WARPS, 148 * 6);
-        m2_group_small_kernel<<<gs, TILE, sizeof(SmallSmem), st>>>(A);
+        // dispatch + thread kernel over all runs, then the warp kernel and the CTA kernel over the runs it queued
+        m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
         CK(c, cudaEventRecord(c->ev[4], st));
-        m2_group_big_kernel<<<148 * 8, TILE, sizeof(BigSmem), st>>>(A);
-        c->launches += 2;
+        m2_group_warp_kernel<<<148 * 4, TILE, sizeof(WarpSmem), st>>>(A);
+        CK(c, cudaEventRecord(c->ev[5], st));
+        CK(c, cudaEventRecord(c->ev[6], st));
+        m2_group_big_kernel<<<148 * 4, TILE, sizeof(BigSmem), st>>>(A);
+        c->launches += 3;
         CK(c, cudaGetLastError());
         CK(c, cudaEventRecord(c->ev[3], st));
         CKS(c, read_ctr(c, st));
@@ -1227,23 +1258,29 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         const int64_t n_new = (int64_t)c->h_ctr->n_emitted;
         c->node_occ += c->h_ctr->n_new_nodes;
         c->occupied += n_new;
-        if (score && n_new) { sk_min = std::min<uint64_t>(sk_min, c->h_ctr->sk_min); sk_max = std::max<uint64_t>(sk_max, c->h_ctr->sk_max); }
+        if (n_new) { sk_min = std::min<uint64_t>(sk_min, c->h_ctr->sk_min); sk_max = std::max<uint64_t>(sk_max, c->h_ctr->sk_max); }
         n_uniq += n_new;
+        n_slots += n_new;  // dense output
         float t;
         cudaEventElapsedTime(&t, c->ev[0], c->ev[7]); ms[0] += t;   // fan-out + buy records
         cudaEventElapsedTime(&t, c->ev[7], c->ev[1]); ms[2] += t;   // item sort + runs (grouping)
         cudaEventElapsedTime(&t, c->ev[2], c->ev[3]); ms[1] += t;   // per-run dedup + emit + score (the dominant stage)
         if (getenv("SPL_DEBUG")) {
-            float ts = 0, tb = 0;
-            cudaEventElapsedTime(&ts, c->ev[2], c->ev[4]);
-            cudaEventElapsedTime(&tb, c->ev[4], c->ev[3]);
-            fprintf(stderr, "[grouped] level %d round p0=%lld np=%lld takes=%llu buys=%llu runs=%llu big=%u new_nodes=%u winners=%lld  small %.3f ms  big %.3f ms  nodes %llu/%llu\n",
+            float tt = 0, ts = 0, tm = 0, tb = 0, tc = 0, tso = 0;
+            cudaEventElapsedTime(&tt, c->ev[2], c->ev[4]);
+            cudaEventElapsedTime(&ts, c->ev[4], c->ev[5]);
+            cudaEventElapsedTime(&tm, c->ev[5], c->ev[6]);
+            cudaEventElapsedTime(&tb, c->ev[6], c->ev[3]);
+            cudaEventElapsedTime(&tc, c->ev[0], c->ev[7]);
+            cudaEventElapsedTime(&tso, c->ev[7], c->ev[1]);
+            fprintf(stderr, "[grouped] L%d p0=%lld np=%lld takes=%llu buys=%llu runs=%llu cls=%u/%u/%u new_nodes=%u winners=%lld | count+buys %.2f sort+runs %.2f thread %.2f warp %.2f (-) %.2f cta %.2f ms | nodes %llu/%llu\n",
                     s->level, (long long)p0, (long long)np, (unsigned long long)n_takes, (unsigned long long)n_buys,
-                    (unsigned long long)n_runs, c->h_ctr->n_big, c->h_ctr->n_new_nodes, (long long)n_new, ts, tb,
-                    (unsigned long long)c->node_occ, (unsigned long long)c->nn);
+                    (unsigned long long)n_runs, (unsigned)(n_runs - c->h_ctr->n_cls[CLS_WARP] - c->h_ctr->n_cls[CLS_CTA]), c->h_ctr->n_cls[CLS_WARP], c->h_ctr->n_cls[CLS_CTA], c->h_ctr->n_new_nodes,
+                    (long long)n_new, tc, tso, tt, ts, tm, tb, (unsigned long long)c->node_occ, (unsigned long long)c->nn);
         }
     }
     *n_uniq_out = n_uniq;
+    *n_slots_out = n_slots;
     *generated_out = generated;
     *sk_min_out = sk_min;
     *sk_max_out = sk_max;
@@ -1252,9 +1289,11 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
 
 // ------------------------------------------------------------------ second half of a speedrun level
 // beam cut (src/solver.py:452-456) or plain BFS hand-over, then bookkeeping
+// n_uniq states in the first n_slots elements of s->uniq / c->sk (n_slots > n_uniq: the grouped level leaves unused slots)
 static int speedrun_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t n_uniq, uint64_t sk_min, uint64_t sk_max,
-                        cudaStream_t st) {
+                        cudaStream_t st, int64_t n_slots = -1) {
     spl_ctx *c = s->c;
+    if (n_slots < 0) n_slots = n_uniq;
     int64_t kept = n_uniq;
     if (s->use_h && n_uniq > 0) {
         int which = 0;
@@ -1262,8 +1301,8 @@ static int speedrun_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t 
         // grouped level: the winners are unordered, so `stable` ties are broken on the link words (arrival order)
         const bool link_ties = s->grouped && s->tie == SPL_TIE_STABLE;
         c->tie_link_top = link_ties ? 8 + bitlen((uint64_t)n) : 0;
-        const int rc_cut = run_cut_sort(c, c->sk.as<uint64_t>(), s->uniq.as<Rec>(), n_uniq, s->beam, sk_min, sk_max,
-                                        s->tie == SPL_TIE_KEY || link_ties, &which, &kept, st);
+        const int rc_cut = run_cut_sort(c, c->sk.as<uint64_t>(), s->uniq.as<Rec>(), n_slots, s->beam, sk_min, sk_max,
+                                        s->tie == SPL_TIE_KEY || link_ties, &which, &kept, st, n_uniq);
         c->tie_link_top = 0;
         CKS(c, rc_cut);
         CK(c, cudaEventRecord(c->ev[5], st));
@@ -1578,12 +1617,13 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     int64_t n_uniq = 0, generated = 0;
     uint64_t sk_min = ~0ull, sk_max = 0;
     if (s->grouped) {
-        CKS(c, grouped_expand(s, front, n, &n_uniq, &generated, &sk_min, &sk_max, ms, st));
+        int64_t n_slots = 0;
+        CKS(c, grouped_expand(s, front, n, &n_uniq, &n_slots, &generated, &sk_min, &sk_max, ms, st));
         info->expanded = n;
         info->generated = generated;
         info->unique = n_uniq;
         info->ms_count = ms[0]; info->ms_expand = ms[1]; info->ms_resolve = ms[2];
-        return speedrun_cut(s, info, n, n_uniq, sk_min, sk_max, st);
+        return speedrun_cut(s, info, n, n_uniq, sk_min, sk_max, st, n_slots);
     }
     for (int64_t p0 = 0; p0 < n; p0 += (int64_t)c->chunk_parents) {
         const int64_t np = std::min<int64_t>((int64_t)c->chunk_parents, n - p0);
