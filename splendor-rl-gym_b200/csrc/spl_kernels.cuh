@@ -1076,6 +1076,60 @@ __global__ void __launch_bounds__(TILE) cut_det_kernel(const uint64_t *__restric
     }
 }
 
+// Arrival-order ties on unordered input with a score dictionary (the beam cut of the grouped level): keep x > T and
+// the ties whose tie word is >= the selected threshold; emit ONE sort word y = score rank << link_top | link
+// (ascending == better first) and the source index.  16 consecutive scores per thread (four 32-byte loads), link
+// words are read for ties and survivors only, one block scan and one look-back chain.
+constexpr int CUTP_ITEMS = 16;
+__global__ void __launch_bounds__(TILE) cut_pack_kernel(const uint64_t *__restrict__ sk, const uint64_t *__restrict__ kb, int ks,
+                                                        int64_t n, uint64_t sk_min, int keep_all, int all_ties,
+                                                        const SelState *st, const ScoreDict *__restrict__ dict, int link_top,
+                                                        uint64_t *__restrict__ out_y, uint32_t *__restrict__ out_idx,
+                                                        uint64_t *status_keep, Counters *ctr, int ticket_id) {
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_keep_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t T = keep_all ? 0 : st->prefix, Tlo = st->klo, LMAX = (1ull << link_top) - 1;
+    const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * CUTP_ITEMS;
+    uint64_t v[CUTP_ITEMS];
+    if (b0 + CUTP_ITEMS <= n) {
+#pragma unroll
+        for (int q = 0; q < CUTP_ITEMS; q += 4) ld_u64x4(sk + b0 + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < CUTP_ITEMS; ++q) v[q] = b0 + q < n ? sk[b0 + q] : 0;
+    }
+    uint32_t keepmask = 0;
+    uint64_t link[CUTP_ITEMS];
+#pragma unroll
+    for (int q = 0; q < CUTP_ITEMS; ++q) {
+        link[q] = 0;
+        if (v[q] == 0) continue;  // unused slot
+        const uint64_t x = v[q] - sk_min;
+        if (!(keep_all || x >= T)) continue;
+        link[q] = kb[(b0 + q) * ks + 3];
+        if (keep_all || x > T || all_ties || LMAX - link[q] >= Tlo) keepmask |= 1u << q;
+    }
+    uint32_t tot;
+    const uint32_t keep_ex = block_excl_scan(__popc(keepmask), warp_sums, tot);
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status_keep, tile, tot, 0);
+        if (threadIdx.x == 0) s_keep_base = e;
+    }
+    __syncthreads();
+    uint64_t pos = s_keep_base + keep_ex;
+#pragma unroll
+    for (int q = 0; q < CUTP_ITEMS; ++q)
+        if (keepmask >> q & 1) {
+            out_y[pos] = ((uint64_t)dict_rank_of(dict, v[q]) << link_top) | link[q];
+            out_idx[pos] = (uint32_t)(b0 + q);
+            ++pos;
+        }
+}
+
 // ------------------------------------------------------------------ stable LSD radix sort of (y, idx) pairs
 constexpr int SORT_BITS = 8;
 constexpr int SORT_BINS = 1 << SORT_BITS;

@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
 // kernel beyond: one warp on a heavy run would keep the whole grid waiting).
 constexpr int TINY_ITEMS = 16;
 #ifndef SPL_BIG_W
-#define SPL_BIG_W 512
+#define SPL_BIG_W 1024
 #endif
 constexpr uint32_t BIG_W = SPL_BIG_W;
 __global__ void __launch_bounds__(TILE) m2_group_tiny_kernel(GroupArgs A, uint32_t n_runs) {

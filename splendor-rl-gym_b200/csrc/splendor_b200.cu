@@ -588,14 +588,21 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
             CK(c, c->kh[b].ensure((size_t)kept * 8 + 8, 0, st));
         }
     }
-    const unsigned ct = nblk(n, TILE * CUT_ITEMS);
+    const int lt0 = det == 1 ? c->tie_link_top : 0;
+    const unsigned ct = nblk(n, TILE * ((lt0 && use_dict) ? CUTP_ITEMS : CUT_ITEMS));
     CKS(c, prep_status(c, 1, ct, st));
     CKS(c, prep_status(c, 2, ct, st));
     CKS(c, reset_ticket(c, 1, st));
     uint64_t vary_lo = 0, vary_hi = 0;
     const int lt = det == 1 ? c->tie_link_top : 0;
     const int pack = lt && use_dict;  // one sort word: score rank << lt | link
-    if (det) {
+    if (pack) {
+        CKS(c, zero_ctr(c, st));
+        cut_pack_kernel<<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, keep_all, all_ties, c->d_sel, c->d_dict, lt, c->y[0].as<uint64_t>(),
+                                              c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+    } else if (det) {
         CKS(c, zero_ctr(c, st));
         if (use_dict)
             cut_det_kernel<true><<<ct, TILE, 0, st>>>(sk, kb, ks, n, sk_min, sk_max, keep_all, all_ties, c->d_sel, c->d_dict,
@@ -1145,6 +1152,29 @@ static int ensure_nodes(spl_ctx *c, uint64_t need, cudaStream_t st) {
     return SPL_OK;
 }
 
+// stable LSD sort of packed 64-bit items on bits [lo_bit, 64): result in c->y[*cur]
+static int sort_items(spl_ctx *c, int64_t n_items, int lo_bit, int *cur, cudaStream_t st) {
+    const unsigned snt = nblk(n_items, SORT_TILE);
+    const size_t msz = (size_t)SORT_BINS * snt;
+    CK(c, c->matrix.ensure(msz * 4, 0, st));
+    CK(c, c->matrix2.ensure(msz * 4, 0, st));
+    const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
+    if (n_items > 1)
+        for (int shift = lo_bit; shift < 64; shift += SORT_BITS) {
+            sort_hist_kernel<<<snt, TILE, 0, st>>>(c->y[*cur].as<uint64_t>(), n_items, shift, c->matrix.as<uint32_t>(), snt);
+            CKS(c, prep_status(c, 1, st_tiles, st));
+            CKS(c, reset_ticket(c, 2, st));
+            scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
+                                                        c->status[1].as<uint64_t>(), c->d_ctr, 2);
+            psort_scatter_kernel<<<snt, TILE, 0, st>>>(c->y[*cur].as<uint64_t>(), n_items, shift, c->matrix2.as<uint32_t>(), snt,
+                                                        c->y[*cur ^ 1].as<uint64_t>());
+            c->launches += 3;
+            CK(c, cudaGetLastError());
+            *cur ^= 1;
+        }
+    return SPL_OK;
+}
+
 // expand + dedup (+ score) of the whole queue `front[0..n)` in rounds of parents; winners are appended to
 // s->uniq / c->sk in no particular order (their link words carry the arrival order)
 static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n_uniq_out, int64_t *n_slots_out, int64_t *generated_out,
@@ -1188,26 +1218,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         CK(c, cudaEventRecord(c->ev[7], st));
         // ---- 2. stable LSD sort of the items by the high half of their card-set hash
         int cur = 0;
-        {
-            const unsigned snt = nblk(n_items, SORT_TILE);
-            const size_t msz = (size_t)SORT_BINS * snt;
-            CK(c, c->matrix.ensure(msz * 4, 0, st));
-            CK(c, c->matrix2.ensure(msz * 4, 0, st));
-            const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
-            if (n_items > 1)
-                for (int shift = 32; shift < 64; shift += SORT_BITS) {
-                    sort_hist_kernel<<<snt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), n_items, shift, c->matrix.as<uint32_t>(), snt);
-                    CKS(c, prep_status(c, 1, st_tiles, st));
-                    CKS(c, reset_ticket(c, 2, st));
-                    scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
-                                                                c->status[1].as<uint64_t>(), c->d_ctr, 2);
-                    psort_scatter_kernel<<<snt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), n_items, shift, c->matrix2.as<uint32_t>(), snt,
-                                                                c->y[cur ^ 1].as<uint64_t>());
-                    c->launches += 3;
-                    CK(c, cudaGetLastError());
-                    cur ^= 1;
-                }
-        }
+        CKS(c, sort_items(c, n_items, 32, &cur, st));
         // ---- 3. runs of equal key + candidate-weight prefix
         const unsigned rt = nblk(n_items, TILE * RUN_ITEMS);
         CK(c, c->run_start.ensure((size_t)n_items * 4 + 8, 0, st));
