@@ -91,6 +91,24 @@ def _load():
         'spl_solver_cut': (i32, [vp, vp, i64, C.POINTER(LevelInfo), vp]),
         'spl_solver_frontier': (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]),
         'spl_solver_path': (i32, [vp, vp, vp, i32, C.POINTER(i32)]),
+        'spl_gs_create': (i32, [vp, i32, i32, C.POINTER(Key), u64, i32, i32, i64, i32, i32, C.POINTER(vp)]),
+        'spl_gs_destroy': (i32, [vp]),
+        'spl_gs_goal': (i32, [vp, C.POINTER(i64), C.POINTER(i64), vp]),
+        'spl_gs_round_begin': (i32, [vp, i64, i64, vp, C.POINTER(i64), vp]),
+        'spl_gs_round_buys': (i32, [vp, vp, vp]),
+        'spl_gs_round_group': (i32, [vp, vp, i64, C.POINTER(i64), vp]),
+        'spl_gs_counters': (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        'spl_gs_dict': (i32, [vp, C.POINTER(vp), C.POINTER(i64), vp]),
+        'spl_gs_threshold': (i32, [vp, vp, i64, i64, C.POINTER(i32), vp]),
+        'spl_gs_tie_begin': (i32, [vp, C.POINTER(i32), vp]),
+        'spl_gs_tie_hist': (i32, [vp, i32, i32, i32, C.POINTER(vp), vp]),
+        'spl_gs_tie_pick': (i32, [vp, i32, i32, vp]),
+        'spl_gs_cut': (i32, [vp, i32, C.POINTER(i64), C.POINTER(vp), C.POINTER(i32), vp]),
+        'spl_gs_partition': (i32, [vp, vp, i32, vp, vp]),
+        'spl_gs_rank_sort': (i32, [vp, vp, i64, i32, i64, vp, vp]),
+        'spl_gs_adopt': (i32, [vp, vp, i64, vp]),
+        'spl_gs_frontier': (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]),
+        'spl_gs_link_at': (i32, [vp, i32, i64, C.POINTER(i32), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError here == the library does not export the ABI

@@ -357,7 +357,9 @@ struct GroupArgs {
     const uint64_t *iv;            // sorted items: sort key << 32 | item id (id < np: parent, else np + buy index)
     const uint32_t *run_start, *run_wpre;
     uint32_t np;
-    int64_t rank_base;             // global rank of parent 0 of the round
+    int64_t rank_base;             // global rank of parent 0 of the round (when the parents' ranks are contiguous) ...
+    const uint64_t *grank;         // ... or the global rank of every parent of the round (sharded queue), ascending
+    int unordered;                 // buy records are not in arrival order (received from several ranks)
     const DevTables *tabs;
     const uint32_t *takes_idx;
     const uint16_t *takes_edges;
@@ -384,6 +386,9 @@ struct GroupArgs {
 //     generating parent Q, and Q != P for every parent P of the run (Q owns one card less than the run's card
 //     set), so merging the two lists by rank alone yields the arrival order.
 __device__ __forceinline__ uint32_t item_id(const GroupArgs &A, uint32_t i) { return (uint32_t)A.iv[i]; }
+__device__ __forceinline__ uint64_t parent_rank(const GroupArgs &A, uint32_t id) {
+    return A.grank ? A.grank[id] : (uint64_t)(A.rank_base + id);
+}
 
 // per-warp winner staging: records are collected in shared memory and written out 17..48 at a time behind one
 // global atomic (dense output, few same-address atomics)
@@ -509,7 +514,7 @@ __device__ __forceinline__ void load_item(const GroupArgs &A, const SmemTabs &ta
         ld_rec(A.front + id, it);
         uint64_t bl, bh;
         derive_parent(tabs, A.takes_idx, it.lo, it.hi, it.aux, bl, bh, nb, tk);
-        grank = (uint64_t)(A.rank_base + id);
+        grank = parent_rank(A, id);
     } else {
         ld_rec(A.brec + (id - A.np), it);
         grank = it.link >> 8;  // rank of the generating parent
@@ -700,8 +705,15 @@ __global__ void __launch_bounds__(TILE) m2_group_tiny_kernel(GroupArgs A, uint32
                     if (j < (int)cnt) {
                         const uint32_t g = (gp[j >> 1] >> (16 * (j & 1))) & 0x7fffu;
                         bool dup = false;
+                        if (!A.unordered) {  // records in arrival order: an earlier record with the same gems wins
 #pragma unroll
-                        for (int i = 0; i < j; ++i) dup = dup || ((gp[i >> 1] >> (16 * (i & 1))) & 0x7fffu) == g;
+                            for (int i = 0; i < j; ++i) dup = dup || ((gp[i >> 1] >> (16 * (i & 1))) & 0x7fffu) == g;
+                        } else {             // any order: the record with the smaller arrival index wins
+#pragma unroll
+                            for (int i = 0; i < TINY_ITEMS; ++i)
+                                if (i != j && i < (int)cnt && ((gp[i >> 1] >> (16 * (i & 1))) & 0x7fffu) == g)
+                                    dup = dup || A.brec[item_id(A, s + i) - A.np].link < A.brec[item_id(A, s + j) - A.np].link;
+                        }
                         if (!dup && (fresh || !node_bit(N, __ldg(A.gemrank + g)))) winmask |= 1u << j;
                     }
                 }
@@ -787,7 +799,7 @@ __device__ __forceinline__ void big_enumerate(const GroupArgs &A, BigSmem &S, ui
             uint64_t bl, bh;
             uint32_t nb, tk;
             derive_parent(S.tabs, A.takes_idx, it.lo, it.hi, it.aux, bl, bh, nb, tk);
-            const uint64_t tb = ((uint64_t)(A.rank_base + id) << 8) | nb;
+            const uint64_t tb = (parent_rank(A, id) << 8) | nb;
             const uint32_t ntk = tk & 0xff;
             for (uint32_t q = 0; q < ntk; ++q) {
                 const uint32_t g = __ldg(A.takes_edges + (tk >> 8) + q);

@@ -13,6 +13,7 @@
 
 #include "spl_kernels.cuh"
 #include "spl_m2.cuh"
+#include "spl_shard.cuh"
 #include "spl_realistic.cuh"
 #include "spl_tables.cuh"
 
@@ -81,7 +82,8 @@ struct spl_ctx {
     Counters *d_ctr = nullptr, *h_ctr = nullptr;
     SelState *d_sel = nullptr, *h_sel = nullptr;
     uint32_t *d_hist = nullptr;
-    ScoreDict *d_dict = nullptr;
+    ScoreDict *d_dict = nullptr, *d_dict2 = nullptr;  // d_dict2: the merged (global) dictionary of the sharded cut
+    unsigned long long *d_dest = nullptr;             // [2][MAX_RANKS]: per-destination record counts / send cursors
     int dict_skip = 0;
     int identity = IDENT_KEY;  // visited-table identity of the speedrun solver (spl_set_identity)  // levels left before the dictionary path is tried again after a miss
     DevBuf status[3];
@@ -260,6 +262,10 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(m2_buys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuySmem)));
     CKC(cudaFuncSetAttribute(m2_group_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
     CKC(cudaFuncSetAttribute(m2_group_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
+    CKC(cudaFuncSetAttribute(gs_buys_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RouteSmem)));
+    CKC(cudaFuncSetAttribute(gs_group_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TblSmem)));
+    CKC(cudaMalloc(&c->d_dict2, sizeof(ScoreDict)));
+    CKC(cudaMalloc(&c->d_dest, 2 * MAX_RANKS * 8));
     {
         c->max_node_bytes = cfg->max_node_bytes ? cfg->max_node_bytes : (uint64_t)(free_b * 0.5);
         uint64_t nn = cfg->node_slots ? cfg->node_slots : (1ull << 12);
@@ -288,7 +294,7 @@ int32_t spl_destroy(spl_ctx *c) {
     cudaDeviceSynchronize();
     cudaFree(c->table); cudaFree(c->d_tabs); cudaFree(c->d_takes_idx); cudaFree(c->d_takes_edges);
     cudaFree(c->d_lut); cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr); cudaFree(c->d_sel); cudaFreeHost(c->h_sel);
-    cudaFree(c->d_hist); cudaFree(c->d_dict); cudaFree(c->nodes); cudaFree(c->d_gemrank);
+    cudaFree(c->d_hist); cudaFree(c->d_dict); cudaFree(c->d_dict2); cudaFree(c->d_dest); cudaFree(c->nodes); cudaFree(c->d_gemrank);
     for (auto *b : c->pool_links) delete b;
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     delete c;
@@ -1243,7 +1249,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         GroupArgs A;
         A.front = front + p0; A.brec = c->brec.as<Rec>(); A.iv = c->y[cur].as<uint64_t>();
         A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
-        A.np = (uint32_t)np; A.rank_base = p0; A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges;
+        A.np = (uint32_t)np; A.rank_base = p0; A.grank = nullptr; A.unordered = 0; A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges;
         A.gemrank = c->d_gemrank; A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>();
         A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)n_slots;
         for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
@@ -1297,6 +1303,543 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
     *sk_max_out = sk_max;
     return SPL_OK;
 }
+
+// ------------------------------------------------------------------ sharded grouped level (spl_shard.cuh)
+// One spl_gsolver per rank.  The host (Python, torch.distributed) issues the collectives between these calls:
+//   level:  spl_gs_goal -> all-reduce MIN
+//           per round: spl_gs_round_begin (-> per-destination record counts) -> all-gather of the counts ->
+//                      spl_gs_round_buys (records into the send buffer) -> all-to-all -> spl_gs_round_group
+//           cut:    spl_gs_dict -> all-gather -> spl_gs_threshold [-> spl_gs_tie_begin, (spl_gs_tie_hist -> all-reduce
+//                      -> spl_gs_tie_pick) x passes] -> spl_gs_cut (local survivors, sorted by their sort word)
+//           ranks:  sample sort of the sort words across ranks (spl_gs_partition / spl_gs_rank_sort + all-to-all) ->
+//                   spl_gs_adopt (next queue = survivors with their global ranks)
+struct spl_gsolver {
+    spl_ctx *c = nullptr;
+    int rank = 0, world = 1, goal = 15, heuristic = 0, noise = 0, keep_links = 1;
+    int64_t beam = 0;
+    DevBuf front, grank, uniq;
+    int64_t n_local = 0, n_global = 1;
+    int level = 0;
+    // round
+    int64_t r_p0 = 0, r_np = 0;
+    uint64_t r_takes = 0, r_buys = 0;
+    int64_t counts[MAX_RANKS]{};
+    // level accumulators
+    int64_t n_uniq = 0, generated = 0;
+    // cut
+    int lt = 0, cut_cur = 0;
+    int64_t kept_local = 0;
+    std::vector<DevBuf *> link_cols, rank_cols;  // per level: links / global ranks of the local queue (path reconstruction)
+    std::vector<int64_t> level_n;
+    ~spl_gsolver() {
+        if (c->active == this) c->active = nullptr;
+        for (auto *b : link_cols) delete b;
+        for (auto *b : rank_cols) delete b;
+    }
+};
+
+static int gs_save_links(spl_gsolver *s, cudaStream_t st) {
+    spl_ctx *c = s->c;
+    DevBuf *lb = new DevBuf(), *rb = new DevBuf();
+    s->link_cols.push_back(lb);
+    s->rank_cols.push_back(rb);
+    s->level_n.push_back(s->n_local);
+    if (!s->keep_links || s->n_local == 0) return SPL_OK;
+    CK(c, lb->ensure((size_t)s->n_local * 8, 0, st));
+    CK(c, rb->ensure((size_t)s->n_local * 8, 0, st));
+    unpack_rec_kernel<<<nblk(s->n_local), TILE, 0, st>>>(s->front.as<Rec>(), s->n_local, nullptr, nullptr, lb->as<uint64_t>());
+    ++c->launches;
+    CK(c, cudaMemcpyAsync(rb->p, s->grank.p, (size_t)s->n_local * 8, cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+extern "C" {
+
+int32_t spl_gs_create(spl_ctx *c, int32_t rank, int32_t world, const spl_key *root_key, uint64_t root_aux, int32_t goal,
+                      int32_t heuristic, int64_t beam, int32_t noise, int32_t keep_links, spl_gsolver **out) {
+    if (!c || !root_key || !out || world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || beam < 1)
+        return fail(c, SPL_E_INVALID, "spl_gs_create: bad arguments (1 <= world <= %d)", MAX_RANKS);
+    if (noise != SPL_NOISE_CONST && noise != SPL_NOISE_HASH) return fail(c, SPL_E_INVALID, "spl_gs_create: noise must be const or hash");
+    NO_LIVE_SOLVER(c, "spl_gs_create");
+    CK(c, enter_device(c));
+    cudaStream_t st = 0;
+    CKS(c, reset_visited(c, st));
+    spl_gsolver *s = new spl_gsolver();
+    s->c = c; s->rank = rank; s->world = world; s->goal = goal; s->heuristic = heuristic; s->beam = beam; s->noise = noise;
+    s->keep_links = keep_links;
+    uint64_t m0, m1;
+    mask_words(root_key->lo, root_key->hi & HI_KEY_MASK, m0, m1);
+    int rc = SPL_OK;
+    if ((int)owner_of_mask(m0, m1, (uint32_t)world) == rank) {  // the root lives on the rank that owns its card set
+        Rec r{root_key->lo, root_key->hi & HI_KEY_MASK, root_aux, ~0ull};
+        uint64_t zero = 0;
+        cudaError_t e = s->front.ensure(32, 0, st);
+        if (e == cudaSuccess) e = s->grank.ensure(8, 0, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->front.p, &r, 32, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->grank.p, &zero, 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        c->h2d_bytes += 40;
+        if (e != cudaSuccess) rc = fail(c, SPL_E_CUDA, "root upload: %s", cudaGetErrorString(e));
+        if (rc == SPL_OK) rc = zero_ctr(c, st);
+        if (rc == SPL_OK) {
+            m2_root_kernel<<<1, 1, 0, st>>>(c->nodes, c->nn, r.lo, r.hi, c->d_gemrank, c->d_ctr);
+            ++c->launches;
+            c->node_occ = 1;
+            c->occupied = 1;
+        }
+        s->n_local = 1;
+    }
+    if (rc == SPL_OK) rc = gs_save_links(s, st);
+    if (rc == SPL_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(c, SPL_E_CUDA, "spl_gs_create: sync failed");
+    if (rc != SPL_OK) { delete s; return rc; }
+    c->active = s;
+    *out = s;
+    return SPL_OK;
+}
+
+int32_t spl_gs_destroy(spl_gsolver *s) {
+    if (s) { cudaSetDevice(s->c->device); cudaDeviceSynchronize(); delete s; }
+    return SPL_OK;
+}
+
+// first local queue state with pts >= goal -> its GLOBAL rank (INT64_MAX: none); also the local queue length
+int32_t spl_gs_goal(spl_gsolver *s, int64_t *rank_host, int64_t *n_local_host, void *stream) {
+    if (!s || !rank_host || !n_local_host) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    *rank_host = 0x7fffffffffffffffll;
+    *n_local_host = s->n_local;
+    s->n_uniq = 0;
+    s->generated = 0;
+    if (s->n_local == 0) return SPL_OK;
+    CKS(c, zero_ctr(c, st));
+    goal_kernel<<<nblk(s->n_local), TILE, 0, st>>>(s->front.as<Rec>(), s->n_local, s->goal, c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    if (c->h_ctr->goal_rank != 0x7fffffffffffffffll) {
+        uint64_t g = 0;
+        CK(c, cudaMemcpyAsync(&g, s->grank.as<uint64_t>() + c->h_ctr->goal_rank, 8, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        c->d2h_bytes += 8;
+        *rank_host = (int64_t)g;
+    }
+    return SPL_OK;
+}
+
+// first local index whose global rank is >= r (the local queue is ascending in global rank)
+static int gs_lower(spl_gsolver *s, int64_t r, int64_t *idx, cudaStream_t st) {
+    spl_ctx *c = s->c;
+    int64_t lo = 0, hi = s->n_local;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        uint64_t v = 0;
+        CK(c, cudaMemcpyAsync(&v, s->grank.as<uint64_t>() + mid, 8, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        c->d2h_bytes += 8;
+        if ((int64_t)v < r) lo = mid + 1; else hi = mid;
+    }
+    *idx = lo;
+    return SPL_OK;
+}
+
+// round = the local parents whose global rank is in [rank_lo, rank_hi): fan-out, sort keys, and the number of buy
+// records this rank will send to every rank (counts_host[world])
+int32_t spl_gs_round_begin(spl_gsolver *s, int64_t rank_lo, int64_t rank_hi, int64_t *counts_host, int64_t *n_parents_host,
+                           void *stream) {
+    if (!s || !counts_host || !n_parents_host) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    int64_t p0 = 0, p1 = s->n_local;
+    if (rank_lo > 0) CKS(c, gs_lower(s, rank_lo, &p0, st));
+    if (rank_hi < s->n_global) CKS(c, gs_lower(s, rank_hi, &p1, st));
+    const int64_t np = p1 - p0;
+    s->r_p0 = p0; s->r_np = np; s->r_takes = s->r_buys = 0;
+    for (int g = 0; g < s->world; ++g) counts_host[g] = s->counts[g] = 0;
+    *n_parents_host = np;
+    if (np == 0) return SPL_OK;
+    if (np >= (1ll << 31)) return fail(c, SPL_E_INVALID, "round of %lld parents: use smaller rank windows", (long long)np);
+    CKS(c, zero_ctr(c, st));
+    CK(c, cudaMemsetAsync(c->d_dest, 0, 2 * MAX_RANKS * 8, st));
+    CK(c, c->ntk8.ensure((size_t)np + 8, 0, st));
+    CK(c, c->y[0].ensure((size_t)np * 8 + 8, 0, st));
+    gs_count_kernel<<<nblk(np), TILE, 0, st>>>(s->front.as<Rec>() + p0, np, c->d_tabs, c->d_takes_idx, c->y[0].as<uint64_t>(),
+                                                c->ntk8.as<uint8_t>(), (uint32_t)s->world, c->d_dest, c->d_ctr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    unsigned long long h_dest[MAX_RANKS];
+    CK(c, cudaMemcpyAsync(h_dest, c->d_dest, MAX_RANKS * 8, cudaMemcpyDeviceToHost, st));
+    CKS(c, read_ctr(c, st));
+    c->d2h_bytes += MAX_RANKS * 8;
+    s->r_takes = c->h_ctr->total_cands;
+    s->r_buys = c->h_ctr->n_buys;
+    uint64_t sum = 0;
+    for (int g = 0; g < s->world; ++g) { counts_host[g] = s->counts[g] = (int64_t)h_dest[g]; sum += h_dest[g]; }
+    if (sum != s->r_buys) return fail(c, SPL_E_CUDA, "internal: destination counts %llu != buys %llu", (unsigned long long)sum, (unsigned long long)s->r_buys);
+    s->generated += (int64_t)(s->r_takes + s->r_buys);
+    return SPL_OK;
+}
+
+// the round's buy records into send_dev: destination d owns [sum(counts[0..d)), +counts[d])
+int32_t spl_gs_round_buys(spl_gsolver *s, void *send_dev, void *stream) {
+    if (!s) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    if (s->r_np == 0 || s->r_buys == 0) return SPL_OK;
+    if (!send_dev) return fail(c, SPL_E_INVALID, "spl_gs_round_buys: null send buffer");
+    unsigned long long cur[MAX_RANKS] = {0};
+    for (int g = 1; g < s->world; ++g) cur[g] = cur[g - 1] + (unsigned long long)s->counts[g - 1];
+    CK(c, cudaMemcpyAsync(c->d_dest + MAX_RANKS, cur, MAX_RANKS * 8, cudaMemcpyHostToDevice, st));
+    CK(c, cudaStreamSynchronize(st));  // cur is a stack array
+    c->h2d_bytes += MAX_RANKS * 8;
+    gs_buys_route_kernel<<<nblk(s->r_np), TILE, sizeof(RouteSmem), st>>>(
+        s->front.as<Rec>() + s->r_p0, s->r_np, s->grank.as<uint64_t>() + s->r_p0, c->d_tabs, c->d_takes_idx, (uint32_t)s->world,
+        reinterpret_cast<Rec *>(send_dev), c->d_dest + MAX_RANKS);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+// owner side: the round's local parents + the n_recv records received for this rank -> sort by card set, per-run
+// dedup against this rank's nodes, winners (+ scores) appended to the level's list
+int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv, int64_t *n_new_host, void *stream) {
+    if (!s || !n_new_host || n_recv < 0) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    *n_new_host = 0;
+    const int64_t np = s->r_np, n_items = np + n_recv;
+    const uint64_t total = s->r_takes + (uint64_t)n_recv;
+    if (total == 0) return SPL_OK;
+    if (total >= 0xFFFFFFFFull || (uint64_t)n_items >= 0xFFFFFFFFull)
+        return fail(c, SPL_E_INVALID, "round holds %llu candidates (>= 2^32): use smaller rank windows", (unsigned long long)total);
+    CK(c, c->y[0].ensure((size_t)n_items * 8 + 8, (size_t)np * 8, st));
+    CK(c, c->y[1].ensure((size_t)n_items * 8 + 8, 0, st));
+    if (n_recv) {
+        gs_recv_items_kernel<<<nblk(n_recv), TILE, 0, st>>>(reinterpret_cast<const Rec *>(recv_dev), n_recv, (uint32_t)np, c->y[0].as<uint64_t>());
+        ++c->launches;
+    }
+    int cur = 0;
+    CKS(c, sort_items(c, n_items, 32, &cur, st));
+    const unsigned rt = nblk(n_items, TILE * RUN_ITEMS);
+    CK(c, c->run_start.ensure((size_t)n_items * 4 + 8, 0, st));
+    CK(c, c->run_wpre.ensure((size_t)n_items * 4 + 8, 0, st));
+    CKS(c, zero_ctr(c, st));
+    CKS(c, prep_status(c, 1, rt, st));
+    CKS(c, prep_status(c, 2, rt, st));
+    m2_runs_kernel<<<rt, TILE, 0, st>>>(c->y[cur].as<uint64_t>(), n_items, (uint32_t)np, c->ntk8.as<uint8_t>(), c->run_start.as<uint32_t>(),
+                                         c->run_wpre.as<uint32_t>(), c->status[1].as<uint64_t>(), c->status[2].as<uint64_t>(), c->d_ctr, 1);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    const uint64_t n_runs = c->h_ctr->n_runs;
+    CKS(c, ensure_nodes(c, n_runs + n_runs / 8 + 64, st));
+    CK(c, c->cls_list.ensure((size_t)n_runs * 8 + 16, 0, st));
+    CK(c, s->uniq.ensure((size_t)(s->n_uniq + (int64_t)total) * 32, (size_t)s->n_uniq * 32, st));
+    CK(c, c->sk.ensure((size_t)(s->n_uniq + (int64_t)total) * 8, (size_t)s->n_uniq * 8, st));
+    GroupArgs A;
+    A.front = s->front.as<Rec>() + s->r_p0; A.brec = reinterpret_cast<const Rec *>(recv_dev); A.iv = c->y[cur].as<uint64_t>();
+    A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
+    A.np = (uint32_t)np; A.rank_base = 0; A.grank = s->grank.as<uint64_t>() + s->r_p0; A.unordered = 1;
+    A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges; A.gemrank = c->d_gemrank;
+    A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>(); A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)s->n_uniq;
+    for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
+    A.cls_list[CLS_WARP] = c->cls_list.as<uint32_t>();
+    A.cls_list[CLS_CTA] = c->cls_list.as<uint32_t>() + n_runs;
+    A.h = s->heuristic; A.noise_mode = s->noise; A.L = c->luts; A.ctr = c->d_ctr;
+    m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
+    gs_group_table_kernel<<<148 * 5, TBL_WARPS * 32, sizeof(TblSmem), st>>>(A);
+    m2_group_big_kernel<<<148 * 4, TILE, sizeof(BigSmem), st>>>(A);
+    c->launches += 3;
+    CK(c, cudaGetLastError());
+    CKS(c, read_ctr(c, st));
+    if (c->h_ctr->error)
+        return fail(c, c->h_ctr->error == 3 ? SPL_E_CUDA : SPL_E_TABLE_FULL, "sharded level %d: device error code %u (2 = card-set table full, 3 = too many card sets under one sort key)",
+                    s->level, c->h_ctr->error);
+    const int64_t n_new = (int64_t)c->h_ctr->n_emitted;
+    c->node_occ += c->h_ctr->n_new_nodes;
+    c->occupied += n_new;
+    s->n_uniq += n_new;
+    *n_new_host = n_new;
+    return SPL_OK;
+}
+
+int32_t spl_gs_counters(spl_gsolver *s, int64_t *n_uniq_host, int64_t *generated_host, int64_t *visited_host) {
+    if (!s) return SPL_E_INVALID;
+    if (n_uniq_host) *n_uniq_host = s->n_uniq;
+    if (generated_host) *generated_host = s->generated;
+    if (visited_host) *visited_host = (int64_t)s->c->occupied;
+    return SPL_OK;
+}
+
+// local dictionary of the level's scores (distinct score -> count); *dict_dev points at sizeof(ScoreDict) = *bytes
+int32_t spl_gs_dict(spl_gsolver *s, void **dict_dev, int64_t *bytes, void *stream) {
+    if (!s || !dict_dev || !bytes) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    CK(c, cudaMemsetAsync(c->d_dict->key, 0xFF, sizeof(c->d_dict->key), st));
+    CK(c, cudaMemsetAsync(c->d_dict->cnt, 0, sizeof(ScoreDict) - sizeof(c->d_dict->key), st));
+    if (s->n_uniq) {
+        dict_build_kernel<<<std::min<unsigned>(nblk(s->n_uniq), 148 * 8), TILE, 0, st>>>(c->sk.as<uint64_t>(), s->n_uniq, c->d_dict);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+    }
+    *dict_dev = c->d_dict;
+    *bytes = (int64_t)sizeof(ScoreDict);
+    return SPL_OK;
+}
+
+// all ranks' dictionaries (all-gathered, `world` x sizeof(ScoreDict)) -> global threshold for the k best of
+// n_uniq_global states.  *need_ties_host = 1: the threshold score has more states than fit (split by arrival order)
+int32_t spl_gs_threshold(spl_gsolver *s, const void *dicts_dev, int64_t k, int64_t n_uniq_global, int32_t *need_ties_host,
+                         void *stream) {
+    if (!s || !dicts_dev || !need_ties_host || k < 1) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    CK(c, cudaMemsetAsync(c->d_dict2->key, 0xFF, sizeof(c->d_dict2->key), st));
+    CK(c, cudaMemsetAsync(c->d_dict2->cnt, 0, sizeof(ScoreDict) - sizeof(c->d_dict2->key), st));
+    memset(c->h_sel, 0, sizeof(SelState));
+    c->h_sel->rank_t = ~0ull;
+    CK(c, cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(SelState), cudaMemcpyHostToDevice, st));
+    gs_dict_merge_kernel<<<nblk((int64_t)s->world * DICT_CAP), TILE, 0, st>>>(reinterpret_cast<const ScoreDict *>(dicts_dev), s->world, c->d_dict2);
+    dict_rank_kernel<<<1, 1024, 0, st>>>(c->d_dict2, (uint64_t)std::min(k, n_uniq_global), 0, c->d_sel);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(SelState), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += sizeof(SelState);
+    if (c->h_sel->rank_t == ~0ull)
+        return fail(c, SPL_E_CAPACITY, "the level has more than %d distinct scores: the dictionary cut does not apply", DICT_MAX);
+    s->lt = 8 + bitlen((uint64_t)s->n_global);
+    *need_ties_host = (n_uniq_global > k && c->h_sel->k_rem < c->h_sel->tie_count) ? 1 : 0;
+    if (!*need_ties_host) c->h_sel->tie_count = 0;  // all ties are kept
+    return SPL_OK;
+}
+
+// ties of the threshold score: collect their arrival words locally, then radix-select the quota-th one globally --
+// the host all-reduces *hist_dev (2048 x uint32) between spl_gs_tie_hist and spl_gs_tie_pick; passes: shift = lt - 11,
+// lt - 22, ... (bits = min(11, remaining))
+int32_t spl_gs_tie_begin(spl_gsolver *s, int32_t *link_bits_host, void *stream) {
+    if (!s || !link_bits_host) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    *link_bits_host = s->lt;
+    CK(c, c->rtmp.ensure((size_t)std::max<int64_t>(s->n_uniq, 1) * 8 + 8, 0, st));
+    CK(c, cudaMemsetAsync(&c->d_ctr->n_ties, 0, 8, st));
+    if (s->n_uniq) {
+        tie_collect_kernel<<<std::min<unsigned>(nblk(s->n_uniq), 148 * 8), TILE, 0, st>>>(
+            c->sk.as<uint64_t>(), reinterpret_cast<const uint64_t *>(s->uniq.p), 4, s->n_uniq, 0, c->d_sel, s->lt, c->rtmp.as<uint64_t>(), c->d_ctr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+    }
+    CKS(c, read_ctr(c, st));
+    return SPL_OK;
+}
+int32_t spl_gs_tie_hist(spl_gsolver *s, int32_t shift, int32_t bits, int32_t first, uint32_t **hist_dev, void *stream) {
+    if (!s || !hist_dev) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    *hist_dev = c->d_hist;
+    const int64_t ntie = (int64_t)c->h_ctr->n_ties;
+    if (ntie) {
+        sel_hist_kernel<3><<<std::min<unsigned>(nblk(ntie), 148 * 8), TILE, 0, st>>>(nullptr, c->rtmp.as<uint64_t>(), 1, ntie, 0, shift, bits, first,
+                                                                                    c->d_sel, c->d_hist);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+    }
+    return SPL_OK;
+}
+int32_t spl_gs_tie_pick(spl_gsolver *s, int32_t shift, int32_t first, void *stream) {
+    if (!s) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    sel_pick_kernel<<<1, 1024, 0, st>>>(c->d_hist, 2, shift, first, 0, 0, c->d_sel);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+// local cut by the global threshold, then local sort by the sort word (score rank << link bits | link: ascending ==
+// better first, and a total order over all ranks).  *y_sorted_dev: the kept_local sort words, ascending.
+int32_t spl_gs_cut(spl_gsolver *s, int32_t have_tie_threshold, int64_t *kept_local_host, const uint64_t **y_sorted_dev, int32_t *y_bits_host,
+                   void *stream) {
+    if (!s || !kept_local_host || !y_sorted_dev || !y_bits_host) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    const int64_t n = s->n_uniq;
+    const int nbits = s->lt + bitlen(c->h_sel->rank_t);
+    *y_bits_host = nbits;
+    *kept_local_host = s->kept_local = 0;
+    *y_sorted_dev = nullptr;
+    s->cut_cur = 0;
+    if (n == 0) return SPL_OK;
+    for (int b = 0; b < 2; ++b) {
+        CK(c, c->y[b].ensure((size_t)n * 8 + 8, 0, st));
+        CK(c, c->idx[b].ensure((size_t)n * 4 + 4, 0, st));
+    }
+    const unsigned ct = nblk(n, TILE * CUTP_ITEMS);
+    CKS(c, prep_status(c, 2, ct, st));
+    CKS(c, zero_ctr(c, st));
+    cut_pack_kernel<<<ct, TILE, 0, st>>>(c->sk.as<uint64_t>(), reinterpret_cast<const uint64_t *>(s->uniq.p), 4, n, 0, 0, have_tie_threshold ? 0 : 1,
+                                          c->d_sel, c->d_dict2, s->lt, c->y[0].as<uint64_t>(), c->idx[0].as<uint32_t>(), c->status[2].as<uint64_t>(),
+                                          c->d_ctr, 1);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    uint64_t last = 0;
+    CK(c, cudaMemcpyAsync(&last, c->status[2].as<uint64_t>() + (ct - 1), 8, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->d2h_bytes += 8;
+    const int64_t kept = (int64_t)(last & ((1ull << 62) - 1));
+    int cur = 0;
+    if (kept > 1) {
+        const unsigned nt = nblk(kept, SORT_TILE);
+        const size_t msz = (size_t)SORT_BINS * nt;
+        CK(c, c->matrix.ensure(msz * 4, 0, st));
+        CK(c, c->matrix2.ensure(msz * 4, 0, st));
+        for (int shift = 0; shift < nbits; shift += SORT_BITS) {
+            CKS(c, sort_pass(c, 0, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
+            cur ^= 1;
+        }
+    }
+    s->cut_cur = cur;
+    *kept_local_host = s->kept_local = kept;
+    *y_sorted_dev = c->y[cur].as<uint64_t>();
+    return SPL_OK;
+}
+
+// lower bounds of n_probes ascending probes in the local sorted sort words (sample-sort partition)
+int32_t spl_gs_partition(spl_gsolver *s, const uint64_t *probes_host, int32_t n_probes, int64_t *bounds_host, void *stream) {
+    if (!s || n_probes < 0 || n_probes > 4 * MAX_RANKS) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    if (n_probes == 0) return SPL_OK;
+    CK(c, c->rtmp.ensure(16 * 4 * MAX_RANKS, 0, st));
+    uint64_t *dp = c->rtmp.as<uint64_t>();
+    int64_t *dout = reinterpret_cast<int64_t *>(dp + 4 * MAX_RANKS);
+    CK(c, cudaMemcpyAsync(dp, probes_host, (size_t)n_probes * 8, cudaMemcpyHostToDevice, st));
+    gs_lower_bound_kernel<<<1, 64, 0, st>>>(c->y[s->cut_cur].as<uint64_t>(), s->kept_local, dp, n_probes, dout);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(bounds_host, dout, (size_t)n_probes * 8, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+// receiver side of the sample sort: n sort words (any order) -> ranks_out[i] = base + (number of words smaller than
+// word i); the words of all ranks are pairwise distinct (they contain the arrival index)
+int32_t spl_gs_rank_sort(spl_gsolver *s, const uint64_t *y_dev, int64_t n, int32_t y_bits, int64_t base, int64_t *ranks_out_dev, void *stream) {
+    if (!s || n < 0) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    if (n == 0) return SPL_OK;
+    // y[] / idx[] of the context hold the local survivors (spl_gs_cut): work in separate buffers
+    CK(c, c->kl[0].ensure((size_t)n * 8 + 8, 0, st));
+    CK(c, c->kl[1].ensure((size_t)n * 8 + 8, 0, st));
+    CK(c, c->kh[0].ensure((size_t)n * 4 + 8, 0, st));
+    CK(c, c->kh[1].ensure((size_t)n * 4 + 8, 0, st));
+    CK(c, cudaMemcpyAsync(c->kl[0].p, y_dev, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    gs_iota_kernel<<<nblk(n), TILE, 0, st>>>(c->kh[0].as<uint32_t>(), n);
+    ++c->launches;
+    int cur = 0;
+    const unsigned nt = nblk(n, SORT_TILE);
+    const size_t msz = (size_t)SORT_BINS * nt;
+    CK(c, c->matrix.ensure(msz * 4, 0, st));
+    CK(c, c->matrix2.ensure(msz * 4, 0, st));
+    const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
+    if (n > 1)
+        for (int shift = 0; shift < y_bits; shift += SORT_BITS) {
+            sort_hist_kernel<<<nt, TILE, 0, st>>>(c->kl[cur].as<uint64_t>(), n, shift, c->matrix.as<uint32_t>(), nt);
+            CKS(c, prep_status(c, 1, st_tiles, st));
+            CKS(c, reset_ticket(c, 2, st));
+            scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
+                                                        c->status[1].as<uint64_t>(), c->d_ctr, 2);
+            sort_scatter_kernel<false><<<nt, TILE, 0, st>>>(c->kl[cur].as<uint64_t>(), c->kl[cur].as<uint64_t>(), c->kh[cur].as<uint32_t>(), n, shift,
+                                                             c->matrix2.as<uint32_t>(), nt, c->kl[cur ^ 1].as<uint64_t>(), c->kh[cur ^ 1].as<uint32_t>(),
+                                                             nullptr, nullptr, nullptr, nullptr);
+            c->launches += 3;
+            cur ^= 1;
+        }
+    gs_scatter_ranks_kernel<<<nblk(n), TILE, 0, st>>>(c->kh[cur].as<uint32_t>(), n, base, ranks_out_dev);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
+// next queue of this rank = its survivors in sort-word order (== ascending global rank) with the global ranks the
+// sample sort assigned (granks_dev[i] for the i-th local survivor); n_global_next = queue length over all ranks
+int32_t spl_gs_adopt(spl_gsolver *s, const int64_t *granks_dev, int64_t n_global_next, void *stream) {
+    if (!s) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    const int64_t kept = s->kept_local;
+    if (kept) {
+        if (!granks_dev) return fail(c, SPL_E_INVALID, "spl_gs_adopt: null ranks");
+        CK(c, s->front.ensure((size_t)kept * 32, 0, st));
+        CK(c, s->grank.ensure((size_t)kept * 8, 0, st));
+        gather_rec_kernel<<<nblk(kept), TILE, 0, st>>>(s->uniq.as<Rec>(), c->idx[s->cut_cur].as<uint32_t>(), kept, s->front.as<Rec>());
+        ++c->launches;
+        CK(c, cudaMemcpyAsync(s->grank.p, granks_dev, (size_t)kept * 8, cudaMemcpyDeviceToDevice, st));
+        CK(c, cudaGetLastError());
+    }
+    s->n_local = kept;
+    s->n_global = n_global_next;
+    s->level += 1;
+    CKS(c, gs_save_links(s, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SPL_OK;
+}
+
+// device view of the local queue: records (32 B each) and their global ranks
+int32_t spl_gs_frontier(spl_gsolver *s, const void **recs_dev, const uint64_t **granks_dev, int64_t *n_local_host) {
+    if (!s || !n_local_host) return SPL_E_INVALID;
+    if (recs_dev) *recs_dev = s->front.p;
+    if (granks_dev) *granks_dev = s->grank.as<uint64_t>();
+    *n_local_host = s->n_local;
+    return SPL_OK;
+}
+
+// link (parent rank << 8 | ordinal) of the state with global rank `grank` in the queue of `level`, if this rank holds it
+int32_t spl_gs_link_at(spl_gsolver *s, int32_t level, int64_t grank, int32_t *found_host, uint64_t *link_host) {
+    if (!s || !found_host || !link_host || level < 0 || level >= (int)s->rank_cols.size()) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    if (!s->keep_links) return fail(c, SPL_E_STATE, "spl_gs_link_at: solver was created with keep_links = 0");
+    CK(c, enter_device(c));
+    *found_host = 0;
+    *link_host = 0;
+    const int64_t n = s->level_n[level];
+    const uint64_t *rk = s->rank_cols[level]->as<uint64_t>();
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        uint64_t v = 0;
+        CK(c, cudaMemcpy(&v, rk + mid, 8, cudaMemcpyDeviceToHost));
+        if ((int64_t)v < grank) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n) {
+        uint64_t v = 0;
+        CK(c, cudaMemcpy(&v, rk + lo, 8, cudaMemcpyDeviceToHost));
+        if ((int64_t)v == grank) {
+            CK(c, cudaMemcpy(link_host, s->link_cols[level]->as<uint64_t>() + lo, 8, cudaMemcpyDeviceToHost));
+            *found_host = 1;
+        }
+    }
+    return SPL_OK;
+}
+
+}  // extern "C"
 
 // ------------------------------------------------------------------ second half of a speedrun level
 // beam cut (src/solver.py:452-456) or plain BFS hand-over, then bookkeeping

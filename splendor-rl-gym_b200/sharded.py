@@ -28,7 +28,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._lib import check, lib
+from ._lib import Key as _Key, check, lib
 from .engine import NOISE_IDS, TIE_IDS, Engine, _DevArray, heuristic_id
 
 import os
@@ -526,3 +526,210 @@ class ShardedSolver:
                 x = self._global_of_local(torch.arange(sizes[g], dtype=torch.int64, device=dev), g)
                 out[x] = torch.stack([cols[c][g] for c in range(4)], dim=1)
         return out
+
+
+
+class GroupedShardedSolver:
+    """Beam search of State.solve (src/solver.py:390-464) over a queue sharded BY CARD SET (spl_gs_* entry points,
+    csrc/spl_shard.cuh): a queue state lives on the rank that owns its cards, so its gem-take successors are
+    deduplicated on the generating GPU by the fused on-chip walk and only card buys travel (32-byte records, one
+    all-to-all per round).  The beam cut is global: the ranks' score dictionaries are all-gathered and merged into one
+    threshold, score ties at the threshold are split by arrival order with all-reduced radix histograms, and the
+    survivors get their dense global ranks -- the queue order of the next level -- from a sample sort of their sort
+    words (score rank, arrival index).  Every level is the same set of states, in the same order, as on one GPU.
+
+    Policy: ties by arrival order (`stable`), noise `const` (the score dictionary needs few distinct scores);
+    anything else runs on ShardedSolver."""
+
+    SAMPLES = 256
+
+    def __init__(self, eng: Engine, comm: Comm, root_key: int, root_aux: int, goal_pts: int, heuristic: str, beam_width: int,
+                 noise: str = 'const', round_parents: int = 1 << 27, keep_links: bool = True):
+        self.eng, self.comm = eng, comm
+        self.goal, self.h, self.beam, self.noise = goal_pts, heuristic, beam_width, noise
+        self.C = int(round_parents)   # global ranks per round (all ranks walk the same window of the queue)
+        k = _Key(root_key & ((1 << 64) - 1), root_key >> 64)
+        h = C.c_void_p()
+        check(lib.spl_gs_create(eng._h, comm.rank, comm.world, C.byref(k), root_aux, goal_pts, heuristic_id(heuristic), beam_width,
+                                NOISE_IDS[noise], int(keep_links), C.byref(h)), eng._h)
+        self._h = h
+        self.N = 1
+        self.level = 0
+        self.ended = False
+        self.goal_rank = -1
+        self.infos = []
+        self.noise_source = None
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib.spl_gs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- helpers
+    def _st(self):
+        return self.eng._stream()
+
+    def _sum_ints(self, *vals):
+        a = self.comm.gather_ints(*vals)
+        return [int(x) for x in a.sum(axis=0)]
+
+    def _dev(self, ptr, shape, typestr='<i8'):
+        return torch.as_tensor(_DevArray(ptr, shape, typestr), device=self.eng.tdev)
+
+    # ---------------------------------------------------------------- one `while queue` iteration
+    def step(self) -> dict:
+        eng, comm, dev = self.eng, self.comm, self.eng.tdev
+        G, me = comm.world, comm.rank
+        N = self.N
+        info = dict(level=self.level, ended=0, frontier=N, expanded=0, generated=0, unique=0, kept=0, goal_rank=-1)
+        # 1. goal test (src/solver.py:443-445): first state in global queue order with pts >= goal
+        gr, nl = C.c_int64(), C.c_int64()
+        check(lib.spl_gs_goal(self._h, C.byref(gr), C.byref(nl), self._st()), eng._h)
+        gt = torch.tensor([gr.value], dtype=torch.int64, device=dev)
+        comm.all_reduce(gt, dist.ReduceOp.MIN)
+        if int(gt) != I64_MAX:
+            self.ended, self.goal_rank = True, int(gt)
+            info.update(ended=1, goal_rank=self.goal_rank)
+            self.infos.append(info)
+            return info
+        # 2. rounds over windows of the global queue
+        for lo in range(0, N, self.C):
+            counts = (C.c_int64 * G)()
+            npar = C.c_int64()
+            check(lib.spl_gs_round_begin(self._h, lo, min(lo + self.C, N), counts, C.byref(npar), self._st()), eng._h)
+            counts = np.array(counts[:], dtype=np.int64)
+            allc = comm.gather_ints(*counts.tolist())          # [src, dst]
+            send = torch.empty((max(int(counts.sum()), 1), 4), dtype=torch.int64, device=dev)
+            check(lib.spl_gs_round_buys(self._h, send.data_ptr(), self._st()), eng._h)
+            recv = comm.all_to_all_rows(send[:int(counts.sum())], counts, allc[:, me])
+            n_new = C.c_int64()
+            check(lib.spl_gs_round_group(self._h, recv.data_ptr() if recv.shape[0] else None, recv.shape[0], C.byref(n_new), self._st()), eng._h)
+            del send, recv
+        nu, gen, vis = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.spl_gs_counters(self._h, C.byref(nu), C.byref(gen), C.byref(vis)), eng._h)
+        u_total, g_total, v_total = self._sum_ints(nu.value, gen.value, vis.value)
+        info.update(expanded=N, generated=g_total, unique=u_total, visited=v_total)
+        if u_total == 0:  # frontier exhausted: `puzzle` stays the last dequeued state
+            self.ended, self.goal_rank = True, N - 1
+            info['ended'] = 1
+            self.infos.append(info)
+            return info
+        # 3. global beam threshold from the merged score dictionaries
+        dp, nbytes = C.c_void_p(), C.c_int64()
+        check(lib.spl_gs_dict(self._h, C.byref(dp), C.byref(nbytes), self._st()), eng._h)
+        local = self._dev(dp.value, (nbytes.value,), '|u1')
+        if comm.on:
+            alld = torch.empty((G, nbytes.value), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(alld, local.reshape(1, -1))
+        else:
+            alld = local.reshape(1, -1)
+        need = C.c_int32()
+        check(lib.spl_gs_threshold(self._h, alld.data_ptr(), self.beam, u_total, C.byref(need), self._st()), eng._h)
+        if need.value:  # split the ties of the threshold score by arrival order
+            lt = C.c_int32()
+            check(lib.spl_gs_tie_begin(self._h, C.byref(lt), self._st()), eng._h)
+            top, first = lt.value, True
+            while top > 0:
+                bits = min(SEL_BITS, top)
+                shift = top - bits
+                hp = C.c_void_p()
+                check(lib.spl_gs_tie_hist(self._h, shift, bits, int(first), C.byref(hp), self._st()), eng._h)
+                comm.all_reduce(self._dev(hp.value, (1 << SEL_BITS,), '<i4'), dist.ReduceOp.SUM)
+                check(lib.spl_gs_tie_pick(self._h, shift, int(first), self._st()), eng._h)
+                first = False
+                top = shift
+        kept, yp, ybits = C.c_int64(), C.c_void_p(), C.c_int32()
+        check(lib.spl_gs_cut(self._h, need.value, C.byref(kept), C.byref(yp), C.byref(ybits), self._st()), eng._h)
+        k_local = kept.value
+        k_all = comm.gather_ints(k_local)[:, 0]
+        k_total = int(k_all.sum())
+        assert k_total == min(u_total, self.beam), (k_total, u_total, self.beam)
+        # 4. dense global ranks of the survivors: sample sort of the sort words
+        granks = self._global_ranks(yp.value, k_local, ybits.value, k_total)
+        check(lib.spl_gs_adopt(self._h, granks.data_ptr() if k_local else None, k_total, self._st()), eng._h)
+        info['kept'] = k_total
+        self.infos.append(info)
+        self.N = k_total
+        self.level += 1
+        return info
+
+    def _global_ranks(self, y_ptr, k_local, y_bits, k_total):
+        eng, comm, dev = self.eng, self.comm, self.eng.tdev
+        G, me = comm.world, comm.rank
+        if G == 1:
+            return torch.arange(k_local, dtype=torch.int64, device=dev)
+        y = self._dev(y_ptr, (k_local,)) if k_local else torch.empty(0, dtype=torch.int64, device=dev)
+        # splitters: regular samples of every rank's sorted words -> G - 1 quantiles of their union
+        S = self.SAMPLES
+        smp = torch.full((S,), I64_MAX, dtype=torch.int64, device=dev)
+        if k_local:
+            pick = torch.linspace(0, k_local - 1, min(S, k_local), device=dev).long()
+            smp[:pick.numel()] = y[pick]
+        alls = torch.empty((G, S), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(alls, smp.reshape(1, -1))
+        alls = np.sort(alls.cpu().numpy().reshape(-1))
+        alls = alls[alls != I64_MAX]
+        if len(alls):
+            spl = [int(alls[min(len(alls) - 1, (g * len(alls)) // G)]) for g in range(1, G)]
+        else:
+            spl = [0] * (G - 1)
+        bounds = (C.c_int64 * (G - 1))()
+        check(lib.spl_gs_partition(self._h, (C.c_uint64 * (G - 1))(*spl), G - 1, bounds, self._st()), eng._h)
+        b = [0] + [int(x) for x in bounds[:]] + [k_local]
+        send_counts = np.diff(np.array(b, dtype=np.int64))
+        allc = comm.gather_ints(*send_counts.tolist())            # [src, dst]
+        recv_counts = allc[:, me]
+        recv_y = comm.all_to_all_rows(y, send_counts, recv_counts)
+        base = int(allc[:, :me].sum())                              # sort words held by the ranks below this one
+        n_recv = int(recv_counts.sum())
+        ranks_recv = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
+        check(lib.spl_gs_rank_sort(self._h, recv_y.data_ptr() if n_recv else None, n_recv, y_bits, base, ranks_recv.data_ptr(), self._st()), eng._h)
+        return comm.all_to_all_rows(ranks_recv[:n_recv], recv_counts, send_counts)
+
+    def run(self, max_levels=None):
+        while not self.ended:
+            self.step()
+            if max_levels is not None and len(self.infos) >= max_levels:
+                break
+        return self.infos
+
+    def frontier_local(self):
+        """(records [n, 4] int64, global ranks [n] int64) of this rank's share of the queue (device views)"""
+        rp, gp, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        check(lib.spl_gs_frontier(self._h, C.byref(rp), C.byref(gp), C.byref(n)), self.eng._h)
+        if n.value == 0:
+            z = torch.empty((0, 4), dtype=torch.int64, device=self.eng.tdev)
+            return z, z[:, 0]
+        return self._dev(rp.value, (n.value, 4)), self._dev(gp.value, (n.value,))
+
+    def gather_frontier(self):
+        """the whole queue in global rank order on every rank (tests / parity digests; small cases only)"""
+        recs, gr = self.frontier_local()
+        out = torch.zeros((self.N, 4), dtype=torch.int64, device=self.eng.tdev)
+        if recs.shape[0]:
+            out[gr] = recs
+        self.comm.all_reduce(out, dist.ReduceOp.SUM)
+        return out
+
+    def path(self):
+        """(ranks, ordinals) of the winning line: walk the per-level link columns, each held by the rank that owns
+        the state's cards (src/solver.py:459-464)."""
+        L, r = self.level, self.goal_rank
+        ranks, ords = [0] * (L + 1), [0] * L
+        for lv in range(L, -1, -1):
+            ranks[lv] = r
+            if lv > 0:
+                found, link = C.c_int32(), C.c_uint64()
+                check(lib.spl_gs_link_at(self._h, lv, r, C.byref(found), C.byref(link)), self.eng._h)
+                t = torch.tensor([link.value if found.value else 0, found.value], dtype=torch.int64, device=self.eng.tdev)
+                self.comm.all_reduce(t, dist.ReduceOp.SUM)
+                assert int(t[1]) == 1, f'state of rank {r} in level {lv} is held by {int(t[1])} ranks'
+                ords[lv - 1] = int(t[0]) & 0xff
+                r = int(t[0]) >> 8
+        return ranks, ords

@@ -340,6 +340,33 @@ def test_sharded_solver_world1_vs_oracle(eng, cfg):
     eng.reset_visited()
 
 
+@pytest.mark.parametrize('hname,beam,rounds', [('aggressive', 20_000, 1 << 27), ('aggressive', 20_000, 3000), ('balanced', 5_000, 1 << 27),
+                                               ('simple', 50_000, 20_000)])
+def test_grouped_sharded_solver_world1_vs_oracle(eng, hname, beam, rounds):
+    """The card-set-sharded driver (spl_gs_*: routed buy records, order-agnostic per-run dedup, merged score dictionary,
+    arrival-order tie select, sample-sort ranks) on a single rank must reproduce the oracle level by level, with one and
+    with many rounds per level (2+ ranks: tools/sharded_check.py --grouped under torchrun)."""
+    from splendor_rl_gym_b200.sharded import Comm, GroupedShardedSolver
+    sol = GroupedShardedSolver(eng, Comm(eng.tdev), 0, 0, 15, hname, beam, 'const', round_parents=rounds)
+    orc = oracle.Solver(15, use_heuristic=True, heuristic_name=hname, beam_width=beam, policy='stable', noise='const')
+    try:
+        while True:
+            gi, oi = sol.step(), orc.step()
+            fields = ('frontier', 'goal_rank') if gi['ended'] else ('frontier', 'generated', 'unique', 'kept', 'goal_rank', 'visited')
+            for f in fields:
+                assert gi[f] == oi[f], (f, gi, oi)
+            if gi['ended']:
+                break
+            fr = sol.gather_frontier().cpu().numpy().view(np.uint64)
+            st, lk = orc.level(oi['level'] + 1)
+            assert (fr[:, 0] == st['lo']).all() and (fr[:, 1] == st['hi']).all() and (fr[:, 2] == st['aux']).all()
+            assert (fr[:, 3] == lk).all()
+        assert len(sol.path()[1]) == orc.nlevels - 1
+    finally:
+        sol.close()
+        orc.close()
+
+
 def test_owner_partition_and_count_less(eng):
     import ctypes as C
     from splendor_rl_gym_b200.sharded import CudaBackend

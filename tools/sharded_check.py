@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 import splendor_rl_gym_b200 as S
-from splendor_rl_gym_b200.sharded import Comm, CudaBackend, ShardedSolver
+from splendor_rl_gym_b200.sharded import Comm, CudaBackend, GroupedShardedSolver, ShardedSolver
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--goal', type=int, default=15)
@@ -27,14 +27,20 @@ ap.add_argument('--reps', type=int, default=1)
 ap.add_argument('--block', type=int, default=1 << 20, help='parents per block (round granularity)')
 ap.add_argument('--slots', type=int, default=0, help='visited-table slots per rank')
 ap.add_argument('--no-links', action='store_true')
+ap.add_argument('--grouped', action='store_true', help='queue sharded by card set (GroupedShardedSolver); --block = global ranks per round')
+ap.add_argument('--nodes', type=int, default=0, help='node-table slots per rank (grouped)')
 a = ap.parse_args()
 
 local = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(local)
 if int(os.environ.get('WORLD_SIZE', '1')) > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-eng = S.Engine(local, table_slots=a.slots or max(1 << 22, int(a.beam * 110 / 0.6 / max(1, int(os.environ.get('WORLD_SIZE', '1'))))),
-               max_table_bytes=int(120e9))
+world_env = max(1, int(os.environ.get('WORLD_SIZE', '1')))
+if a.grouped:
+    eng = S.Engine(local, table_slots=1 << 22, node_slots=a.nodes or min(int(140e9 / 384), max(1 << 14, a.beam * 4 // world_env)),
+                   max_node_bytes=int(150e9))
+else:
+    eng = S.Engine(local, table_slots=a.slots or max(1 << 22, int(a.beam * 110 / 0.6 / world_env)), max_table_bytes=int(120e9))
 comm = Comm(eng.tdev)
 use_h = a.bfs == 0
 check = comm.rank == 0 and not a.no_oracle
@@ -48,8 +54,12 @@ for rep in range(a.reps):
                             policy=a.tie, noise=a.noise)
     torch.cuda.synchronize()
     t0 = time.time()
-    sol = ShardedSolver(CudaBackend(eng), comm, 0, 0, 255 if a.bfs else a.goal, use_h, a.heuristic, a.beam, a.tie, a.noise,
-                        block_parents=a.block, keep_links=not a.no_links)
+    if a.grouped:
+        sol = GroupedShardedSolver(eng, comm, 0, 0, a.goal, a.heuristic, a.beam, a.noise, round_parents=max(a.block, 1024) if a.block != 1 << 20 else 1 << 27,
+                                   keep_links=not a.no_links)
+    else:
+        sol = ShardedSolver(CudaBackend(eng), comm, 0, 0, 255 if a.bfs else a.goal, use_h, a.heuristic, a.beam, a.tie, a.noise,
+                            block_parents=a.block, keep_links=not a.no_links)
     while True:
         gi = sol.step()
         if rep == 0 and not a.no_oracle:
@@ -71,6 +81,12 @@ for rep in range(a.reps):
             break
     torch.cuda.synchronize()
     dt = time.time() - t0
+    if rep == 0 and not a.no_oracle and not a.no_links and not a.bfs:
+        ranks, ords = sol.path()
+        if check:
+            assert len(ords) == orc.nlevels - 1, (len(ords), orc.nlevels)
+    if a.grouped:
+        sol.close()
     if comm.rank == 0:
         exp = sum(i['expanded'] for i in sol.infos)
         print(f'world={comm.world} rep={rep} levels={len(sol.infos)} expanded={exp} wall={dt:.3f}s -> {exp / dt / 1e6:.2f} M expanded/s'
