@@ -106,12 +106,13 @@ typedef struct {
     int64_t goal_rank;    /* rank of the first state with pts >= goal in queue order, or -1 */
     int64_t visited;      /* len(trail) */
     uint64_t table_slots; /* current visited-table capacity */
-    float ms_count;       /* CUDA-event time of the fan-out count + offset scan launches */
-    float ms_expand;      /* ... of the expand+probe launches (the dominant kernel) */
-    float ms_resolve;     /* ... of the resolve+emit(+score) launches */
+    /* CUDA-event times of the level's stages.  Key-table level (BFS, pyhash, mt noise) | card-set-grouped level (beam): */
+    float ms_count;       /* fan-out count + offset scan                 | fan-out count + buy records */
+    float ms_expand;      /* expand+probe launches (dominant kernel)     | per-run dedup: thread + warp + CTA kernels */
+    float ms_resolve;     /* resolve+emit(+score) launches               | item sort + run boundaries (grouping) */
     float ms_select;      /* ... of the radix-select + cut */
     float ms_sort;        /* ... of the rank-ordering sort + gather */
-    float reserved1;
+    float ms_warp;        /* grouped level: the warp kernel alone (the dominant kernel of ms_expand) */
 } spl_level_info;
 
 /* ---- library / context ------------------------------------------------------------------ */

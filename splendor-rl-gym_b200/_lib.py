@@ -35,7 +35,7 @@ class LevelInfo(C.Structure):
     _fields_ = [('level', C.c_int32), ('ended', C.c_int32), ('frontier', C.c_int64), ('expanded', C.c_int64),
                 ('generated', C.c_int64), ('unique', C.c_int64), ('kept', C.c_int64), ('goal_rank', C.c_int64),
                 ('visited', C.c_int64), ('table_slots', C.c_uint64), ('ms_count', C.c_float), ('ms_expand', C.c_float),
-                ('ms_resolve', C.c_float), ('ms_select', C.c_float), ('ms_sort', C.c_float), ('reserved1', C.c_float)]
+                ('ms_resolve', C.c_float), ('ms_select', C.c_float), ('ms_sort', C.c_float), ('ms_warp', C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -98,6 +98,7 @@ def _load():
         'spl_gs_round_buys': (i32, [vp, vp, vp]),
         'spl_gs_round_group': (i32, [vp, vp, i64, C.POINTER(i64), vp]),
         'spl_gs_counters': (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        'spl_gs_stage_ms': (i32, [vp, vp]),
         'spl_gs_dict': (i32, [vp, C.POINTER(vp), C.POINTER(i64), vp]),
         'spl_gs_threshold': (i32, [vp, vp, i64, i64, C.POINTER(i32), vp]),
         'spl_gs_tie_begin': (i32, [vp, C.POINTER(i32), vp]),

@@ -89,7 +89,7 @@ struct spl_ctx {
     DevBuf status[3];
     // scratch
     DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2;
-    DevBuf pool_front, pool_uniq;      // frontier buffers lent to the active solver
+    DevBuf pool_front, pool_uniq, pool_grank;  // frontier buffers lent to the active solver
     DevBuf rcfg, rcand, rkeys, rvmask, ridx64, rtmp;  // realistic mode scratch
     std::vector<DevBuf *> pool_links;  // link columns of finished solves, reused by the next one
     cudaEvent_t ev[8]{};
@@ -1184,7 +1184,7 @@ static int sort_items(spl_ctx *c, int64_t n_items, int lo_bit, int *cur, cudaStr
 // expand + dedup (+ score) of the whole queue `front[0..n)` in rounds of parents; winners are appended to
 // s->uniq / c->sk in no particular order (their link words carry the arrival order)
 static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n_uniq_out, int64_t *n_slots_out, int64_t *generated_out,
-                          uint64_t *sk_min_out, uint64_t *sk_max_out, float ms[5], cudaStream_t st) {
+                          uint64_t *sk_min_out, uint64_t *sk_max_out, float ms[6], cudaStream_t st) {
     spl_ctx *c = s->c;
     const int64_t chunk = c->chunk_user ? (int64_t)c->chunk_parents : (16ll << 20);
     int64_t n_uniq = 0, n_slots = 0, generated = 0;
@@ -1282,6 +1282,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         cudaEventElapsedTime(&t, c->ev[0], c->ev[7]); ms[0] += t;   // fan-out + buy records
         cudaEventElapsedTime(&t, c->ev[7], c->ev[1]); ms[2] += t;   // item sort + runs (grouping)
         cudaEventElapsedTime(&t, c->ev[2], c->ev[3]); ms[1] += t;   // per-run dedup + emit + score (the dominant stage)
+        cudaEventElapsedTime(&t, c->ev[4], c->ev[5]); ms[5] += t;   // ... of which the warp kernel
         if (getenv("SPL_DEBUG")) {
             float tt = 0, ts = 0, tm = 0, tb = 0, tc = 0, tso = 0;
             cudaEventElapsedTime(&tt, c->ev[2], c->ev[4]);
@@ -1326,6 +1327,7 @@ struct spl_gsolver {
     int64_t counts[MAX_RANKS]{};
     // level accumulators
     int64_t n_uniq = 0, generated = 0;
+    float ms[4] = {0, 0, 0, 0};  // CUDA-event time of: item sort + runs, thread kernel, table warp kernel, CTA kernel
     // cut
     int lt = 0, cut_cur = 0;
     int64_t kept_local = 0;
@@ -1333,6 +1335,9 @@ struct spl_gsolver {
     std::vector<int64_t> level_n;
     ~spl_gsolver() {
         if (c->active == this) c->active = nullptr;
+        c->pool_front.swap(front);  // keep the big buffers for the next solve on this context
+        c->pool_uniq.swap(uniq);
+        c->pool_grank.swap(grank);
         for (auto *b : link_cols) delete b;
         for (auto *b : rank_cols) delete b;
     }
@@ -1368,6 +1373,9 @@ int32_t spl_gs_create(spl_ctx *c, int32_t rank, int32_t world, const spl_key *ro
     spl_gsolver *s = new spl_gsolver();
     s->c = c; s->rank = rank; s->world = world; s->goal = goal; s->heuristic = heuristic; s->beam = beam; s->noise = noise;
     s->keep_links = keep_links;
+    s->front.swap(c->pool_front);
+    s->uniq.swap(c->pool_uniq);
+    s->grank.swap(c->pool_grank);
     uint64_t m0, m1;
     mask_words(root_key->lo, root_key->hi & HI_KEY_MASK, m0, m1);
     int rc = SPL_OK;
@@ -1413,6 +1421,7 @@ int32_t spl_gs_goal(spl_gsolver *s, int64_t *rank_host, int64_t *n_local_host, v
     *n_local_host = s->n_local;
     s->n_uniq = 0;
     s->generated = 0;
+    s->ms[0] = s->ms[1] = s->ms[2] = s->ms[3] = 0;
     if (s->n_local == 0) return SPL_OK;
     CKS(c, zero_ctr(c, st));
     goal_kernel<<<nblk(s->n_local), TILE, 0, st>>>(s->front.as<Rec>(), s->n_local, s->goal, c->d_ctr);
@@ -1523,6 +1532,8 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
         gs_recv_items_kernel<<<nblk(n_recv), TILE, 0, st>>>(reinterpret_cast<const Rec *>(recv_dev), n_recv, (uint32_t)np, c->y[0].as<uint64_t>());
         ++c->launches;
     }
+    const bool dbg = getenv("SPL_DEBUG") != nullptr;
+    CK(c, cudaEventRecord(c->ev[0], st));
     int cur = 0;
     CKS(c, sort_items(c, n_items, 32, &cur, st));
     const unsigned rt = nblk(n_items, TILE * RUN_ITEMS);
@@ -1551,12 +1562,25 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     A.cls_list[CLS_WARP] = c->cls_list.as<uint32_t>();
     A.cls_list[CLS_CTA] = c->cls_list.as<uint32_t>() + n_runs;
     A.h = s->heuristic; A.noise_mode = s->noise; A.L = c->luts; A.ctr = c->d_ctr;
+    CK(c, cudaEventRecord(c->ev[1], st));
     m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
+    CK(c, cudaEventRecord(c->ev[2], st));
     gs_group_table_kernel<<<148 * 5, TBL_WARPS * 32, sizeof(TblSmem), st>>>(A);
+    CK(c, cudaEventRecord(c->ev[3], st));
     m2_group_big_kernel<<<148 * 4, TILE, sizeof(BigSmem), st>>>(A);
+    CK(c, cudaEventRecord(c->ev[4], st));
     c->launches += 3;
     CK(c, cudaGetLastError());
     CKS(c, read_ctr(c, st));
+    float t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    cudaEventElapsedTime(&t1, c->ev[0], c->ev[1]); cudaEventElapsedTime(&t2, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&t3, c->ev[2], c->ev[3]); cudaEventElapsedTime(&t4, c->ev[3], c->ev[4]);
+    s->ms[0] += t1; s->ms[1] += t2; s->ms[2] += t3; s->ms[3] += t4;
+    if (dbg) {
+        fprintf(stderr, "[gs r%d] L%d np=%lld recv=%lld takes=%llu runs=%llu warp=%u cta=%u winners=%llu | sort+runs %.2f tiny %.2f table %.2f cta %.2f ms\n",
+                s->rank, s->level, (long long)np, (long long)n_recv, (unsigned long long)s->r_takes, (unsigned long long)n_runs,
+                c->h_ctr->n_cls[CLS_WARP], c->h_ctr->n_cls[CLS_CTA], (unsigned long long)c->h_ctr->n_emitted, t1, t2, t3, t4);
+    }
     if (c->h_ctr->error)
         return fail(c, c->h_ctr->error == 3 ? SPL_E_CUDA : SPL_E_TABLE_FULL, "sharded level %d: device error code %u (2 = card-set table full, 3 = too many card sets under one sort key)",
                     s->level, c->h_ctr->error);
@@ -1565,6 +1589,12 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     c->occupied += n_new;
     s->n_uniq += n_new;
     *n_new_host = n_new;
+    return SPL_OK;
+}
+
+int32_t spl_gs_stage_ms(spl_gsolver *s, float ms_host[4]) {
+    if (!s || !ms_host) return SPL_E_INVALID;
+    for (int i = 0; i < 4; ++i) ms_host[i] = s->ms[i];
     return SPL_OK;
 }
 
@@ -1785,6 +1815,8 @@ int32_t spl_gs_adopt(spl_gsolver *s, const int64_t *granks_dev, int64_t n_global
     cudaStream_t st = (cudaStream_t)stream;
     CK(c, enter_device(c));
     const int64_t kept = s->kept_local;
+    const bool dbg = getenv("SPL_DEBUG") != nullptr;
+    if (dbg) CK(c, cudaEventRecord(c->ev[0], st));
     if (kept) {
         if (!granks_dev) return fail(c, SPL_E_INVALID, "spl_gs_adopt: null ranks");
         CK(c, s->front.ensure((size_t)kept * 32, 0, st));
@@ -1797,8 +1829,15 @@ int32_t spl_gs_adopt(spl_gsolver *s, const int64_t *granks_dev, int64_t n_global
     s->n_local = kept;
     s->n_global = n_global_next;
     s->level += 1;
+    if (dbg) CK(c, cudaEventRecord(c->ev[1], st));
     CKS(c, gs_save_links(s, st));
+    if (dbg) CK(c, cudaEventRecord(c->ev[2], st));
     CK(c, cudaStreamSynchronize(st));
+    if (dbg) {
+        float t1 = 0, t2 = 0;
+        cudaEventElapsedTime(&t1, c->ev[0], c->ev[1]); cudaEventElapsedTime(&t2, c->ev[1], c->ev[2]);
+        fprintf(stderr, "[gs r%d] adopt L%d kept=%lld gather %.2f links %.2f ms\n", s->rank, s->level, (long long)kept, t1, t2);
+    }
     return SPL_OK;
 }
 
@@ -2150,7 +2189,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
     info->goal_rank = -1;
     const int64_t n = s->n_front;
     const Rec *front = s->front.as<Rec>();
-    float ms[5] = {0, 0, 0, 0, 0};  // count, expand, resolve, select, sort
+    float ms[6] = {0, 0, 0, 0, 0, 0};  // count, expand, resolve, select, sort, (grouped level) warp kernel
     // ---- goal test on the queue (src/solver.py:443-445): the first state in queue order with
     // pts >= goal ends the search; the states before it would be expanded and discarded.
     CKS(c, zero_ctr(c, st));
@@ -2176,7 +2215,7 @@ int32_t spl_solver_step(spl_solver *s, spl_level_info *info, void *stream) {
         info->expanded = n;
         info->generated = generated;
         info->unique = n_uniq;
-        info->ms_count = ms[0]; info->ms_expand = ms[1]; info->ms_resolve = ms[2];
+        info->ms_count = ms[0]; info->ms_expand = ms[1]; info->ms_resolve = ms[2]; info->ms_warp = ms[5];
         return speedrun_cut(s, info, n, n_uniq, sk_min, sk_max, st, n_slots);
     }
     for (int64_t p0 = 0; p0 < n; p0 += (int64_t)c->chunk_parents) {

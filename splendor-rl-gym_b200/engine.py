@@ -136,6 +136,7 @@ class Engine:
         h = C.c_void_p()
         check(lib.spl_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        self.host_bytes = [0, 0]  # bytes this Python layer copied host->device / device->host itself (torch tensors)
 
     @classmethod
     def get(cls, device: int = 0, **kw) -> 'Engine':
@@ -189,9 +190,10 @@ class Engine:
         return n.value
 
     def transfer_bytes(self):
+        """(host->device, device->host) bytes copied so far: by the library (spl_transfer_bytes) plus by this layer"""
         a, b = C.c_int64(), C.c_int64()
         check(lib.spl_transfer_bytes(self._h, C.byref(a), C.byref(b)), self._h)
-        return a.value, b.value
+        return a.value + self.host_bytes[0], b.value + self.host_bytes[1]
 
     # -------------------------------------------------------------- stage operators
     def expand(self, keys: torch.Tensor, aux: torch.Tensor):

@@ -589,6 +589,7 @@ class GroupedShardedSolver:
         N = self.N
         info = dict(level=self.level, ended=0, frontier=N, expanded=0, generated=0, unique=0, kept=0, goal_rank=-1)
         # 1. goal test (src/solver.py:443-445): first state in global queue order with pts >= goal
+        t0 = _tick('', time.perf_counter() if TIMING else 0.0)
         gr, nl = C.c_int64(), C.c_int64()
         check(lib.spl_gs_goal(self._h, C.byref(gr), C.byref(nl), self._st()), eng._h)
         gt = torch.tensor([gr.value], dtype=torch.int64, device=dev)
@@ -598,23 +599,31 @@ class GroupedShardedSolver:
             info.update(ended=1, goal_rank=self.goal_rank)
             self.infos.append(info)
             return info
+        t0 = _tick('goal', t0)
         # 2. rounds over windows of the global queue
         for lo in range(0, N, self.C):
             counts = (C.c_int64 * G)()
             npar = C.c_int64()
             check(lib.spl_gs_round_begin(self._h, lo, min(lo + self.C, N), counts, C.byref(npar), self._st()), eng._h)
             counts = np.array(counts[:], dtype=np.int64)
+            t0 = _tick('count', t0)
             allc = comm.gather_ints(*counts.tolist())          # [src, dst]
             send = torch.empty((max(int(counts.sum()), 1), 4), dtype=torch.int64, device=dev)
             check(lib.spl_gs_round_buys(self._h, send.data_ptr(), self._st()), eng._h)
+            t0 = _tick('buys', t0)
             recv = comm.all_to_all_rows(send[:int(counts.sum())], counts, allc[:, me])
+            t0 = _tick('a2a', t0)
             n_new = C.c_int64()
             check(lib.spl_gs_round_group(self._h, recv.data_ptr() if recv.shape[0] else None, recv.shape[0], C.byref(n_new), self._st()), eng._h)
             del send, recv
+            t0 = _tick('group', t0)
         nu, gen, vis = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib.spl_gs_counters(self._h, C.byref(nu), C.byref(gen), C.byref(vis)), eng._h)
         u_total, g_total, v_total = self._sum_ints(nu.value, gen.value, vis.value)
-        info.update(expanded=N, generated=g_total, unique=u_total, visited=v_total)
+        ms = (C.c_float * 4)()
+        check(lib.spl_gs_stage_ms(self._h, ms), eng._h)
+        info.update(expanded=N, generated=g_total, unique=u_total, visited=v_total, local_unique=nu.value,
+                    ms_sort=ms[0], ms_thread=ms[1], ms_warp=ms[2], ms_cta=ms[3])
         if u_total == 0:  # frontier exhausted: `puzzle` stays the last dequeued state
             self.ended, self.goal_rank = True, N - 1
             info['ended'] = 1
@@ -645,14 +654,18 @@ class GroupedShardedSolver:
                 first = False
                 top = shift
         kept, yp, ybits = C.c_int64(), C.c_void_p(), C.c_int32()
+        t0 = _tick('threshold', t0)
         check(lib.spl_gs_cut(self._h, need.value, C.byref(kept), C.byref(yp), C.byref(ybits), self._st()), eng._h)
+        t0 = _tick('cut', t0)
         k_local = kept.value
         k_all = comm.gather_ints(k_local)[:, 0]
         k_total = int(k_all.sum())
         assert k_total == min(u_total, self.beam), (k_total, u_total, self.beam)
         # 4. dense global ranks of the survivors: sample sort of the sort words
         granks = self._global_ranks(yp.value, k_local, ybits.value, k_total)
+        t0 = _tick('ranks', t0)
         check(lib.spl_gs_adopt(self._h, granks.data_ptr() if k_local else None, k_total, self._st()), eng._h)
+        t0 = _tick('adopt', t0)
         info['kept'] = k_total
         self.infos.append(info)
         self.N = k_total
@@ -669,8 +682,9 @@ class GroupedShardedSolver:
         S = self.SAMPLES
         smp = torch.full((S,), I64_MAX, dtype=torch.int64, device=dev)
         if k_local:
-            pick = torch.linspace(0, k_local - 1, min(S, k_local), device=dev).long()
-            smp[:pick.numel()] = y[pick]
+            m = min(S, k_local)
+            pick = (torch.arange(m, dtype=torch.int64, device=dev) * (k_local - 1)) // max(m - 1, 1)  # exact integer positions
+            smp[:m] = y[pick]
         alls = torch.empty((G, S), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(alls, smp.reshape(1, -1))
         alls = np.sort(alls.cpu().numpy().reshape(-1))

@@ -156,6 +156,8 @@ class State:
         ck, ca, _ = eng.expand(keys, aux)
         ck = ck.cpu().numpy().view(np.uint64)
         ca = ca.cpu().numpy().view(np.uint64)
+        eng.host_bytes[0] += 24                  # the state's key + aux up ...
+        eng.host_bytes[1] += ck.nbytes + ca.nbytes  # ... its successor list down
         return [State.from_record(int(ck[i, 0]), int(ck[i, 1]), int(ca[i])) for i in range(len(ca))]
 
     def solve(
@@ -202,15 +204,23 @@ class State:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             # one process per GPU (torchrun): every rank calls solve() collectively; the frontier is
             # sharded by key hash and each level is bit-identical to the single-GPU search
-            from .sharded import Comm, CudaBackend, ShardedSolver
+            from .sharded import Comm, CudaBackend, GroupedShardedSolver, ShardedSolver
             if identity != 'key':
                 raise ValueError("identity='pyhash' is a single-GPU option")
-            sh = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), k, a, goal_pts, use_heuristic, heuristic_name,
-                               beam_width, tie_policy, noise)
-            for info in sh.run():
-                if stats is not None:
-                    stats.append(info)
-            _, ordinals = sh.path()
+            if use_heuristic and tie_policy == 'stable' and noise == 'const':
+                # queue sharded by card set: gem takes never leave the GPU, only card buys are routed
+                sh = GroupedShardedSolver(eng, Comm(eng.tdev), k, a, goal_pts, heuristic_name, beam_width, noise)
+            else:  # exhaustive BFS, key ties, hash / mt noise: queue sharded by key hash
+                sh = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), k, a, goal_pts, use_heuristic, heuristic_name,
+                                   beam_width, tie_policy, noise)
+            try:
+                for info in sh.run():
+                    if stats is not None:
+                        stats.append(info)
+                _, ordinals = sh.path()
+            finally:
+                if hasattr(sh, 'close'):
+                    sh.close()
             if sh.noise_source is not None:
                 sh.noise_source.finish()
             path = [self]

@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "grouped_sharded" > gpurun_out/r2l_pytest.log 2>&1
-tail -15 gpurun_out/r2l_pytest.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+SPL_TIMING=1 timeout 300 $TR tools/sharded_check.py --grouped --beam 60000000 --no-oracle --no-links --reps 3 > gpurun_out/r2q_time60m.log 2>&1; grep -v "^\*\*\|OMP" gpurun_out/r2q_time60m.log | tail -6
+timeout 300 $TR tools/sharded_check.py --grouped --beam 60000000 --no-oracle --no-links --reps 3 > gpurun_out/r2q_time60m_nt.log 2>&1; grep -v "^\*\*\|OMP" gpurun_out/r2q_time60m_nt.log | tail -4
