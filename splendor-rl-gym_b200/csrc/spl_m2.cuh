@@ -360,6 +360,7 @@ struct GroupArgs {
     int64_t rank_base;             // global rank of parent 0 of the round (when the parents' ranks are contiguous) ...
     const uint64_t *grank;         // ... or the global rank of every parent of the round (sharded queue), ascending
     int unordered;                 // buy records are not in arrival order (received from several ranks)
+    uint32_t warp_max;             // runs of more candidates than this go to the CTA kernel
     const DevTables *tabs;
     const uint32_t *takes_idx;
     const uint16_t *takes_edges;
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(TILE) m2_group_tiny_kernel(GroupArgs A, uint32
         const uint32_t id0 = item_id(A, s);
         const uint32_t wgt = A.run_wpre[r + 1] - A.run_wpre[r];
         if (cnt <= TINY_ITEMS && id0 >= A.np) cls = 0;
-        else cls = wgt <= BIG_W ? CLS_WARP : CLS_CTA;
+        else cls = wgt <= A.warp_max ? CLS_WARP : CLS_CTA;
         if (cls == 0) {
             uint64_t lo0, hi0, M0, M1;
             ld_cg_u64x2(reinterpret_cast<const uint64_t *>(A.brec + (id0 - A.np)), lo0, hi0);

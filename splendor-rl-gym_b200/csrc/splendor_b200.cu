@@ -1249,7 +1249,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         GroupArgs A;
         A.front = front + p0; A.brec = c->brec.as<Rec>(); A.iv = c->y[cur].as<uint64_t>();
         A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
-        A.np = (uint32_t)np; A.rank_base = p0; A.grank = nullptr; A.unordered = 0; A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges;
+        A.np = (uint32_t)np; A.rank_base = p0; A.grank = nullptr; A.unordered = 0; A.warp_max = BIG_W; A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges;
         A.gemrank = c->d_gemrank; A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>();
         A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)n_slots;
         for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
@@ -1338,14 +1338,16 @@ struct spl_gsolver {
         c->pool_front.swap(front);  // keep the big buffers for the next solve on this context
         c->pool_uniq.swap(uniq);
         c->pool_grank.swap(grank);
-        for (auto *b : link_cols) delete b;
-        for (auto *b : rank_cols) delete b;
+        for (auto *b : link_cols) c->pool_links.push_back(b);
+        for (auto *b : rank_cols) c->pool_links.push_back(b);
     }
 };
 
 static int gs_save_links(spl_gsolver *s, cudaStream_t st) {
     spl_ctx *c = s->c;
-    DevBuf *lb = new DevBuf(), *rb = new DevBuf();
+    DevBuf *lb, *rb;  // reuse the columns of earlier solves on this context (smallest first: the queue grows)
+    if (c->pool_links.empty()) lb = new DevBuf(); else { lb = c->pool_links.back(); c->pool_links.pop_back(); }
+    if (c->pool_links.empty()) rb = new DevBuf(); else { rb = c->pool_links.back(); c->pool_links.pop_back(); }
     s->link_cols.push_back(lb);
     s->rank_cols.push_back(rb);
     s->level_n.push_back(s->n_local);
@@ -1376,6 +1378,7 @@ int32_t spl_gs_create(spl_ctx *c, int32_t rank, int32_t world, const spl_key *ro
     s->front.swap(c->pool_front);
     s->uniq.swap(c->pool_uniq);
     s->grank.swap(c->pool_grank);
+    std::sort(c->pool_links.begin(), c->pool_links.end(), [](DevBuf *a, DevBuf *b) { return a->cap > b->cap; });
     uint64_t m0, m1;
     mask_words(root_key->lo, root_key->hi & HI_KEY_MASK, m0, m1);
     int rc = SPL_OK;
@@ -1556,6 +1559,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     A.front = s->front.as<Rec>() + s->r_p0; A.brec = reinterpret_cast<const Rec *>(recv_dev); A.iv = c->y[cur].as<uint64_t>();
     A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
     A.np = (uint32_t)np; A.rank_base = 0; A.grank = s->grank.as<uint64_t>() + s->r_p0; A.unordered = 1;
+    A.warp_max = TBL_W;  // the table of the order-agnostic warp kernel holds TBL_SLOTS = 2 x TBL_W entries
     A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges; A.gemrank = c->d_gemrank;
     A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>(); A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)s->n_uniq;
     for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
