@@ -249,6 +249,53 @@ int32_t spl_solver_frontier(spl_solver *s, const spl_key **keys_dev, const uint6
 int32_t spl_solver_path(spl_solver *s, int64_t *ranks_host, int32_t *ordinals_host, int32_t cap,
                         int32_t *n_moves_host);
 
+/* ---- sharded beam search: queue sharded BY CARD SET, one process per GPU (csrc/spl_shard.cuh) -------------------
+ * The reference has no distributed path; these entry points spread State.solve's level loop
+ * (src/solver.py:434-457) over `world` ranks so that every level holds the same states, in the same order, as on one
+ * GPU.  A queue state lives on the rank that owns its cards; its gem-take successors (same cards, :381-388) are
+ * deduplicated on that GPU, card buys (:369-374) are written as 32-byte records {key, aux, link} into per-destination
+ * ranges of a send buffer.  The collectives themselves (all-to-all of the records, all-gather of the score
+ * dictionaries, all-reduce of the tie histograms, sample sort of the survivors' sort words) are issued by the host
+ * between these calls (torch.distributed / NCCL).  Policy: ties by arrival order, noise const | hash. */
+typedef struct spl_gsolver spl_gsolver;
+int32_t spl_gs_create(spl_ctx *ctx, int32_t rank, int32_t world, const spl_key *root_key_host, uint64_t root_aux_host,
+                      int32_t goal_pts, int32_t heuristic, int64_t beam_width, int32_t noise, int32_t keep_links,
+                      spl_gsolver **out);
+int32_t spl_gs_destroy(spl_gsolver *s);
+/* goal test on dequeue (:443-445): GLOBAL rank of the first local queue state with pts >= goal (INT64_MAX: none) */
+int32_t spl_gs_goal(spl_gsolver *s, int64_t *rank_host, int64_t *n_local_host, void *stream);
+/* round = the local parents with global rank in [rank_lo, rank_hi): fan-out and the number of buy records this rank
+ * sends to every rank (counts_host[world]) */
+int32_t spl_gs_round_begin(spl_gsolver *s, int64_t rank_lo, int64_t rank_hi, int64_t *counts_host, int64_t *n_parents_host,
+                           void *stream);
+/* the round's buy records into send_dev (destination d owns [sum(counts[0..d)), +counts[d])) */
+int32_t spl_gs_round_buys(spl_gsolver *s, void *send_dev, void *stream);
+/* owner side (:447-450): local parents + the n_recv records received -> first-arrival dedup per card set, winners + scores */
+int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv, int64_t *n_new_host, void *stream);
+int32_t spl_gs_counters(spl_gsolver *s, int64_t *n_uniq_host, int64_t *generated_host, int64_t *visited_host);
+/* CUDA-event times of the level's owner-side stages: item sort + runs, thread kernel, warp kernel, CTA kernel */
+int32_t spl_gs_stage_ms(spl_gsolver *s, float ms_host[4]);
+/* beam cut (:452-456) across ranks: local score dictionary -> (host all-gathers) -> global threshold ... */
+int32_t spl_gs_dict(spl_gsolver *s, void **dict_dev, int64_t *bytes_host, void *stream);
+int32_t spl_gs_threshold(spl_gsolver *s, const void *dicts_dev, int64_t k, int64_t n_uniq_global, int32_t *need_ties_host,
+                         void *stream);
+/* ... ties of the threshold score split by arrival order: radix select over the ranks' tie words; the host
+ * all-reduces *hist_dev (2048 x uint32) between spl_gs_tie_hist and spl_gs_tie_pick ... */
+int32_t spl_gs_tie_begin(spl_gsolver *s, int32_t *link_bits_host, void *stream);
+int32_t spl_gs_tie_hist(spl_gsolver *s, int32_t shift, int32_t bits, int32_t first, uint32_t **hist_dev, void *stream);
+int32_t spl_gs_tie_pick(spl_gsolver *s, int32_t shift, int32_t first, void *stream);
+/* ... local cut + local sort by the sort word (score rank << link bits | link; a total order over all ranks) */
+int32_t spl_gs_cut(spl_gsolver *s, int32_t have_tie_threshold, int64_t *kept_local_host, const uint64_t **y_sorted_dev,
+                   int32_t *y_bits_host, void *stream);
+/* global ranks of the survivors (= queue order of the next level): sample sort of the sort words */
+int32_t spl_gs_partition(spl_gsolver *s, const uint64_t *probes_host, int32_t n_probes, int64_t *bounds_host, void *stream);
+int32_t spl_gs_rank_sort(spl_gsolver *s, const uint64_t *y_dev, int64_t n, int32_t y_bits, int64_t base, int64_t *ranks_out_dev,
+                         void *stream);
+int32_t spl_gs_adopt(spl_gsolver *s, const int64_t *granks_dev, int64_t n_global_next, void *stream);
+int32_t spl_gs_frontier(spl_gsolver *s, const void **recs_dev, const uint64_t **granks_dev, int64_t *n_local_host);
+/* parent chain (:459-464): link of the state with global rank `grank` in the queue of `level`, if this rank holds it */
+int32_t spl_gs_link_at(spl_gsolver *s, int32_t level, int64_t grank, int32_t *found_host, uint64_t *link_host);
+
 /* ---- realistic multi-player mode: MultiPlayerState (src/solver.py:471-860) ---------------------
  * State record = 96 bytes:
  *   struct { uint64 mlo; uint32 mhi; uint16 gems; uint16 saved; } p[4];   card mask / gems (3 b per colour) / saved
