@@ -302,6 +302,7 @@ int32_t spl_gs_link_at(spl_gsolver *s, int32_t level, int64_t grank, int32_t *fo
  *   uint8 vis[12];  visible card per market slot in slot order, tier-major (255 = empty)
  *   uint8 cur; uint8 pad[3]; uint64 link; uint64 spare;
  * bonus, pts, gem pool, deck position and final-round state are derived (see csrc/spl_realistic.cuh).
+ * The visited set of this mode is keyed by the EXACT identity (spl_rpack: 384-bit packing), 64-byte buckets.
  * The market order is an INPUT: deck[t] = full sequence of tier t (visible cards first), as built by
  * CardMarket.from_full_deck(shuffle, seed) (src/solver.py:94-119) on the host. */
 typedef struct {
@@ -319,6 +320,10 @@ int32_t spl_rexpand(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, 
                     int64_t cap, int64_t *n_out_host, void *stream);
 /* multi_competitive_heuristic (:778-812), bit-exact doubles */
 int32_t spl_rscore(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, int64_t n, double *scores_dev, void *stream);
+/* The exact identity key of realistic mode (src/solver.py:495-500, PlayerState :177-186): 6 x uint64 per record --
+ * card owner codes, gems and saved per player, deck position of every visible slot, current player (injective; the
+ * reference's own identity is a 64-bit hash of the same fields).  keys_out_dev[n][6]. */
+int32_t spl_rpack(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, int64_t n, uint64_t *keys_out_dev, void *stream);
 /* max(p.pts for p in state.players) per record: the progress line at :832-836 */
 int32_t spl_rmaxpts(spl_ctx *ctx, const spl_rconfig *cfg, const void *recs_dev, int64_t n, uint8_t *out_dev, void *stream);
 /* MultiPlayerState.solve (:750-860): beam always applied, ties by arrival order, game over when play

@@ -83,6 +83,7 @@ def _load():
         'spl_rexpand': (i32, [vp, vp, vp, i64, vp, i64, C.POINTER(i64), vp]),
         'spl_rscore': (i32, [vp, vp, vp, i64, vp, vp]),
         'spl_rmaxpts': (i32, [vp, vp, vp, i64, vp, vp]),
+        'spl_rpack': (i32, [vp, vp, vp, i64, vp, vp]),
         'spl_rsolver_create': (i32, [vp, vp, vp, i64, i32, C.POINTER(vp)]),
         'spl_rsolver_frontier': (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
         'spl_solver_create': (i32, [vp, C.POINTER(Key), u64, i32, i32, i32, i64, i32, i32, i32, C.POINTER(vp)]),

@@ -10,8 +10,9 @@
 //   deck position   : 4 + #cards of the tier owned by anyone            (CardMarket.buy_card :121-170)
 //   is_game_over()  : players[cur].pts >= target  (final round ends when play returns to its trigger, :542-549)
 // Identity (src/solver.py:495-500) = (players incl. saved, pool, visible cards in slot order, current
-// player): the visited table stores a 105-bit fingerprint of exactly those bytes (the reference itself
-// dedups on a 64-bit hash of them).
+// player).  The visited set is keyed by an EXACT 384-bit packing of those fields (r_pack_key): card owner codes,
+// gems and saved per player, the deck position of every visible slot, the current player; the pool is a function
+// of the players' gems.  (The reference itself dedups on a 64-bit hash of the same fields.)
 #pragma once
 #include "spl_kernels.cuh"
 
@@ -37,6 +38,7 @@ struct RConfigDev {
     uint64_t col_lo[NCOL], pt_lo[6], tier_lo[3];
     uint32_t col_hi[NCOL], pt_hi[6], tier_hi[3];
     uint32_t card[SPL_NUM_CARDS];
+    uint8_t pos_of[SPL_NUM_CARDS];  // position of a card inside its tier's deck sequence
 };
 
 __device__ __forceinline__ void ld_rrec(const RRec *p, RRec &r) {
@@ -141,24 +143,185 @@ __device__ __forceinline__ void r_make_child(const RConfigDev &C, const RRec &s,
     }
 }
 
-// 105-bit fingerprint of the identity bytes (players[0..P), vis, cur)
-__device__ __forceinline__ void r_fingerprint(const RConfigDev &C, const RRec &s, uint64_t &lo, uint64_t &hi) {
-    uint64_t a = 0x243F6A8885A308D3ull, b = 0x13198A2E03707344ull;
-    for (int q = 0; q < C.P; ++q) {
-        const uint64_t w0 = s.p[q].mlo, w1 = (uint64_t)s.p[q].mhi | (uint64_t)s.p[q].gems << 32 | (uint64_t)s.p[q].saved << 48;
-        a = mix64(a ^ w0, w1);
-        b = mix64(b + w1 * 0x9E3779B97F4A7C15ull, w0 ^ 0xA4093822299F31D0ull);
+// ------------------------------------------------------------------ exact identity key (384 bits)
+// Injective packing of MultiPlayerState's identity (src/solver.py:495-500; PlayerState :177-186):
+//   owner of every card : 2 bits x 90 (0 = nobody, 1 + player) for 2-3 players; three cards per 7 bits (base 5)
+//                         for 4 players                                                   180 | 210 bits
+//   per player          : gems 15 bits, saved 10 bits                                     25 x P
+//   market              : deck position (6 bits, 63 = empty) of each of the 12 slots, in slot order   72 bits
+//   current player      : 2 bits
+// = 304 / 329 / 384 bits for 2 / 3 / 4 players.  bonus and pts are functions of the cards, the pool of the gems.
+constexpr int RKEY_WORDS = 6;
+struct RKeyWriter {
+    uint64_t w[RKEY_WORDS];
+    int at;
+    __device__ __forceinline__ void put(uint64_t v, int bits) {
+        const int i = at >> 6, o = at & 63;
+        w[i] |= v << o;
+        if (o + bits > 64) w[i + 1] |= v >> (64 - o);
+        at += bits;
     }
-    uint64_t v0 = 0, v1 = 0;
+};
+// returns false if a field does not fit (saved >= 1024): the caller raises an error instead of merging states
+__device__ __forceinline__ bool r_pack_key(const RConfigDev &C, const RRec &s, uint64_t key[RKEY_WORDS]) {
+    RKeyWriter K;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v0 |= (uint64_t)s.vis[k] << (8 * k);
+    for (int i = 0; i < RKEY_WORDS; ++i) K.w[i] = 0;
+    K.at = 0;
+    bool ok = true;
+    auto owner = [&](int card) -> uint32_t {
+        for (int q = 0; q < C.P; ++q)
+            if (card < 64 ? (s.p[q].mlo >> card) & 1 : (s.p[q].mhi >> (card - 64)) & 1) return (uint32_t)q + 1;
+        return 0u;
+    };
+    if (C.P <= 3) {
+        for (int card = 0; card < SPL_NUM_CARDS; ++card) K.put(owner(card), 2);
+    } else {
+        for (int card = 0; card < SPL_NUM_CARDS; card += 3) K.put(owner(card) + 5 * owner(card + 1) + 25 * owner(card + 2), 7);
+    }
+    for (int q = 0; q < C.P; ++q) {
+        K.put(s.p[q].gems & 0x7fffu, 15);
+        ok &= s.p[q].saved < 1024;
+        K.put(s.p[q].saved & 1023u, 10);
+    }
+    for (int k = 0; k < 12; ++k) K.put(s.vis[k] == 255 ? 63u : (uint32_t)C.pos_of[s.vis[k]], 6);
+    K.put(s.cur, 2);
 #pragma unroll
-    for (int k = 8; k < 12; ++k) v1 |= (uint64_t)s.vis[k] << (8 * (k - 8));
-    v1 |= (uint64_t)s.cur << 32;
-    a = mix64(a ^ v0, v1);
-    b = mix64(b ^ v1, v0 * 0xC2B2AE3D27D4EB4Full);
-    lo = a;
-    hi = b & HI_KEY_MASK;
+    for (int i = 0; i < RKEY_WORDS; ++i) key[i] = K.w[i];
+    return ok;
+}
+__device__ __forceinline__ uint64_t r_key_hash(const uint64_t key[RKEY_WORDS]) {
+    uint64_t h = 0x243F6A8885A308D3ull;
+#pragma unroll
+    for (int i = 0; i < RKEY_WORDS; i += 2) h = mix64(h ^ key[i], key[i + 1] + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1));
+    return h;
+}
+
+// Visited table of realistic mode: 64-byte buckets, one state each: {key[6], ctrl, ~t, pad}.
+//   ctrl = 0 empty | tag << 8 | 1 claimed, key being written | tag << 8 | 3 ready.  tag = epoch (level) of insertion.
+// A bucket is claimed with one 64-bit CAS on ctrl; the claimer writes the key and publishes ctrl = ready.  A probe that
+// meets a claimed bucket waits for the key (the writer is running and waits for nobody), then compares all 384 bits.
+// ~t (t = arrival index in the epoch): atomicMax keeps the FIRST arrival, as in the speedrun table.
+struct __align__(64) RBucket {
+    uint64_t key[RKEY_WORDS];
+    unsigned long long ctrl;
+    unsigned int tinv, pad;
+};
+static_assert(sizeof(RBucket) == 64, "RBucket layout");
+constexpr uint32_t R_DEAD = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t r_probe(RBucket *__restrict__ table, uint64_t nb, uint64_t tag, const uint64_t key[RKEY_WORDS],
+                                            uint32_t tinv, uint32_t &n_new, unsigned int *error) {
+    uint64_t b = __umul64hi(r_key_hash(key), nb);
+    for (int probes = 0; probes < MAX_PROBE; ++probes) {
+        RBucket *B = table + b;
+        unsigned long long c = *reinterpret_cast<volatile unsigned long long *>(&B->ctrl);
+        if (c == 0) {
+            c = atomicCAS(&B->ctrl, 0ull, (unsigned long long)(tag << 8 | 1));
+            if (c == 0) {  // claimed: write the key, then publish
+#pragma unroll
+                for (int i = 0; i < RKEY_WORDS; ++i) B->key[i] = key[i];
+                __threadfence();
+                atomicExch(&B->ctrl, (unsigned long long)(tag << 8 | 3));
+                ++n_new;
+                atomicMax(&B->tinv, tinv);
+                return (uint32_t)b;
+            }
+        }
+        while ((c & 3) == 1) c = *reinterpret_cast<volatile unsigned long long *>(&B->ctrl);  // key not published yet
+        __threadfence();
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < RKEY_WORDS; ++i) same &= *reinterpret_cast<volatile uint64_t *>(&B->key[i]) == key[i];
+        if (same) {
+            if ((c >> 8) != tag) return R_DEAD;  // visited in an earlier level
+            if (*reinterpret_cast<volatile unsigned int *>(&B->tinv) > tinv) return R_DEAD;  // an earlier arrival is registered
+            atomicMax(&B->tinv, tinv);
+            return (uint32_t)b;
+        }
+        if (++b == nb) b = 0;
+    }
+    atomicExch(error, 1u);
+    return R_DEAD;
+}
+
+// exact-key probe / insert of a materialised successor list (arrival index = list index)
+__global__ void __launch_bounds__(TILE) r_probe_kernel(const RRec *__restrict__ cand, int64_t n, const RConfigDev *__restrict__ cfg,
+                                                       RBucket *__restrict__ table, uint64_t nb, uint64_t tag,
+                                                       uint32_t *__restrict__ cand_slot, Counters *ctr) {
+    const int64_t t = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    uint32_t n_new = 0;
+    if (t < n) {
+        RRec s;
+        ld_rrec(cand + t, s);
+        uint64_t key[RKEY_WORDS];
+        if (!r_pack_key(*cfg, s, key)) atomicExch(&ctr->error, 4u);
+        cand_slot[t] = r_probe(table, nb, tag, key, ~(uint32_t)t, n_new, &ctr->error);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, d);
+    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&ctr->n_new, (unsigned long long)n_new);
+}
+// winners (first arrivals of new states) in arrival order: out_idx[rank] = list index; 8 candidates per thread
+__global__ void __launch_bounds__(TILE) r_winners_kernel(const uint32_t *__restrict__ cand_slot, const RBucket *__restrict__ table,
+                                                         int64_t n, int64_t *__restrict__ out_idx, uint64_t *status, Counters *ctr,
+                                                         int ticket_id) {
+    __shared__ uint32_t warp_sums[TILE / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * 8;
+    uint32_t mask = 0;
+    for (int q = 0; q < 8; ++q)
+        if (b0 + q < n) {
+            const uint32_t sl = cand_slot[b0 + q];
+            if (sl != R_DEAD && ~ld_cg_u32(&table[sl].tinv) == (uint32_t)(b0 + q)) mask |= 1u << q;
+        }
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(__popc(mask), warp_sums, tot);
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(status, tile, tot, 0);
+        if (threadIdx.x == 0) {
+            s_base = e;
+            if (((int64_t)tile + 1) * TILE * 8 >= n) ctr->n_emitted = e + tot;
+        }
+    }
+    __syncthreads();
+    uint64_t pos = s_base + ex;
+    for (; mask; mask &= mask - 1) out_idx[pos++] = b0 + (__ffs(mask) - 1);
+}
+// move every ready bucket of an old table into a larger one (tags preserved)
+__global__ void __launch_bounds__(TILE) r_rehash_kernel(const RBucket *__restrict__ old_table, uint64_t old_nb,
+                                                        RBucket *__restrict__ table, uint64_t nb, Counters *ctr) {
+    const uint64_t i = (uint64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i >= old_nb || old_table[i].ctrl == 0) return;
+    uint64_t key[RKEY_WORDS];
+#pragma unroll
+    for (int k = 0; k < RKEY_WORDS; ++k) key[k] = old_table[i].key[k];
+    uint64_t b = __umul64hi(r_key_hash(key), nb);
+    for (int probes = 0; probes < MAX_PROBE; ++probes) {
+        if (atomicCAS(&table[b].ctrl, 0ull, old_table[i].ctrl) == 0) {
+#pragma unroll
+            for (int k = 0; k < RKEY_WORDS; ++k) table[b].key[k] = key[k];
+            return;
+        }
+        if (++b == nb) b = 0;
+    }
+    atomicExch(&ctr->error, 1u);
+}
+// the packed keys of a batch (tests: injectivity against the identity bytes)
+__global__ void __launch_bounds__(TILE) r_pack_kernel(const RRec *__restrict__ recs, int64_t n, const RConfigDev *__restrict__ cfg,
+                                                      uint64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (i >= n) return;
+    RRec s;
+    ld_rrec(recs + i, s);
+    uint64_t key[RKEY_WORDS];
+    r_pack_key(*cfg, s, key);
+#pragma unroll
+    for (int k = 0; k < RKEY_WORDS; ++k) out[i * RKEY_WORDS + k] = key[k];
 }
 
 // multi_competitive_heuristic (src/solver.py:778-812), bit-exact: LUT pows, separately rounded ops
@@ -245,12 +408,12 @@ __global__ void __launch_bounds__(TILE) r_count_scan_kernel(const RRec *__restri
     if (p < n) off[p] = (uint32_t)(s_base + excl);
 }
 
-// one thread per parent: write its successors (record + fingerprint) at off[parent] + ordinal
+// one thread per parent: write its successors at off[parent] + ordinal
 __global__ void __launch_bounds__(TILE) r_expand_kernel(const RRec *__restrict__ front, int64_t n,
                                                         const RConfigDev *__restrict__ cfg,
                                                         const uint32_t *__restrict__ off,
                                                         const uint32_t *__restrict__ vmask, int64_t rank_base,
-                                                        RRec *__restrict__ cand, spl_key *__restrict__ cand_key) {
+                                                        RRec *__restrict__ cand) {
     const int64_t p = (int64_t)blockIdx.x * TILE + threadIdx.x;
     if (p >= n) return;
     RRec s;
@@ -267,12 +430,6 @@ __global__ void __launch_bounds__(TILE) r_expand_kernel(const RRec *__restrict__
         o.link = ((uint64_t)(rank_base + p) << 8) | ord;
         o.spare = 0;
         st_rrec(cand + t, o);
-        if (cand_key) {
-            uint64_t lo, hi;
-            r_fingerprint(*cfg, o, lo, hi);
-            cand_key[t].lo = lo;
-            cand_key[t].hi = hi;
-        }
         ++t;
         ++ord;
     }
@@ -328,15 +485,6 @@ __global__ void __launch_bounds__(TILE) r_maxpts_kernel(const RRec *__restrict__
         for (int q = 0; q < cfg->P; ++q) m = max(m, r_pts(*cfg, recs[i].p[q]));
         out[i] = (uint8_t)min(m, 255);
     }
-}
-
-__global__ void r_root_key_kernel(const RRec *root, const RConfigDev *cfg, spl_key *key) {
-    RRec s;
-    ld_rrec(root, s);
-    uint64_t lo, hi;
-    r_fingerprint(*cfg, s, lo, hi);
-    key->lo = lo;
-    key->hi = hi;
 }
 
 __global__ void __launch_bounds__(TILE) r_links_kernel(const RRec *__restrict__ recs, int64_t n, uint64_t *__restrict__ out) {

@@ -90,7 +90,9 @@ struct spl_ctx {
     // scratch
     DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2;
     DevBuf pool_front, pool_uniq, pool_grank;  // frontier buffers lent to the active solver
-    DevBuf rcfg, rcand, rkeys, rvmask, ridx64, rtmp;  // realistic mode scratch
+    DevBuf rcfg, rcand, rvmask, ridx64, rtmp;  // realistic mode scratch
+    RBucket *rtable = nullptr;  // realistic mode: exact-key visited table (64-byte buckets, one state each)
+    uint64_t rnb = 0, rocc = 0, rslots_hint = 0;
     std::vector<DevBuf *> pool_links;  // link columns of finished solves, reused by the next one
     cudaEvent_t ev[8]{};
     long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -274,6 +276,7 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
         CKC(cudaMemset(c->nodes, 0, nn * NODE_WORDS * 8));
         c->nn = nn;
     }
+    c->rslots_hint = cfg->table_slots;
     uint64_t slots = cfg->table_slots ? cfg->table_slots : (1ull << 22);
     slots = std::min<uint64_t>(slots, c->max_table_bytes / 64 * BUCKET_SLOTS);
     slots = std::max<uint64_t>(slots, 1024);
@@ -294,7 +297,7 @@ int32_t spl_destroy(spl_ctx *c) {
     cudaDeviceSynchronize();
     cudaFree(c->table); cudaFree(c->d_tabs); cudaFree(c->d_takes_idx); cudaFree(c->d_takes_edges);
     cudaFree(c->d_lut); cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr); cudaFree(c->d_sel); cudaFreeHost(c->h_sel);
-    cudaFree(c->d_hist); cudaFree(c->d_dict); cudaFree(c->d_dict2); cudaFree(c->d_dest); cudaFree(c->nodes); cudaFree(c->d_gemrank);
+    cudaFree(c->rtable); cudaFree(c->d_hist); cudaFree(c->d_dict); cudaFree(c->d_dict2); cudaFree(c->d_dest); cudaFree(c->nodes); cudaFree(c->d_gemrank);
     for (auto *b : c->pool_links) delete b;
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     delete c;
@@ -1945,6 +1948,8 @@ static int upload_rconfig(spl_ctx *c, const spl_rconfig *cfg, cudaStream_t st) {
         if (cfg->deck_len[t] < 0 || cfg->deck_len[t] > 40) return fail(c, SPL_E_INVALID, "realistic config: bad deck length");
         h.deck_len[t] = cfg->deck_len[t];
         memcpy(h.deck[t], cfg->deck[t], 40);
+        for (int i = 0; i < cfg->deck_len[t]; ++i)
+            if (cfg->deck[t][i] < SPL_NUM_CARDS) h.pos_of[cfg->deck[t][i]] = (uint8_t)i;
     }
     for (int i = 0; i < SPL_NUM_CARDS; ++i) {
         const int t = T.card_pt[i] == 0 ? 0 : T.card_pt[i] <= 2 ? 1 : 2;  // tiers by points, src/solver.py:102-104
@@ -1960,7 +1965,49 @@ static int upload_rconfig(spl_ctx *c, const spl_rconfig *cfg, cudaStream_t st) {
     return SPL_OK;
 }
 
-// count + materialise the successors of front[0..n) into c->rcand (+ fingerprints in c->rkeys)
+// realistic mode's visited table: allocate / grow so that `need` more states keep the load factor <= 0.6
+static int ensure_rtable(spl_ctx *c, uint64_t need, cudaStream_t st) {
+    if (!c->rtable) {
+        // first use: the caller's table_slots sizes THIS table (a realistic search does not use the speedrun tables:
+        // give their memory back first if they were sized large)
+        if (c->occupied == 0 && c->nb > (1ull << 16)) {
+            cudaFree(c->table);
+            c->table = nullptr;
+            CKS(c, alloc_table(c, 1ull << 12, st));
+        }
+        uint64_t nb = std::max<uint64_t>(c->rslots_hint ? c->rslots_hint : (1ull << 16), 1024);
+        nb = std::min<uint64_t>(nb, c->max_table_bytes / 64);
+        CK(c, cudaMalloc(&c->rtable, nb * 64));
+        CK(c, cudaMemsetAsync(c->rtable, 0, nb * 64, st));
+        c->rnb = nb;
+        c->rocc = 0;
+    }
+    while ((double)(c->rocc + need) > 0.6 * (double)c->rnb) {
+        uint64_t nnb = c->rnb * 2;
+        if (nnb * 64 > c->max_table_bytes) nnb = c->max_table_bytes / 64;
+        if (nnb <= c->rnb + c->rnb / 8) break;
+        RBucket *nt = nullptr;
+        cudaError_t e = cudaMalloc(&nt, nnb * 64);
+        if (e != cudaSuccess) { cudaGetLastError(); break; }
+        CK(c, cudaMemsetAsync(nt, 0, nnb * 64, st));
+        r_rehash_kernel<<<nblk((int64_t)c->rnb), TILE, 0, st>>>(c->rtable, c->rnb, nt, nnb, c->d_ctr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        unsigned int err = 0;
+        CK(c, cudaMemcpyAsync(&err, &c->d_ctr->error, 4, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        if (err) { cudaFree(nt); return fail(c, SPL_E_TABLE_FULL, "realistic table rehash into %llu buckets overflowed a probe sequence", (unsigned long long)nnb); }
+        cudaFree(c->rtable);
+        c->rtable = nt;
+        c->rnb = nnb;
+    }
+    if (c->rocc + need / 4 > c->rnb - c->rnb / 16)
+        return fail(c, SPL_E_TABLE_FULL, "realistic visited table full: %llu states + %llu candidates vs %llu buckets (max_table_bytes=%llu)",
+                    (unsigned long long)c->rocc, (unsigned long long)need, (unsigned long long)c->rnb, (unsigned long long)c->max_table_bytes);
+    return SPL_OK;
+}
+
+// count + materialise the successors of front[0..n) into c->rcand
 static int r_expand_all(spl_ctx *c, const RRec *front, int64_t n, int64_t rank_base, bool keys, int64_t *total_out,
                         cudaStream_t st) {
     const unsigned nt = nblk(n);
@@ -1977,9 +2024,9 @@ static int r_expand_all(spl_ctx *c, const RRec *front, int64_t n, int64_t rank_b
     *total_out = total;
     if (total == 0) return SPL_OK;
     CK(c, c->rcand.ensure((size_t)total * 96, 0, st));
-    if (keys) CK(c, c->rkeys.ensure((size_t)total * 16, 0, st));
+    (void)keys;
     r_expand_kernel<<<nt, TILE, 0, st>>>(front, n, c->rcfg.as<RConfigDev>(), c->off.as<uint32_t>(), c->rvmask.as<uint32_t>(),
-                                          rank_base, c->rcand.as<RRec>(), keys ? c->rkeys.as<spl_key>() : nullptr);
+                                          rank_base, c->rcand.as<RRec>());
     ++c->launches;
     CK(c, cudaGetLastError());
     return SPL_OK;
@@ -2011,7 +2058,7 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
         info->ended = 1;
         info->goal_rank = s->goal_rank;
         info->visited = (int64_t)c->occupied;
-        info->table_slots = c->cap;
+        info->table_slots = c->rnb;
         return SPL_OK;
     }
     int64_t total = 0, n_new = 0;
@@ -2021,32 +2068,32 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
     info->expanded = n;
     info->generated = total;
     if (total >= 0xFFFFFFFFll) return fail(c, SPL_E_INVALID, "level produced %lld candidates (>= 2^32)", (long long)total);
-    if (total) {  // first-arrival dedup on the identity fingerprint (:840-843)
-        CKS(c, ensure_table(c, (uint64_t)total, st));
+    if (total) {  // first-arrival dedup on the exact identity key (:840-843)
+        CKS(c, zero_ctr(c, st));
+        CKS(c, ensure_rtable(c, (uint64_t)total, st));
         uint64_t tag;
         CKS(c, next_epoch(c, tag));
         CK(c, c->cand_slot.ensure((size_t)total * 4, 0, st));
         CKS(c, zero_ctr(c, st));
-        probe_list_kernel<IDENT_KEY><<<nblk(total), TILE, 0, st>>>(c->rkeys.as<spl_key>(), total, c->table, c->nb, tag,
-                                                        c->cand_slot.as<uint32_t>(), c->d_ctr);
+        r_probe_kernel<<<nblk(total), TILE, 0, st>>>(c->rcand.as<RRec>(), total, c->rcfg.as<RConfigDev>(), c->rtable, c->rnb, tag,
+                                                      c->cand_slot.as<uint32_t>(), c->d_ctr);
         ++c->launches;
         CK(c, cudaGetLastError());
         CKS(c, read_ctr(c, st));
+        if (c->h_ctr->error == 4) return fail(c, SPL_E_INVALID, "a player saved 1024 gems or more: outside the packed identity key");
         if (c->h_ctr->error) return fail(c, SPL_E_TABLE_FULL, "visited table full during level %d", s->level);
         n_new = (int64_t)c->h_ctr->n_new;
+        c->rocc += n_new;
         c->occupied += n_new;
     }
     info->unique = n_new;
     if (n_new) {
-        CK(c, c->rtmp.ensure((size_t)n_new * 32, 0, st));
         CK(c, c->ridx64.ensure((size_t)n_new * 8, 0, st));
-        const unsigned nt = nblk(total, TILE * 32);
+        const unsigned nt = nblk(total, TILE * 8);
         CKS(c, prep_status(c, 0, nt, st));
         CKS(c, reset_ticket(c, 0, st));
-        resolve_kernel<SRC_LIST, false><<<nt, TILE, sizeof(ResolveSmem), st>>>(
-            nullptr, 0, c->d_tabs, c->d_takes_idx, c->d_takes_edges, nullptr, (uint32_t)total, c->table,
-            c->cand_slot.as<uint32_t>(), c->rkeys.as<spl_key>(), nullptr, 0, 0, c->rtmp.as<Rec>(), nullptr,
-            c->ridx64.as<int64_t>(), 0, 0, c->luts, c->status[0].as<uint64_t>(), c->d_ctr, 0);
+        r_winners_kernel<<<nt, TILE, 0, st>>>(c->cand_slot.as<uint32_t>(), c->rtable, total, c->ridx64.as<int64_t>(),
+                                               c->status[0].as<uint64_t>(), c->d_ctr, 0);
         CK(c, s->uniq.ensure((size_t)n_new * 96, 0, st));
         r_gather_kernel<int64_t><<<nblk(n_new), TILE, 0, st>>>(c->rcand.as<RRec>(), c->ridx64.as<int64_t>(), n_new, s->uniq.as<RRec>());
         c->launches += 2;
@@ -2058,7 +2105,7 @@ static int rsolver_step(spl_solver *s, spl_level_info *info, cudaStream_t st) {
             s->pend_uniq = n_new;
             info->kept = -1;
             info->visited = (int64_t)c->occupied;
-            info->table_slots = c->cap;
+            info->table_slots = c->rnb;
             s->pend_info = *info;
             return SPL_OK;
         }
@@ -2096,7 +2143,7 @@ static int realistic_cut(spl_solver *s, spl_level_info *info, int64_t n, int64_t
     }
     info->kept = kept;
     info->visited = (int64_t)c->occupied;
-    info->table_slots = c->cap;
+    info->table_slots = c->rnb;
     // queue exhausted, or the turn limit: the reference leaves its loop after the iteration with turn == 1000
     // (src/solver.py:846-852), so `puzzle` is the last state dequeued from THAT queue and the path has 1001 states
     if (kept == 0 || s->level >= 1000) {
@@ -2336,6 +2383,18 @@ int32_t spl_rscore(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t
     return SPL_OK;
 }
 
+int32_t spl_rpack(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, uint64_t *keys_out, void *stream) {
+    if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_rpack: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    if (n == 0) return SPL_OK;
+    CKS(c, upload_rconfig(c, cfg, st));
+    r_pack_kernel<<<nblk(n), TILE, 0, st>>>(reinterpret_cast<const RRec *>(recs), n, c->rcfg.as<RConfigDev>(), keys_out);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
 int32_t spl_rmaxpts(spl_ctx *c, const spl_rconfig *cfg, const void *recs, int64_t n, uint8_t *out, void *stream) {
     if (!c || n < 0) return fail(c, SPL_E_INVALID, "spl_rmaxpts: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -2369,21 +2428,26 @@ int32_t spl_rsolver_create(spl_ctx *c, const spl_rconfig *cfg, const void *root_
         c->h2d_bytes += 96;
         if (e != cudaSuccess) rc = fail(c, SPL_E_CUDA, "root upload: %s", cudaGetErrorString(e));
     }
-    if (rc == SPL_OK) {  // trail = {self: None}: register the root's identity fingerprint
+    if (rc == SPL_OK) {  // trail = {self: None}: register the root's identity key
         s->n_front = 1;
-        cudaError_t e = c->rkeys.ensure(16, 0, st);
-        if (e == cudaSuccess) e = c->rcand.ensure(96, 0, st);
+        cudaError_t e = c->rcand.ensure(96, 0, st);
         if (e == cudaSuccess) e = c->cand_slot.ensure(4, 0, st);
         if (e != cudaSuccess) rc = fail(c, SPL_E_NOMEM, "realistic scratch alloc");
     }
     if (rc == SPL_OK) rc = zero_ctr(c, st);
+    if (rc == SPL_OK) rc = ensure_rtable(c, 1, st);
+    if (rc == SPL_OK && c->rocc) {  // forget the previous search
+        if (cudaMemsetAsync(c->rtable, 0, c->rnb * 64, st) != cudaSuccess) rc = fail(c, SPL_E_CUDA, "realistic table reset failed");
+        c->rocc = 0;
+    }
     if (rc == SPL_OK) {
         uint64_t tag;
         rc = next_epoch(c, tag);
         if (rc == SPL_OK) {
-            r_root_key_kernel<<<1, 1, 0, st>>>(s->front.as<RRec>(), c->rcfg.as<RConfigDev>(), c->rkeys.as<spl_key>());
-            probe_list_kernel<IDENT_KEY><<<1, TILE, 0, st>>>(c->rkeys.as<spl_key>(), 1, c->table, c->nb, tag, c->cand_slot.as<uint32_t>(), c->d_ctr);
-            c->launches += 2;
+            r_probe_kernel<<<1, TILE, 0, st>>>(s->front.as<RRec>(), 1, c->rcfg.as<RConfigDev>(), c->rtable, c->rnb, tag,
+                                                c->cand_slot.as<uint32_t>(), c->d_ctr);
+            ++c->launches;
+            c->rocc = 1;
             c->occupied = 1;
         }
     }

@@ -260,6 +260,15 @@ class Engine:
         check(lib.spl_rscore(self._h, C.byref(rcfg), src.data_ptr(), n, out.data_ptr(), self._stream()), self._h)
         return out.cpu().numpy()
 
+    def rpack(self, rcfg, recs_np: np.ndarray) -> np.ndarray:
+        """exact 384-bit identity keys (6 x uint64 per record) of a batch of realistic-mode records"""
+        recs_np = np.ascontiguousarray(recs_np).reshape(-1)
+        n = len(recs_np)
+        src = torch.from_numpy(recs_np.view(np.uint8).reshape(n, 96).copy()).to(self.tdev)
+        out = torch.zeros((n, 6), dtype=torch.int64, device=self.tdev)
+        check(lib.spl_rpack(self._h, C.byref(rcfg), src.data_ptr(), n, out.data_ptr(), self._stream()), self._h)
+        return out.cpu().numpy().view(np.uint64)
+
     def rsolver(self, rcfg, root_rec_np: np.ndarray, beam_width: int, keep_links: bool = True) -> 'RLevelSolver':
         return RLevelSolver(self, rcfg, root_rec_np, beam_width, keep_links)
 

@@ -62,6 +62,27 @@ def test_rscore_bit_exact_vs_oracle(eng, golden):
     s.close()
 
 
+@pytest.mark.parametrize('run_idx', [4, 5, 6])
+def test_exact_identity_key_is_injective(eng, golden, run_idx):
+    """spl_rpack: two states get the same 384-bit key iff their identity bytes (players incl. saved, visible cards in
+    slot order, current player: src/solver.py:495-500) are equal -- over the queues of a 2-, 3- and 4-player search."""
+    run = golden['realistic_runs'][run_idx]
+    P, gpc = run['players'], run['gems_per_color']
+    ocfg = oracle.make_rconfig(P, run['goal'], gpc, [run['market']['t1'], run['market']['t2'], run['market']['t3']])
+    cfg = _cfg(P, run['goal'], gpc, run['market'])
+    s = oracle.RSolver(ocfg, run['beam'])
+    for _ in range(25):
+        s.step()
+    recs = np.concatenate([s.level(i) for i in range(3, 25)])
+    s.close()
+    keys = eng.rpack(cfg, recs)
+    ident = [oracle.rident_bytes(r, P) for r in recs]
+    assert len({bytes(k) for k in keys}) == len(set(ident))
+    by_key = {}
+    for k, i in zip(keys, ident):
+        assert by_key.setdefault(bytes(k), i) == i
+
+
 def test_rsolver_vs_reference_and_oracle(eng, golden):
     """MultiPlayerState.solve: every ply's kept set in rank order (incl. saved, market order, parent links),
     visited count, ply count and the winning line vs the unmodified reference; full arrays vs the oracle."""
