@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(TILE) m2_buys_kernel(const Rec *__restrict__ f
 // counts come from sort_hist_kernel + scan_u32_kernel (digit-major matrix).  The tile is first ordered by digit
 // in shared memory, so that consecutive threads write consecutive addresses of each digit's output range (whole
 // sectors) instead of scattering single values.
-__global__ void __launch_bounds__(TILE) psort_scatter_kernel(const uint64_t *__restrict__ v_in, int64_t n, int shift,
-                                                             const uint32_t *__restrict__ matrix_scanned, uint32_t ntiles,
-                                                             uint64_t *__restrict__ v_out) {
+__global__ void __launch_bounds__(TILE, 4) psort_scatter_kernel(const uint64_t *__restrict__ v_in, int64_t n, int shift,
+                                                                const uint32_t *__restrict__ matrix_scanned, uint32_t ntiles,
+                                                                uint64_t *__restrict__ v_out) {
     __shared__ uint32_t whist[TILE / 32][SORT_BINS];
     __shared__ uint32_t dbase[SORT_BINS], gbase[SORT_BINS];
     __shared__ uint32_t warp_sums[TILE / 32 + 1];
@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(TILE) psort_scatter_kernel(const uint64_t *__r
     __syncthreads();
     const int64_t tbase = (int64_t)blockIdx.x * SORT_TILE, wbase = tbase + (int64_t)w * (32 * SORT_ITEMS);
     uint64_t v[SORT_ITEMS];
+    uint16_t off[SORT_ITEMS];  // position of the value among the warp's values with the same digit (stable)
 #pragma unroll
     for (int q = 0; q < SORT_ITEMS; ++q) {  // the warp's contiguous 512-value segment, 32 consecutive values per step
         const int64_t i = wbase + q * 32 + lane;
@@ -247,9 +248,17 @@ __global__ void __launch_bounds__(TILE) psort_scatter_kernel(const uint64_t *__r
         v[q] = ok ? v_in[i] : 0;
         const uint32_t d = (uint32_t)(v[q] >> shift) & (SORT_BINS - 1);
         const unsigned act = __ballot_sync(0xffffffffu, ok);
+        off[q] = 0;
         if (ok) {
             const unsigned peers = __match_any_sync(act, d);
-            if (lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += __popc(peers);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if ((int)lane == leader) {
+                old = whist[w][d];
+                whist[w][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(peers, old, leader);
+            off[q] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
         }
         __syncwarp();
     }
@@ -272,16 +281,7 @@ __global__ void __launch_bounds__(TILE) psort_scatter_kernel(const uint64_t *__r
 #pragma unroll
     for (int q = 0; q < SORT_ITEMS; ++q) {  // stable placement inside the tile
         const int64_t i = wbase + q * 32 + lane;
-        const bool ok = i < n;
-        const uint32_t d = (uint32_t)(v[q] >> shift) & (SORT_BINS - 1);
-        const unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            const unsigned peers = __match_any_sync(act, d);
-            stage[whist[w][d] + __popc(peers & ((1u << lane) - 1))] = v[q];
-            __syncwarp(peers);
-            if (lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += __popc(peers);
-        }
-        __syncwarp();
+        if (i < n) stage[whist[w][(uint32_t)(v[q] >> shift) & (SORT_BINS - 1)] + off[q]] = v[q];
     }
     __syncthreads();
     const uint32_t cnt = (uint32_t)min((int64_t)SORT_TILE, n - tbase);
@@ -492,6 +492,21 @@ __device__ __forceinline__ void bm_step(const GroupArgs &A, WarpStage &W, uint64
     W.cnt += __popc(wb);
     if (W.cnt > SM_STAGE - 32) stage_flush(A, W);
 }
+// the gem takes of TWO parents in one step: lanes 0..15 the earlier parent (lane P0 of the item window), lanes 16..31
+// the later one (lane P1); both have at most 16 takes.  Their successors may coincide, so the step resolves equal
+// gem hands in lane order (== arrival order).
+__device__ __forceinline__ void take_steps_pair(const GroupArgs &A, WarpStage &W, uint64_t *bm, const Rec &it, uint64_t grank,
+                                                uint32_t tk, uint32_t nb, int P0, int P1) {
+    const unsigned lane = threadIdx.x & 31;
+    const int src = lane < 16 ? P0 : P1;
+    const uint64_t plo = __shfl_sync(0xffffffffu, it.lo, src), phi = __shfl_sync(0xffffffffu, it.hi, src);
+    const uint64_t paux = __shfl_sync(0xffffffffu, it.aux, src), pgr = __shfl_sync(0xffffffffu, grank, src);
+    const uint32_t ptk = __shfl_sync(0xffffffffu, tk, src), pnb = __shfl_sync(0xffffffffu, nb, src);
+    const uint32_t q = lane & 15;
+    const bool act = q < (ptk & 0xff);
+    const uint32_t g = act ? (uint32_t)__ldg(A.takes_edges + (ptk >> 8) + q) : 0u;
+    bm_step(A, W, bm, act, true, g, (pgr << 8) | (pnb + q), (plo & ~GEM_MASK) | g, phi, paux);
+}
 // the gem takes (src/solver.py:381-388) of one parent (fields warp-uniform), 32 table edges per step
 __device__ __forceinline__ void take_steps(const GroupArgs &A, WarpStage &W, uint64_t *bm, uint64_t plo, uint64_t phi, uint64_t paux,
                                            uint64_t pgr, uint32_t ptk, uint32_t pnb) {
@@ -630,8 +645,23 @@ __global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
                 } else {  // pmask != 0 here: every record left in the window arrives after parent X
                     const int P = __ffs(pmask) - 1;
                     pmask &= pmask - 1;
-                    take_steps(A, W, bm, __shfl_sync(0xffffffffu, it.lo, P), __shfl_sync(0xffffffffu, it.hi, P),
-                               __shfl_sync(0xffffffffu, it.aux, P), X, __shfl_sync(0xffffffffu, tk, P), __shfl_sync(0xffffffffu, nb, P));
+                    // the next parent of the window rides along if both have at most 16 takes and no buy record arrives
+                    // between them (none left in the window with a smaller rank, none outside the window at all)
+                    const int P1 = pmask ? __ffs(pmask) - 1 : -1;
+                    bool pair = false;
+                    if (P1 >= 0) {
+                        const uint32_t n0 = __shfl_sync(0xffffffffu, tk, P) & 0xff, n1 = __shfl_sync(0xffffffffu, tk, P1) & 0xff;
+                        const uint64_t X1 = __shfl_sync(0xffffffffu, grank, P1);
+                        const unsigned between = bmask & __ballot_sync(0xffffffffu, brank < X1);
+                        pair = n0 <= 16 && n1 <= 16 && between == 0 && (bmask != 0 || bnext >= e);
+                    }
+                    if (pair) {
+                        pmask &= pmask - 1;
+                        take_steps_pair(A, W, bm, it, grank, tk, nb, P, P1);
+                    } else {
+                        take_steps(A, W, bm, __shfl_sync(0xffffffffu, it.lo, P), __shfl_sync(0xffffffffu, it.hi, P),
+                                   __shfl_sync(0xffffffffu, it.aux, P), X, __shfl_sync(0xffffffffu, tk, P), __shfl_sync(0xffffffffu, nb, P));
+                    }
                 }
             }
             node_close(N, bm);

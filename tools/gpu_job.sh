@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -q -x -k "realistic or multiplayer or identity_key" > gpurun_out/r2u_pytest.log 2>&1
-tail -12 gpurun_out/r2u_pytest.log
-timeout 300 python bench.py --config C5 --beam 2000000 --steps 2 --warmup 1 --no-parity --no-cpu-baseline 2>&1 | cut -c1-330
-timeout 300 python bench.py --config C5 --players 3 --beam 2000000 --steps 2 --warmup 1 --no-parity --no-cpu-baseline 2>&1 | cut -c1-330
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_baseline_sizes.py -m gpu -q -x -k "not beam_3m" > gpurun_out/r2x_pytest.log 2>&1
+tail -3 gpurun_out/r2x_pytest.log
+SPL_DEBUG=1 QUIET=1 timeout 300 python tools/explore.py --beam 30000000 --reps 2 > gpurun_out/r2x_debug_30m.log 2>&1; grep -E "grouped|rep|SUMMARY" gpurun_out/r2x_debug_30m.log | tail -4
+SPL_TIMING=1 timeout 300 python tools/sharded_check.py --grouped --beam 30000000 --no-oracle --no-links --reps 2 2>&1 | grep -v "^\*\*\|OMP" | tail -3
