@@ -411,7 +411,7 @@ def run_b200(a):
         ms_stage = {'sort': sum(i['ms_sort'] for i in lv), 'thread': sum(i['ms_thread'] for i in lv),
                     'warp': sum(i['ms_warp'] for i in lv), 'cta': sum(i['ms_cta'] for i in lv)}
         dedup_ms = ms_stage['thread'] + ms_stage['warp'] + ms_stage['cta']
-        kernel = 'm2_group_tiny_kernel + gs_group_table_kernel + m2_group_big_kernel (per-run dedup of the rank\'s card sets)'
+        kernel = 'm2_group_tiny_kernel + m2_group_warp_kernel + m2_group_big_kernel (per-run dedup of the rank\'s card sets)'
         launches_k = 3 * len(lv)
     elif 'ms_expand' in (lv[0] if lv else {}):
         ms_stage = {s: sum(i['ms_' + s] for i in lv) for s in ('count', 'expand', 'resolve', 'select', 'sort')}

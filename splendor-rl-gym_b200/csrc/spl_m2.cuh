@@ -554,16 +554,19 @@ __device__ __forceinline__ void warp_epilogue(const GroupArgs &A, WarpStage &W, 
     }
 }
 
+constexpr int BSORT_MAX = 512;  // buy records of one run the warp kernel can put into arrival order itself
 struct WarpSmem {
     SmemTabs tabs;
     uint64_t bm[M2_WARPS][NODE_BM_WORDS + 2];
     uint64_t st[5][M2_WARPS][SM_STAGE];  // lo, hi, aux, link, sk
+    uint64_t bsort[M2_WARPS][BSORT_MAX]; // UNORDERED only (last member: the arrival-ordered launch leaves it out)
 };
 
 // Class CLS_WARP of the dispatch (THREAD_W < candidates <= WARP_W): one warp per run.  The run is streamed through a
 // parent window and a buy-record window of 32 lanes each, once per card set it holds (almost always one; several
 // only when two sets share a 32-bit sort key).  Persistent grid: warp w takes list entries w, w + W, ...
 constexpr int MAX_SETS = 4;  // card sets under one sort key that the thread / warp kernels can tell apart
+template <bool UNORDERED>
 __global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem &S = *reinterpret_cast<WarpSmem *>(smem_raw);
@@ -583,6 +586,33 @@ __global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
             const unsigned pm = __ballot_sync(0xffffffffu, b0 + lane < e && item_id(A, b0 + lane) < A.np);
             pe += __popc(pm);
             if (pm != 0xffffffffu) break;
+        }
+        // Records that came from several ranks are not in arrival order: sort this run's (link, index) pairs in shared
+        // memory (bitonic, warp-cooperative) and read the buy window through the sorted indices.
+        const uint32_t nbuy = e - pe;
+        const bool resort = UNORDERED && nbuy > 1;
+        uint64_t *bs = S.bsort[w];
+        if (resort) {
+            if (nbuy > BSORT_MAX) {  // (cannot happen while warp_max <= BSORT_MAX; kept as a guard)
+                if (lane == 0) A.cls_list[CLS_CTA][atomicAdd(&A.ctr->n_cls[CLS_CTA], 1u)] = r;
+                continue;
+            }
+            uint32_t npow = 32;
+            while (npow < nbuy) npow <<= 1;
+            for (uint32_t i = lane; i < npow; i += 32)
+                bs[i] = i < nbuy ? (A.brec[item_id(A, pe + i) - A.np].link << 10) | i : ~0ull;
+            __syncwarp();
+            for (uint32_t k = 2; k <= npow; k <<= 1)
+                for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+                    for (uint32_t i = lane; i < npow; i += 32) {
+                        const uint32_t x = i ^ jj;
+                        if (x > i) {
+                            const uint64_t a = bs[i], b = bs[x];
+                            if ((a > b) == ((i & k) == 0)) { bs[i] = b; bs[x] = a; }
+                        }
+                    }
+                    __syncwarp();
+                }
         }
         uint64_t d0[MAX_SETS], d1[MAX_SETS];  // card sets done so far
         int n_done = 0;
@@ -622,7 +652,8 @@ __global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
                     const bool valid = bnext + lane < e;
                     uint64_t m0 = 0, m1 = 0;
                     if (valid) {
-                        ld_rec(A.brec + (item_id(A, bnext + lane) - A.np), bt);
+                        const uint32_t at = resort ? pe + (uint32_t)(bs[bnext - pe + lane] & 1023u) : bnext + lane;
+                        ld_rec(A.brec + (item_id(A, at) - A.np), bt);
                         mask_words(bt.lo, bt.hi, m0, m1);
                         brank = bt.link >> 8;
                     }
@@ -631,7 +662,10 @@ __global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
 #pragma unroll
                     for (int d = 0; d < MAX_SETS; ++d) other = other && !(d < n_done && d0[d] == m0 && d1[d] == m1);
                     const unsigned om = __ballot_sync(0xffffffffu, other);
-                    if (om) next_lead = min(next_lead, bnext + (uint32_t)__ffs(om) - 1);
+                    if (om) {  // item position of the first record of a card set not walked yet
+                        const uint32_t j = bnext - pe + (uint32_t)__ffs(om) - 1;
+                        next_lead = min(next_lead, resort ? pe + (uint32_t)(bs[j] & 1023u) : pe + j);
+                    }
                     bmask = __ballot_sync(0xffffffffu, ok);
                     bnext += 32;
                     continue;

@@ -6,10 +6,10 @@
 // straight into per-destination ranges of a send buffer by the kernel that generates them.  The owner sorts its
 // parents and the records it received by card set and runs the same per-run dedup.
 //
-// Records received from several ranks are NOT in global arrival order, so the kernels here resolve "first arrival
-// wins" (src/solver.py:447-450) by the arrival index itself (link = global parent rank << 8 | ordinal): a
-// shared-memory table keeps the minimum per gem hand (warp kernel) -- the CTA kernel of spl_m2.cuh already works
-// that way -- instead of relying on the walk order as the single-GPU warp kernel does.
+// Records received from several ranks are NOT in global arrival order (GroupArgs::unordered): the thread kernel
+// compares the arrival indices (link = global parent rank << 8 | ordinal) of equal gem hands, the warp kernel first
+// sorts the (link, index) pairs of a run's records in shared memory and then walks them as on one GPU, and the CTA
+// kernel takes the minimum arrival index per gem hand anyway.
 #pragma once
 #include "spl_m2.cuh"
 
@@ -171,136 +171,6 @@ __global__ void __launch_bounds__(TILE) gs_recv_items_kernel(const Rec *__restri
     ld_cg_u64x2(reinterpret_cast<const uint64_t *>(recv + j), lo, hi);
     mask_words(lo, hi, m0, m1);
     iv[np + j] = (mask_hash(m0, m1) & 0xFFFFFFFF00000000ull) | (uint64_t)(np + j);
-}
-
-// ------------------------------------------------------------------ order-agnostic warp kernel
-// One warp per run of at most TBL_W candidates of ONE card set: a shared-memory table keeps, per gem hand, the
-// minimum arrival index among the candidates not in the node's bitmap (pass 0); pass 1 emits the candidates that
-// hold the minimum.  A run with several card sets is handed to the CTA kernel untouched.
-constexpr int TBL_SLOTS = 1024, TBL_W = 512, TBL_WARPS = 4;
-__device__ __forceinline__ uint32_t tbl_slot(uint32_t g) { return (g * 0x9E3779B1u) >> 22; }
-// entry = (gems + 1) << 48 | t : equal gems share the high part, so atomicMin keeps the first arrival
-__device__ __forceinline__ void tbl_insert(uint64_t *tbl, uint32_t g, uint64_t t) {
-    const uint64_t mine = ((uint64_t)(g + 1) << 48) | t;
-    uint32_t s = tbl_slot(g);
-    for (;;) {
-        uint64_t cur = tbl[s];
-        if (cur == 0) {
-            cur = atomicCAS(reinterpret_cast<unsigned long long *>(&tbl[s]), 0ull, (unsigned long long)mine);
-            if (cur == 0) return;
-        }
-        if ((cur >> 48) == (mine >> 48)) {
-            atomicMin(reinterpret_cast<unsigned long long *>(&tbl[s]), (unsigned long long)mine);
-            return;
-        }
-        s = (s + 1) & (TBL_SLOTS - 1);
-    }
-}
-__device__ __forceinline__ bool tbl_is_first(const uint64_t *tbl, uint32_t g, uint64_t t) {
-    const uint64_t mine = ((uint64_t)(g + 1) << 48) | t;
-    uint32_t s = tbl_slot(g);
-    for (;;) {
-        const uint64_t cur = tbl[s];
-        if (cur == 0) return false;
-        if ((cur >> 48) == (mine >> 48)) return cur == mine;
-        s = (s + 1) & (TBL_SLOTS - 1);
-    }
-}
-struct TblSmem {
-    SmemTabs tabs;
-    uint64_t tbl[TBL_WARPS][TBL_SLOTS];
-    uint64_t bm[TBL_WARPS][NODE_BM_WORDS + 2];
-    uint64_t st[5][TBL_WARPS][SM_STAGE];
-};
-__device__ __forceinline__ void tbl_step(const GroupArgs &A, WarpStage &W, uint64_t *tbl, uint64_t *bm, int pass, bool act,
-                                         uint32_t g, uint64_t t, uint64_t clo, uint64_t chi, uint64_t caux) {
-    const unsigned lane = threadIdx.x & 31;
-    uint32_t rk = 0;
-    if (act) rk = __ldg(A.gemrank + g);
-    if (pass == 0) {
-        if (act && !((bm[rk >> 6] >> (rk & 63)) & 1)) tbl_insert(tbl, g, t);
-        return;
-    }
-    const bool win = act && tbl_is_first(tbl, g, t);
-    const unsigned wb = __ballot_sync(0xffffffffu, win);
-    if (win) {
-        const uint32_t at = W.cnt + __popc(wb & ((1u << lane) - 1));
-        W.lo[at] = clo; W.hi[at] = chi; W.aux[at] = caux; W.link[at] = t;
-        const uint64_t k = flip_f64((uint64_t)__double_as_longlong(score_state(A.h, A.noise_mode, clo, chi & HI_KEY_MASK, caux, A.L)));
-        W.sk[at] = k;
-        W.kmin = min(W.kmin, k); W.kmax = max(W.kmax, k);
-        atomicOr(reinterpret_cast<unsigned long long *>(&bm[rk >> 6]), 1ull << (rk & 63));
-    }
-    W.cnt += __popc(wb);
-    if (W.cnt > SM_STAGE - 32) stage_flush(A, W);
-}
-__global__ void __launch_bounds__(TBL_WARPS * 32, 5) gs_group_table_kernel(GroupArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TblSmem &S = *reinterpret_cast<TblSmem *>(smem_raw);
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    load_tabs(S.tabs, A.tabs);
-    __syncthreads();
-    uint64_t *tbl = S.tbl[w], *bm = S.bm[w];
-    WarpStage W{S.st[0][w], S.st[1][w], S.st[2][w], S.st[3][w], S.st[4][w], 0, ~0ull, 0};
-    const uint32_t n_list = A.ctr->n_cls[CLS_WARP];
-    uint32_t n_fresh = 0;
-    for (uint32_t j = blockIdx.x * TBL_WARPS + w; j < n_list; j += gridDim.x * TBL_WARPS) {
-        const uint32_t r = A.cls_list[CLS_WARP][j];
-        const uint32_t s = A.run_start[r], e = A.run_start[r + 1];
-        // card set of the run = that of its first item; any other set in the run -> CTA kernel (nothing done here)
-        uint64_t M0 = 0, M1 = 0;
-        if (lane == 0) {
-            const uint32_t id = item_id(A, s);
-            const Rec *src = id < A.np ? A.front + id : A.brec + (id - A.np);
-            mask_words(src->lo, src->hi, M0, M1);
-        }
-        M0 = __shfl_sync(0xffffffffu, M0, 0); M1 = __shfl_sync(0xffffffffu, M1, 0);
-        bool multi = false;
-        for (uint32_t b0 = s; b0 < e && !multi; b0 += 32) {
-            uint64_t m0 = M0, m1 = M1;
-            if (b0 + lane < e) {
-                const uint32_t id = item_id(A, b0 + lane);
-                uint64_t lo, hi;
-                ld_cg_u64x2(reinterpret_cast<const uint64_t *>(id < A.np ? A.front + id : A.brec + (id - A.np)), lo, hi);
-                mask_words(lo, hi, m0, m1);
-            }
-            multi = __any_sync(0xffffffffu, m0 != M0 || m1 != M1);
-        }
-        if (multi) {
-            if (lane == 0) A.cls_list[CLS_CTA][atomicAdd(&A.ctr->n_cls[CLS_CTA], 1u)] = r;
-            continue;
-        }
-#pragma unroll
-        for (int i = 0; i < TBL_SLOTS / 32; ++i) tbl[i * 32 + lane] = 0;
-        uint64_t *N = node_open(A, M0, M1, bm, n_fresh);
-        for (int pass = 0; pass < 2; ++pass) {
-            for (uint32_t b0 = s; b0 < e; b0 += 32) {
-                const bool valid = b0 + lane < e;
-                Rec it{0, 0, 0, 0};
-                bool isP = false;
-                uint32_t nb = 0, tk = 0;
-                uint64_t grank = 0, m0, m1;
-                if (valid) load_item(A, S.tabs, b0 + lane, it, isP, nb, tk, grank, m0, m1);
-                tbl_step(A, W, tbl, bm, pass, valid && !isP, (uint32_t)(it.lo & GEM_MASK), it.link, it.lo, it.hi, it.aux);
-                for (unsigned rest = __ballot_sync(0xffffffffu, valid && isP); rest; rest &= rest - 1) {
-                    const int P = __ffs(rest) - 1;
-                    const uint64_t plo = __shfl_sync(0xffffffffu, it.lo, P), phi = __shfl_sync(0xffffffffu, it.hi, P);
-                    const uint64_t paux = __shfl_sync(0xffffffffu, it.aux, P), pgr = __shfl_sync(0xffffffffu, grank, P);
-                    const uint32_t ptk = __shfl_sync(0xffffffffu, tk, P), pnb = __shfl_sync(0xffffffffu, nb, P);
-                    const uint32_t ntk = ptk & 0xff;
-                    for (uint32_t q0 = 0; q0 < ntk; q0 += 32) {
-                        const uint32_t q = q0 + lane;
-                        const bool act = q < ntk;
-                        const uint32_t g = act ? (uint32_t)__ldg(A.takes_edges + (ptk >> 8) + q) : 0u;
-                        tbl_step(A, W, tbl, bm, pass, act, g, (pgr << 8) | (pnb + q), (plo & ~GEM_MASK) | g, phi, paux);
-                    }
-                }
-            }
-            __syncwarp();  // pass 0 inserts complete before pass 1 reads the table
-        }
-        node_close(N, bm);
-    }
-    warp_epilogue(A, W, n_fresh);
 }
 
 // ------------------------------------------------------------------ dictionary merge (global beam threshold)

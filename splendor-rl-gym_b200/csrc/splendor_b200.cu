@@ -262,10 +262,10 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_PROBE, IDENT_PYHASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(expand_kernel<MODE_LIST, IDENT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem2)));
     CKC(cudaFuncSetAttribute(m2_buys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuySmem)));
-    CKC(cudaFuncSetAttribute(m2_group_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
+    CKC(cudaFuncSetAttribute(m2_group_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offsetof(WarpSmem, bsort)));
+    CKC(cudaFuncSetAttribute(m2_group_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
     CKC(cudaFuncSetAttribute(m2_group_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
     CKC(cudaFuncSetAttribute(gs_buys_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RouteSmem)));
-    CKC(cudaFuncSetAttribute(gs_group_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TblSmem)));
     CKC(cudaMalloc(&c->d_dict2, sizeof(ScoreDict)));
     CKC(cudaMalloc(&c->d_dest, 2 * MAX_RANKS * 8));
     {
@@ -1263,7 +1263,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         // dispatch + thread kernel over all runs, then the warp kernel and the CTA kernel over the runs it queued
         m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
         CK(c, cudaEventRecord(c->ev[4], st));
-        m2_group_warp_kernel<<<148 * 4, TILE, sizeof(WarpSmem), st>>>(A);
+        m2_group_warp_kernel<false><<<148 * 4, TILE, offsetof(WarpSmem, bsort), st>>>(A);
         CK(c, cudaEventRecord(c->ev[5], st));
         CK(c, cudaEventRecord(c->ev[6], st));
         m2_group_big_kernel<<<148 * 4, TILE, sizeof(BigSmem), st>>>(A);
@@ -1562,7 +1562,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     A.front = s->front.as<Rec>() + s->r_p0; A.brec = reinterpret_cast<const Rec *>(recv_dev); A.iv = c->y[cur].as<uint64_t>();
     A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
     A.np = (uint32_t)np; A.rank_base = 0; A.grank = s->grank.as<uint64_t>() + s->r_p0; A.unordered = 1;
-    A.warp_max = TBL_W;  // the table of the order-agnostic warp kernel holds TBL_SLOTS = 2 x TBL_W entries
+    A.warp_max = std::min<uint32_t>(BIG_W, BSORT_MAX);  // the warp kernel sorts at most BSORT_MAX records of a run itself
     A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges; A.gemrank = c->d_gemrank;
     A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>(); A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)s->n_uniq;
     for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
@@ -1572,7 +1572,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     CK(c, cudaEventRecord(c->ev[1], st));
     m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
     CK(c, cudaEventRecord(c->ev[2], st));
-    gs_group_table_kernel<<<148 * 5, TBL_WARPS * 32, sizeof(TblSmem), st>>>(A);
+    m2_group_warp_kernel<true><<<148 * 4, TILE, sizeof(WarpSmem), st>>>(A);
     CK(c, cudaEventRecord(c->ev[3], st));
     m2_group_big_kernel<<<148 * 4, TILE, sizeof(BigSmem), st>>>(A);
     CK(c, cudaEventRecord(c->ev[4], st));
@@ -1584,7 +1584,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     cudaEventElapsedTime(&t3, c->ev[2], c->ev[3]); cudaEventElapsedTime(&t4, c->ev[3], c->ev[4]);
     s->ms[0] += t1; s->ms[1] += t2; s->ms[2] += t3; s->ms[3] += t4;
     if (dbg) {
-        fprintf(stderr, "[gs r%d] L%d np=%lld recv=%lld takes=%llu runs=%llu warp=%u cta=%u winners=%llu | sort+runs %.2f tiny %.2f table %.2f cta %.2f ms\n",
+        fprintf(stderr, "[gs r%d] L%d np=%lld recv=%lld takes=%llu runs=%llu warp=%u cta=%u winners=%llu | sort+runs %.2f tiny %.2f warp %.2f cta %.2f ms\n",
                 s->rank, s->level, (long long)np, (long long)n_recv, (unsigned long long)s->r_takes, (unsigned long long)n_runs,
                 c->h_ctr->n_cls[CLS_WARP], c->h_ctr->n_cls[CLS_CTA], (unsigned long long)c->h_ctr->n_emitted, t1, t2, t3, t4);
     }
