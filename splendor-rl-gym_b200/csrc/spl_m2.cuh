@@ -292,6 +292,167 @@ __global__ void __launch_bounds__(TILE, 4) psort_scatter_kernel(const uint64_t *
     }
 }
 
+// ------------------------------------------------------------------ 2b. one-sweep passes (rounds below 2^30 items)
+// The sort key of an item is the top ITEM_KEY_BITS = 30 bits of its card-set hash: three stable passes of 10-bit
+// digits.  One kernel reads the items once and builds the global histogram of all three digits; each pass is then a
+// single kernel: the tile (handed out by an atomic ticket) ranks its values, publishes its per-digit counts and
+// finds its digit bases by a decoupled look-back over the tiles before it -- no per-pass histogram read, no scan
+// launch.  status word (u32, one per tile and digit) = flag << 30 | count; flag 1 = tile count, 2 = inclusive prefix.
+constexpr int ITEM_KEY_LO = 34;                 // items are ordered (and runs are cut) by bits 34..63
+constexpr int OS_BITS = 10, OS_BINS = 1 << OS_BITS, OS_PASSES = 3;
+constexpr int OS_DPT = OS_BINS / TILE;          // digits per thread (4, consecutive)
+static_assert(OS_DPT == 4, "the one-sweep pass moves the four digits of a thread as one 16-byte word");
+constexpr int64_t OS_MAX_ITEMS = 1ll << 30;
+
+__global__ void __launch_bounds__(TILE) os_hist_kernel(const uint64_t *__restrict__ v, int64_t n, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[OS_PASSES][OS_BINS];
+    for (int i = threadIdx.x; i < OS_PASSES * OS_BINS; i += TILE) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x; i < n; i += (int64_t)gridDim.x * TILE) {
+        const uint64_t x = v[i];
+#pragma unroll
+        for (int p = 0; p < OS_PASSES; ++p) atomicAdd(&sh[p][(uint32_t)(x >> (ITEM_KEY_LO + p * OS_BITS)) & (OS_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OS_PASSES * OS_BINS; i += TILE) {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+// hist[p][d] -> exclusive prefix over d (one CTA of OS_BINS threads per pass)
+__global__ void __launch_bounds__(OS_BINS) os_base_kernel(uint32_t *hist) {
+    __shared__ uint32_t ws[OS_BINS / 32];
+    uint32_t *h = hist + blockIdx.x * OS_BINS;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t c = h[threadIdx.x];
+    const uint32_t inc = warp_incl_scan(c);
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t x = ws[lane], xi = warp_incl_scan(x);
+        ws[lane] = xi - x;
+    }
+    __syncthreads();
+    h[threadIdx.x] = inc - c + ws[w];
+}
+
+struct OsSmem {
+    uint64_t stage[SORT_TILE];
+    uint32_t gbase[OS_BINS];
+    uint16_t whist[TILE / 32][OS_BINS];
+    uint16_t dbase[OS_BINS];
+    uint32_t warp_sums[TILE / 32 + 1];
+    uint32_t tile;
+};
+__global__ void __launch_bounds__(TILE, 4) os_scatter_kernel(const uint64_t *__restrict__ v_in, int64_t n, int shift,
+                                                             const uint32_t *__restrict__ base /*[OS_BINS]*/, uint32_t *status,
+                                                             Counters *ctr, int ticket_id, uint64_t *__restrict__ v_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OsSmem &S = *reinterpret_cast<OsSmem *>(smem_raw);
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) S.tile = atomicAdd(&ctr->ticket[ticket_id], 1u);
+    for (int i = threadIdx.x; i < (TILE / 32) * OS_BINS / 2; i += TILE) reinterpret_cast<uint32_t *>(&S.whist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const int64_t tbase = (int64_t)tile * SORT_TILE, wbase = tbase + (int64_t)w * (32 * SORT_ITEMS);
+    uint64_t v[SORT_ITEMS];
+    uint16_t off[SORT_ITEMS];  // position of the value among the warp's values with the same digit (stable)
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS; ++q) {
+        const int64_t i = wbase + q * 32 + lane;
+        v[q] = i < n ? v_in[i] : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS; ++q) {
+        const bool ok = wbase + q * 32 + lane < n;
+        const uint32_t d = (uint32_t)(v[q] >> shift) & (OS_BINS - 1);
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        off[q] = 0;
+        if (ok) {
+            const unsigned peers = __match_any_sync(act, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if ((int)lane == leader) {
+                old = S.whist[w][d];
+                S.whist[w][d] = (uint16_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(peers, old, leader);
+            off[q] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // digits 4t..4t+3 of thread t: exclusive over warps, tile count -> published; tile-local start of each digit
+    const uint32_t d0 = threadIdx.x * OS_DPT;
+    uint32_t cnt[OS_DPT] = {0, 0, 0, 0};
+    for (int ww = 0; ww < TILE / 32; ++ww) {
+        uint2 x = *reinterpret_cast<uint2 *>(&S.whist[ww][d0]);
+        const uint32_t c0 = x.x & 0xffffu, c1 = x.x >> 16, c2 = x.y & 0xffffu, c3 = x.y >> 16;
+        x.x = cnt[0] | (cnt[1] << 16); x.y = cnt[2] | (cnt[3] << 16);
+        *reinterpret_cast<uint2 *>(&S.whist[ww][d0]) = x;
+        cnt[0] += c0; cnt[1] += c1; cnt[2] += c2; cnt[3] += c3;
+    }
+    constexpr uint32_t VAL = (1u << 30) - 1;
+    uint32_t *mine = status + (uint64_t)tile * OS_BINS + d0;
+    {
+        const uint32_t f = tile == 0 ? 2u << 30 : 1u << 30;
+        uint4 a{f | cnt[0], f | cnt[1], f | cnt[2], f | cnt[3]};
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(mine), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
+    }
+    {
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(cnt[0] + cnt[1] + cnt[2] + cnt[3], S.warp_sums, tot);
+        const uint32_t e0 = ex, e1 = e0 + cnt[0], e2 = e1 + cnt[1], e3 = e2 + cnt[2];
+        *reinterpret_cast<uint2 *>(&S.dbase[d0]) = uint2{e0 | (e1 << 16), e2 | (e3 << 16)};
+        for (int ww = 0; ww < TILE / 32; ++ww) {  // tile-local position = digit start + warps before + rank in warp
+            uint2 x = *reinterpret_cast<uint2 *>(&S.whist[ww][d0]);
+            x.x += e0 | (e1 << 16); x.y += e2 | (e3 << 16);  // all sums <= 4096: the halves never carry
+            *reinterpret_cast<uint2 *>(&S.whist[ww][d0]) = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS; ++q) {  // stable placement inside the tile
+        if (wbase + q * 32 + lane < n) S.stage[S.whist[w][(uint32_t)(v[q] >> shift) & (OS_BINS - 1)] + off[q]] = v[q];
+    }
+    // look-back over the tiles before this one (they hold earlier tickets, so they are resident or finished)
+    uint32_t ex[OS_DPT] = {0, 0, 0, 0};
+    if (tile > 0) {
+        unsigned open = 15;  // digits whose walk has not met an inclusive prefix yet
+        for (int64_t p = (int64_t)tile - 1; open; --p) {
+            const uint32_t *src = status + (uint64_t)p * OS_BINS + d0;
+            uint32_t s[OS_DPT];
+            bool ready;
+            do {
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]) : "l"(src) : "memory");
+                ready = true;
+#pragma unroll
+                for (int k = 0; k < OS_DPT; ++k) ready = ready && (!((open >> k) & 1) || (s[k] >> 30) != 0);
+            } while (!ready);
+#pragma unroll
+            for (int k = 0; k < OS_DPT; ++k)
+                if ((open >> k) & 1) {
+                    ex[k] += s[k] & VAL;
+                    if ((s[k] >> 30) == 2) open &= ~(1u << k);
+                }
+        }
+        const uint32_t f = 2u << 30;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(mine), "r"(f | (ex[0] + cnt[0])), "r"(f | (ex[1] + cnt[1])),
+                     "r"(f | (ex[2] + cnt[2])), "r"(f | (ex[3] + cnt[3])) : "memory");
+    }
+    {
+        const uint4 b = *reinterpret_cast<const uint4 *>(base + d0);
+        *reinterpret_cast<uint4 *>(&S.gbase[d0]) = uint4{b.x + ex[0], b.y + ex[1], b.z + ex[2], b.w + ex[3]};
+    }
+    __syncthreads();
+    const uint32_t cnt_tile = (uint32_t)min((int64_t)SORT_TILE, n - tbase);
+    for (uint32_t i = threadIdx.x; i < cnt_tile; i += TILE) {
+        const uint64_t x = S.stage[i];
+        const uint32_t d = (uint32_t)(x >> shift) & (OS_BINS - 1);
+        v_out[S.gbase[d] + (i - S.dbase[d])] = x;
+    }
+}
+
 // ------------------------------------------------------------------ 3. runs of equal sort key
 // run_start[r] = first sorted item of run r, run_wpre[r] = candidates (takes of parents + buy records)
 // in the runs before r.  Two look-back chains (run count, weight) walked by two warps at once.
@@ -308,13 +469,13 @@ __global__ void __launch_bounds__(TILE) m2_runs_kernel(const uint64_t *__restric
     const uint32_t tile = s_tile;
     const int64_t b0 = ((int64_t)tile * TILE + threadIdx.x) * RUN_ITEMS;
     uint32_t flags = 0, w[RUN_ITEMS], fsum = 0, wsum = 0;
-    uint64_t prev = (b0 > 0 && b0 - 1 < n_items) ? iv[b0 - 1] >> 32 : 0;
+    uint64_t prev = (b0 > 0 && b0 - 1 < n_items) ? iv[b0 - 1] >> ITEM_KEY_LO : 0;
 #pragma unroll
     for (int q = 0; q < RUN_ITEMS; ++q) {
         const int64_t i = b0 + q;
         w[q] = 0;
         if (i < n_items) {
-            const uint64_t v = iv[i], k = v >> 32;
+            const uint64_t v = iv[i], k = v >> ITEM_KEY_LO;
             if (i == 0 || k != prev) { flags |= 1u << q; ++fsum; }
             prev = k;
             const uint32_t id = (uint32_t)v;

@@ -88,7 +88,7 @@ struct spl_ctx {
     int identity = IDENT_KEY;  // visited-table identity of the speedrun solver (spl_set_identity)  // levels left before the dictionary path is tried again after a miss
     DevBuf status[3];
     // scratch
-    DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2;
+    DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2, os_hist;
     DevBuf pool_front, pool_uniq, pool_grank;  // frontier buffers lent to the active solver
     DevBuf rcfg, rcand, rvmask, ridx64, rtmp;  // realistic mode scratch
     RBucket *rtable = nullptr;  // realistic mode: exact-key visited table (64-byte buckets, one state each)
@@ -265,6 +265,7 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(m2_group_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offsetof(WarpSmem, bsort)));
     CKC(cudaFuncSetAttribute(m2_group_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
     CKC(cudaFuncSetAttribute(m2_group_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
+    CKC(cudaFuncSetAttribute(os_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem)));
     CKC(cudaFuncSetAttribute(gs_buys_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RouteSmem)));
     CKC(cudaMalloc(&c->d_dict2, sizeof(ScoreDict)));
     CKC(cudaMalloc(&c->d_dest, 2 * MAX_RANKS * 8));
@@ -1162,8 +1163,32 @@ static int ensure_nodes(spl_ctx *c, uint64_t need, cudaStream_t st) {
 }
 
 // stable LSD sort of packed 64-bit items on bits [lo_bit, 64): result in c->y[*cur]
-static int sort_items(spl_ctx *c, int64_t n_items, int lo_bit, int *cur, cudaStream_t st) {
+// Stable sort of the round's packed items by their key bits ITEM_KEY_LO..63: three one-sweep passes of 10-bit digits
+// (rounds below 2^30 items), else 8-bit LSD passes with per-pass histogram + scan.
+static int sort_items(spl_ctx *c, int64_t n_items, int *cur, cudaStream_t st) {
     const unsigned snt = nblk(n_items, SORT_TILE);
+    static const bool no_onesweep = getenv("SPL_NO_ONESWEEP") != nullptr;
+    if (n_items > 1 && n_items < OS_MAX_ITEMS && !no_onesweep) {
+        const size_t status_bytes = (size_t)snt * OS_BINS * 4;
+        CK(c, c->os_hist.ensure(OS_PASSES * OS_BINS * 4, 0, st));
+        CK(c, c->matrix.ensure(status_bytes, 0, st));
+        CK(c, cudaMemsetAsync(c->os_hist.p, 0, OS_PASSES * OS_BINS * 4, st));
+        os_hist_kernel<<<std::min<unsigned>(148 * 8, nblk(n_items)), TILE, 0, st>>>(c->y[*cur].as<uint64_t>(), n_items, c->os_hist.as<uint32_t>());
+        os_base_kernel<<<OS_PASSES, OS_BINS, 0, st>>>(c->os_hist.as<uint32_t>());
+        c->launches += 2;
+        for (int p = 0; p < OS_PASSES; ++p) {
+            CK(c, cudaMemsetAsync(c->matrix.p, 0, status_bytes, st));
+            CKS(c, reset_ticket(c, 2, st));
+            os_scatter_kernel<<<snt, TILE, sizeof(OsSmem), st>>>(c->y[*cur].as<uint64_t>(), n_items, ITEM_KEY_LO + p * OS_BITS,
+                                                                 c->os_hist.as<uint32_t>() + p * OS_BINS, c->matrix.as<uint32_t>(), c->d_ctr, 2,
+                                                                 c->y[*cur ^ 1].as<uint64_t>());
+            ++c->launches;
+            CK(c, cudaGetLastError());
+            *cur ^= 1;
+        }
+        return SPL_OK;
+    }
+    const int lo_bit = ITEM_KEY_LO;
     const size_t msz = (size_t)SORT_BINS * snt;
     CK(c, c->matrix.ensure(msz * 4, 0, st));
     CK(c, c->matrix2.ensure(msz * 4, 0, st));
@@ -1227,7 +1252,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         CK(c, cudaEventRecord(c->ev[7], st));
         // ---- 2. stable LSD sort of the items by the high half of their card-set hash
         int cur = 0;
-        CKS(c, sort_items(c, n_items, 32, &cur, st));
+        CKS(c, sort_items(c, n_items, &cur, st));
         // ---- 3. runs of equal key + candidate-weight prefix
         const unsigned rt = nblk(n_items, TILE * RUN_ITEMS);
         CK(c, c->run_start.ensure((size_t)n_items * 4 + 8, 0, st));
@@ -1541,7 +1566,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     const bool dbg = getenv("SPL_DEBUG") != nullptr;
     CK(c, cudaEventRecord(c->ev[0], st));
     int cur = 0;
-    CKS(c, sort_items(c, n_items, 32, &cur, st));
+    CKS(c, sort_items(c, n_items, &cur, st));
     const unsigned rt = nblk(n_items, TILE * RUN_ITEMS);
     CK(c, c->run_start.ensure((size_t)n_items * 4 + 8, 0, st));
     CK(c, c->run_wpre.ensure((size_t)n_items * 4 + 8, 0, st));
