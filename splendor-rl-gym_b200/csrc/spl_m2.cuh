@@ -38,6 +38,7 @@ constexpr int NUM_CLS = 8;             // run classes; used: CLS_WARP (one warp 
 constexpr int CLS_WARP = 6, CLS_CTA = 7;
 constexpr int M2_WARPS = TILE / 32;
 constexpr int BIG_DONE = 16;           // distinct card sets one equal-hash run of the CTA kernel may hold
+constexpr int BIG_AT_BITS = 24;        // item offset inside a run, packed under the arrival index in the CTA kernel's table
 
 // card mask of a key as two words (90 bits)
 __device__ __host__ __forceinline__ void mask_words(uint64_t lo, uint64_t hi, uint64_t &m0, uint64_t &m1) {
@@ -526,6 +527,7 @@ struct GroupArgs {
     const uint32_t *takes_idx;
     const uint16_t *takes_edges;
     const uint16_t *gemrank;
+    const uint16_t *rankgems;      // inverse of gemrank: [GEM_STATES] gem hand of a dense index
     uint64_t *nodes;
     uint64_t nn;
     // Output: winners (any order; link carries the arrival order) and their order-preserving score keys, appended
@@ -999,10 +1001,11 @@ struct BigSmem {
     uint64_t node, base, m0, m1;
 };
 
-// enumerate the candidates of the items of run [s, e) whose card set is (M0, M1): f(gems, rank, t, lo, hi, aux)
+// enumerate the candidates of the items of run [s, e) whose card set is (M0, M1): f(rank, t, item offset in the run)
+// (spreading the takes of a batch of items evenly over the threads was measured: slower, the extra barriers cost more
+// than the serial take loops)
 template <class F>
-__device__ __forceinline__ void big_enumerate(const GroupArgs &A, BigSmem &S, uint32_t s, uint32_t e, uint64_t M0, uint64_t M1,
-                                              bool note_others, F &&f) {
+__device__ __forceinline__ void big_enumerate(const GroupArgs &A, BigSmem &S, uint32_t s, uint32_t e, uint64_t M0, uint64_t M1, F &&f) {
     for (uint32_t i = s + threadIdx.x; i < e; i += TILE) {
         const uint32_t id = item_id(A, i);
         Rec it;
@@ -1010,27 +1013,21 @@ __device__ __forceinline__ void big_enumerate(const GroupArgs &A, BigSmem &S, ui
         if (isP) ld_rec(A.front + id, it); else ld_rec(A.brec + (id - A.np), it);
         uint64_t m0, m1;
         mask_words(it.lo, it.hi, m0, m1);
-        if (m0 != M0 || m1 != M1) {
-            if (note_others) {  // another card set with the same 32-bit sort key: remember the first one not done yet
-                bool done = false;
-                for (uint32_t d = 0; d < S.n_done; ++d) done |= (S.done0[d] == m0 && S.done1[d] == m1);
-                if (!done) atomicMin(&S.next, i);
-            }
+        if (m0 != M0 || m1 != M1) {  // another card set with the same sort key: remember the first one not done yet
+            bool done = false;
+            for (uint32_t d = 0; d < S.n_done; ++d) done |= (S.done0[d] == m0 && S.done1[d] == m1);
+            if (!done) atomicMin(&S.next, i);
             continue;
         }
         if (!isP) {
-            const uint32_t g = (uint32_t)(it.lo & GEM_MASK);
-            f(g, (uint32_t)__ldg(A.gemrank + g), it.link, it.lo, it.hi, it.aux);
+            f((uint32_t)__ldg(A.gemrank + (uint32_t)(it.lo & GEM_MASK)), it.link, i - s);
         } else {
             uint64_t bl, bh;
             uint32_t nb, tk;
             derive_parent(S.tabs, A.takes_idx, it.lo, it.hi, it.aux, bl, bh, nb, tk);
             const uint64_t tb = (parent_rank(A, id) << 8) | nb;
             const uint32_t ntk = tk & 0xff;
-            for (uint32_t q = 0; q < ntk; ++q) {
-                const uint32_t g = __ldg(A.takes_edges + (tk >> 8) + q);
-                f(g, (uint32_t)__ldg(A.gemrank + g), tb + q, (it.lo & ~GEM_MASK) | g, it.hi, it.aux);
-            }
+            for (uint32_t q = 0; q < ntk; ++q) f((uint32_t)__ldg(A.gemrank + __ldg(A.takes_edges + (tk >> 8) + q)), tb + q, i - s);
         }
     }
 }
@@ -1043,9 +1040,14 @@ __global__ void __launch_bounds__(TILE) m2_group_big_kernel(GroupArgs A) {
     const uint32_t n_big = A.ctr->n_cls[CLS_CTA];
     uint32_t n_fresh = 0;
     uint64_t kmin = ~0ull, kmax = 0;
+    uint32_t ticket = 0;  // (thread 0) the next job, fetched while the current one is processed
+    if (tid == 0) ticket = atomicAdd(&A.ctr->ticket[3], 1u);
     for (;;) {
         __syncthreads();
-        if (tid == 0) S.job = atomicAdd(&A.ctr->ticket[3], 1u);
+        if (tid == 0) {
+            S.job = ticket;
+            if (ticket < n_big) ticket = atomicAdd(&A.ctr->ticket[3], 1u);
+        }
         __syncthreads();
         if (S.job >= n_big) break;
         const uint32_t r = A.cls_list[CLS_CTA][S.job];
@@ -1071,34 +1073,43 @@ __global__ void __launch_bounds__(TILE) m2_group_big_kernel(GroupArgs A) {
             for (int i = tid; i < GEM_STATES; i += TILE) S.tbl[i] = ~0ull;
             if (tid < NODE_BM_WORDS) S.bm[tid] = S.fresh ? 0ull : N[2 + tid];
             __syncthreads();
-            // pass 0: first arrival per gem hand among the candidates not in the visited set
-            big_enumerate(A, S, s, e, M0, M1, true, [&](uint32_t, uint32_t rk, uint64_t t, uint64_t, uint64_t, uint64_t) {
-                if (!((S.bm[rk >> 6] >> (rk & 63)) & 1)) atomicMin(reinterpret_cast<unsigned long long *>(&S.tbl[rk]), (unsigned long long)t);
+            // pass 0: first arrival per gem hand among the candidates not in the visited set; the table word is
+            // arrival index << 24 | offset of the producing item in the run (a run holds < 2^24 items: at most
+            // BIG_DONE card sets of <= 2898 parents and their predecessors' buy records; arrival indices are < 2^40)
+            big_enumerate(A, S, s, e, M0, M1, [&](uint32_t rk, uint64_t t, uint32_t at) {
+                if (!((S.bm[rk >> 6] >> (rk & 63)) & 1))
+                    atomicMin(reinterpret_cast<unsigned long long *>(&S.tbl[rk]), (unsigned long long)((t << BIG_AT_BITS) | at));
             });
             __syncthreads();
-            // pass 1a: winners per thread -> output offsets
+            // pass 1: the occupied table entries are the winners; each is rebuilt from its producing item
             uint32_t mywins = 0;
-            big_enumerate(A, S, s, e, M0, M1, false, [&](uint32_t, uint32_t rk, uint64_t t, uint64_t, uint64_t, uint64_t) {
-                mywins += S.tbl[rk] == t;
-            });
+            for (uint32_t rk = tid; rk < GEM_STATES; rk += TILE) mywins += S.tbl[rk] != ~0ull;
             uint32_t tot;
             const uint32_t ex = block_excl_scan(mywins, S.warp_sums, tot);
             if (tid == 0) S.base = A.out_base + atomicAdd(&A.ctr->n_emitted, (unsigned long long)tot);
             __syncthreads();
-            // pass 1b: emit
             uint64_t pos = S.base + ex;
-            big_enumerate(A, S, s, e, M0, M1, false, [&](uint32_t, uint32_t rk, uint64_t t, uint64_t lo, uint64_t hi, uint64_t aux) {
-                if (S.tbl[rk] != t) return;
-                Rec o{lo, hi, aux, t};
+            for (uint32_t rk = tid; rk < GEM_STATES; rk += TILE) {
+                const uint64_t v = S.tbl[rk];
+                if (v == ~0ull) continue;
+                const uint32_t id = item_id(A, s + (uint32_t)(v & ((1u << BIG_AT_BITS) - 1)));
+                Rec o;
+                if (id < A.np) {  // a gem take of that parent: same cards, saved, points and bonus
+                    ld_rec(A.front + id, o);
+                    o.lo = (o.lo & ~GEM_MASK) | __ldg(A.rankgems + rk);
+                } else {
+                    ld_rec(A.brec + (id - A.np), o);
+                }
+                o.link = v >> BIG_AT_BITS;
                 st_rec(A.out + pos, o);
                 if (A.out_sk) {
-                    const uint64_t k = flip_f64((uint64_t)__double_as_longlong(score_state(A.h, A.noise_mode, lo, hi & HI_KEY_MASK, aux, A.L)));
+                    const uint64_t k = flip_f64((uint64_t)__double_as_longlong(score_state(A.h, A.noise_mode, o.lo, o.hi & HI_KEY_MASK, o.aux, A.L)));
                     A.out_sk[pos] = k;
                     kmin = min(kmin, k); kmax = max(kmax, k);
                 }
                 ++pos;
                 atomicOr(reinterpret_cast<unsigned long long *>(&S.bm[rk >> 6]), 1ull << (rk & 63));
-            });
+            }
             __syncthreads();
             if (tid < NODE_BM_WORDS) N[2 + tid] = S.bm[tid];
             if (tid == 0) {

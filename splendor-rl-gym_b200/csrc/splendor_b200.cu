@@ -70,6 +70,7 @@ struct spl_ctx {
     uint64_t *nodes = nullptr;
     uint64_t nn = 0, node_occ = 0, max_node_bytes = 0;
     uint16_t *d_gemrank = nullptr;
+    uint16_t *d_rankgems = nullptr;   // inverse of d_gemrank
     DevBuf brec, ntk8, boff2, run_start, run_wpre, cls_list;
     int tie_link_top = 0;  // > 0: the beam cut breaks score ties on the records' link words (arrival order)
     // constant tables
@@ -250,6 +251,13 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     c->luts.small = c->d_lut + T.lut_pts.size() + T.lut_saved.size();
     CKC(cudaMalloc(&c->d_gemrank, T.gemrank.size() * 2));
     CKC(cudaMemcpy(c->d_gemrank, T.gemrank.data(), T.gemrank.size() * 2, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint16_t> inv(GEM_STATES, 0);
+        for (size_t g = 0; g < T.gemrank.size(); ++g)
+            if (T.gemrank[g] != 0xFFFF) inv[T.gemrank[g]] = (uint16_t)g;
+        CKC(cudaMalloc(&c->d_rankgems, inv.size() * 2));
+        CKC(cudaMemcpy(c->d_rankgems, inv.data(), inv.size() * 2, cudaMemcpyHostToDevice));
+    }
     CKC(cudaMalloc(&c->d_ctr, sizeof(Counters)));
     CKC(cudaMallocHost(&c->h_ctr, sizeof(Counters)));
     CKC(cudaMalloc(&c->d_sel, sizeof(SelState)));
@@ -298,7 +306,7 @@ int32_t spl_destroy(spl_ctx *c) {
     cudaDeviceSynchronize();
     cudaFree(c->table); cudaFree(c->d_tabs); cudaFree(c->d_takes_idx); cudaFree(c->d_takes_edges);
     cudaFree(c->d_lut); cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr); cudaFree(c->d_sel); cudaFreeHost(c->h_sel);
-    cudaFree(c->rtable); cudaFree(c->d_hist); cudaFree(c->d_dict); cudaFree(c->d_dict2); cudaFree(c->d_dest); cudaFree(c->nodes); cudaFree(c->d_gemrank);
+    cudaFree(c->rtable); cudaFree(c->d_hist); cudaFree(c->d_dict); cudaFree(c->d_dict2); cudaFree(c->d_dest); cudaFree(c->nodes); cudaFree(c->d_gemrank); cudaFree(c->d_rankgems);
     for (auto *b : c->pool_links) delete b;
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     delete c;
@@ -1278,7 +1286,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         A.front = front + p0; A.brec = c->brec.as<Rec>(); A.iv = c->y[cur].as<uint64_t>();
         A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
         A.np = (uint32_t)np; A.rank_base = p0; A.grank = nullptr; A.unordered = 0; A.warp_max = BIG_W; A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges;
-        A.gemrank = c->d_gemrank; A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>();
+        A.gemrank = c->d_gemrank; A.rankgems = c->d_rankgems; A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>();
         A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)n_slots;
         for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
         A.cls_list[CLS_WARP] = c->cls_list.as<uint32_t>();
@@ -1291,7 +1299,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         m2_group_warp_kernel<false><<<148 * 4, TILE, offsetof(WarpSmem, bsort), st>>>(A);
         CK(c, cudaEventRecord(c->ev[5], st));
         CK(c, cudaEventRecord(c->ev[6], st));
-        m2_group_big_kernel<<<148 * 4, TILE, sizeof(BigSmem), st>>>(A);
+        m2_group_big_kernel<<<148 * 5, TILE, sizeof(BigSmem), st>>>(A);
         c->launches += 3;
         CK(c, cudaGetLastError());
         CK(c, cudaEventRecord(c->ev[3], st));
@@ -1588,7 +1596,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     A.run_start = c->run_start.as<uint32_t>(); A.run_wpre = c->run_wpre.as<uint32_t>();
     A.np = (uint32_t)np; A.rank_base = 0; A.grank = s->grank.as<uint64_t>() + s->r_p0; A.unordered = 1;
     A.warp_max = std::min<uint32_t>(BIG_W, BSORT_MAX);  // the warp kernel sorts at most BSORT_MAX records of a run itself
-    A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges; A.gemrank = c->d_gemrank;
+    A.tabs = c->d_tabs; A.takes_idx = c->d_takes_idx; A.takes_edges = c->d_takes_edges; A.gemrank = c->d_gemrank; A.rankgems = c->d_rankgems;
     A.nodes = c->nodes; A.nn = c->nn; A.out = s->uniq.as<Rec>(); A.out_sk = c->sk.as<uint64_t>(); A.out_base = (uint64_t)s->n_uniq;
     for (int k = 0; k < NUM_CLS; ++k) A.cls_list[k] = nullptr;
     A.cls_list[CLS_WARP] = c->cls_list.as<uint32_t>();
@@ -1599,7 +1607,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     CK(c, cudaEventRecord(c->ev[2], st));
     m2_group_warp_kernel<true><<<148 * 4, TILE, sizeof(WarpSmem), st>>>(A);
     CK(c, cudaEventRecord(c->ev[3], st));
-    m2_group_big_kernel<<<148 * 4, TILE, sizeof(BigSmem), st>>>(A);
+    m2_group_big_kernel<<<148 * 5, TILE, sizeof(BigSmem), st>>>(A);
     CK(c, cudaEventRecord(c->ev[4], st));
     c->launches += 3;
     CK(c, cudaGetLastError());

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_baseline_sizes.py -m gpu -q -x -k "not beam_3m" > gpurun_out/r2ac_pytest.log 2>&1
-tail -3 gpurun_out/r2ac_pytest.log
-SPL_DEBUG=1 QUIET=1 timeout 300 python tools/explore.py --beam 30000000 --reps 2 > gpurun_out/r2ac_debug_30m.log 2>&1; grep -E "rep|SUMMARY" gpurun_out/r2ac_debug_30m.log | tail -3
-grep -E "grouped\] L1[34]" gpurun_out/r2ac_debug_30m.log | tail -4 | cut -c150-400
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_baseline_sizes.py -m gpu -q -x -k "not beam_3m" > gpurun_out/r2ag_pytest.log 2>&1
+tail -3 gpurun_out/r2ag_pytest.log
+SPL_DEBUG=1 QUIET=1 timeout 300 python tools/explore.py --beam 30000000 --reps 2 > gpurun_out/r2ag_debug_30m.log 2>&1; grep -E "rep|SUMMARY" gpurun_out/r2ag_debug_30m.log | tail -3
+grep -E "grouped\] L1[34]" gpurun_out/r2ag_debug_30m.log | tail -4 | cut -c150-400
