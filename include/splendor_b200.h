@@ -139,6 +139,14 @@ int32_t spl_reset_visited(spl_ctx *ctx, void *stream);
  * realistic mode keep their own identities).  SURVEY.md 8(f).3. */
 int32_t spl_set_identity(spl_ctx *ctx, int32_t identity);
 
+/* Parent links of the kept states (`trail[state] = parent`, src/solver.py:449; walked back from the goal at
+ * :459-464) are held as one 8-byte column per level.  Solvers created afterwards on this context keep at most
+ * `device_bytes` of them in HBM (0 = no limit, the default): past that the oldest levels move to pinned host memory
+ * and spl_solver_path / spl_gs_link_at read them there.  SURVEY.md 8(f).2.  spl_spilled_bytes: bytes moved so far
+ * (they are also counted by spl_transfer_bytes). */
+int32_t spl_set_link_budget(spl_ctx *ctx, uint64_t device_bytes);
+int32_t spl_spilled_bytes(spl_ctx *ctx, int64_t *n_host);
+
 /* out[i] = hash((cards, gems)) of keys[i] as CPython computes it (unsigned 64-bit view); device buffers.
  * Replaces: State.__init__'s `self.hash = hash((self.cards, self.gems))`, src/solver.py:316. */
 int32_t spl_pyhash(spl_ctx *ctx, const spl_key *keys_dev, int64_t n, uint64_t *out_dev, void *stream);

@@ -58,6 +58,8 @@ def _load():
         'spl_destroy': (i32, [vp]),
         'spl_reset_visited': (i32, [vp, vp]),
         'spl_set_identity': (i32, [vp, i32]),
+        'spl_set_link_budget': (i32, [vp, u64]),
+        'spl_spilled_bytes': (i32, [vp, C.POINTER(i64)]),
         'spl_pyhash': (i32, [vp, vp, i64, vp, vp]),
         'spl_visited_count': (i32, [vp, C.POINTER(i64)]),
         'spl_launch_count': (i32, [vp, C.POINTER(i64)]),

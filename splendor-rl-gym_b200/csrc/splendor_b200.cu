@@ -69,6 +69,8 @@ struct spl_ctx {
     // card-set node table of the grouped level (spl_m2.cuh)
     uint64_t *nodes = nullptr;
     uint64_t nn = 0, node_occ = 0, max_node_bytes = 0;
+    uint64_t link_budget = 0;          // device bytes a solver may hold in parent-link columns before it spills (0: no limit)
+    uint64_t spilled_bytes = 0;        // link-column bytes moved to pinned host memory so far
     uint16_t *d_gemrank = nullptr;
     uint16_t *d_rankgems = nullptr;   // inverse of d_gemrank
     DevBuf brec, ntk8, boff2, run_start, run_wpre, cls_list;
@@ -334,6 +336,19 @@ int32_t spl_set_identity(spl_ctx *c, int32_t identity) {
     if (identity != SPL_IDENT_KEY && identity != SPL_IDENT_PYHASH) return fail(c, SPL_E_INVALID, "spl_set_identity: unknown identity %d", identity);
     NO_LIVE_SOLVER(c, "spl_set_identity");
     c->identity = identity == SPL_IDENT_PYHASH ? IDENT_PYHASH : IDENT_KEY;
+    return SPL_OK;
+}
+
+int32_t spl_set_link_budget(spl_ctx *c, uint64_t device_bytes) {
+    if (!c) return SPL_E_INVALID;
+    NO_LIVE_SOLVER(c, "spl_set_link_budget");
+    c->link_budget = device_bytes;
+    return SPL_OK;
+}
+
+int32_t spl_spilled_bytes(spl_ctx *c, int64_t *n_host) {
+    if (!c || !n_host) return SPL_E_INVALID;
+    *n_host = (int64_t)c->spilled_bytes;
     return SPL_OK;
 }
 
@@ -1097,6 +1112,43 @@ int32_t spl_count_less(spl_ctx *c, int32_t words, int32_t inclusive, const uint6
 }  // extern "C"
 
 // ------------------------------------------------------------------ fused solver
+// Parent-link columns (src/solver.py:459-464 walks them back from the goal): one per level, 8 B per queue entry.  Past
+// spl_set_link_budget's device budget the oldest columns move to pinned host memory; the path walk
+// reads a spilled column in place.
+struct LinkCols {
+    std::vector<DevBuf *> dev;      // per level (pool-owned buffers)
+    std::vector<uint64_t *> host;   // per level: pinned copy once spilled, else nullptr
+    std::vector<int64_t> n;         // per level: entries
+    size_t next_spill = 0;          // levels below this one are on the host
+    ~LinkCols() { for (uint64_t *h : host) if (h) cudaFreeHost(h); }
+    void push(DevBuf *b, int64_t cnt) { dev.push_back(b); host.push_back(nullptr); n.push_back(cnt); }
+    // one entry, wherever the column lives
+    cudaError_t read(int level, int64_t i, uint64_t *out) const {
+        if (host[level]) { *out = host[level][i]; return cudaSuccess; }
+        return cudaMemcpy(out, dev[level]->as<uint64_t>() + i, 8, cudaMemcpyDeviceToHost);
+    }
+    // spill oldest-first until the device-resident columns fit `budget` bytes (the newest column stays on the device)
+    cudaError_t spill(uint64_t budget, uint64_t *moved, cudaStream_t st) {
+        if (!budget) return cudaSuccess;
+        uint64_t resident = 0;
+        for (size_t l = next_spill; l < dev.size(); ++l) resident += (uint64_t)n[l] * 8;
+        while (resident > budget && next_spill + 1 < dev.size()) {
+            const size_t l = next_spill++;
+            const size_t bytes = (size_t)n[l] * 8;
+            if (!bytes) continue;
+            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&host[l]), bytes);
+            if (e != cudaSuccess) { host[l] = nullptr; return e; }
+            e = cudaMemcpyAsync(host[l], dev[l]->p, bytes, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            dev[l]->release();  // the memory goes back to the device, not to the column pool
+            resident -= bytes;
+            *moved += bytes;
+        }
+        return cudaSuccess;
+    }
+};
+
 struct spl_solver {
     spl_ctx *c = nullptr;
     int goal = 15, use_h = 0, heuristic = 0, tie = 0, noise = 0, keep_links = 1;
@@ -1113,13 +1165,12 @@ struct spl_solver {
     int level = 0;
     bool ended = false;
     int64_t goal_rank = -1;
-    std::vector<DevBuf *> links;   // per level: link column of the queue (device, 8 B per state)
-    std::vector<int64_t> level_n;
+    LinkCols links;                // per level: link column of the queue
     ~spl_solver() {
         if (c->active == this) c->active = nullptr;
         c->pool_front.swap(front);
         c->pool_uniq.swap(uniq);
-        for (auto *b : links) c->pool_links.push_back(b);
+        for (auto *b : links.dev) c->pool_links.push_back(b);
     }
 };
 
@@ -1128,8 +1179,7 @@ static int save_links(spl_solver *s, cudaStream_t st) {
     DevBuf *b;
     if (c->pool_links.empty()) b = new DevBuf();
     else { b = c->pool_links.back(); c->pool_links.pop_back(); }
-    s->links.push_back(b);
-    s->level_n.push_back(s->n_front);
+    s->links.push(b, s->keep_links ? s->n_front : 0);
     if (!s->keep_links || s->n_front == 0) return SPL_OK;
     CK(c, b->ensure((size_t)s->n_front * 8, 0, st));
     if (s->realistic)
@@ -1138,6 +1188,10 @@ static int save_links(spl_solver *s, cudaStream_t st) {
         unpack_rec_kernel<<<nblk(s->n_front), TILE, 0, st>>>(s->front.as<Rec>(), s->n_front, nullptr, nullptr, b->as<uint64_t>());
     ++c->launches;
     CK(c, cudaGetLastError());
+    uint64_t moved = 0;
+    CK(c, s->links.spill(c->link_budget, &moved, st));
+    c->d2h_bytes += moved;
+    c->spilled_bytes += moved;
     return SPL_OK;
 }
 
@@ -1367,15 +1421,14 @@ struct spl_gsolver {
     // cut
     int lt = 0, cut_cur = 0;
     int64_t kept_local = 0;
-    std::vector<DevBuf *> link_cols, rank_cols;  // per level: links / global ranks of the local queue (path reconstruction)
-    std::vector<int64_t> level_n;
+    LinkCols link_cols, rank_cols;  // per level: links / global ranks of the local queue (path reconstruction)
     ~spl_gsolver() {
         if (c->active == this) c->active = nullptr;
         c->pool_front.swap(front);  // keep the big buffers for the next solve on this context
         c->pool_uniq.swap(uniq);
         c->pool_grank.swap(grank);
-        for (auto *b : link_cols) c->pool_links.push_back(b);
-        for (auto *b : rank_cols) c->pool_links.push_back(b);
+        for (auto *b : link_cols.dev) c->pool_links.push_back(b);
+        for (auto *b : rank_cols.dev) c->pool_links.push_back(b);
     }
 };
 
@@ -1384,9 +1437,8 @@ static int gs_save_links(spl_gsolver *s, cudaStream_t st) {
     DevBuf *lb, *rb;  // reuse the columns of earlier solves on this context (smallest first: the queue grows)
     if (c->pool_links.empty()) lb = new DevBuf(); else { lb = c->pool_links.back(); c->pool_links.pop_back(); }
     if (c->pool_links.empty()) rb = new DevBuf(); else { rb = c->pool_links.back(); c->pool_links.pop_back(); }
-    s->link_cols.push_back(lb);
-    s->rank_cols.push_back(rb);
-    s->level_n.push_back(s->n_local);
+    s->link_cols.push(lb, s->keep_links ? s->n_local : 0);
+    s->rank_cols.push(rb, s->keep_links ? s->n_local : 0);
     if (!s->keep_links || s->n_local == 0) return SPL_OK;
     CK(c, lb->ensure((size_t)s->n_local * 8, 0, st));
     CK(c, rb->ensure((size_t)s->n_local * 8, 0, st));
@@ -1394,6 +1446,11 @@ static int gs_save_links(spl_gsolver *s, cudaStream_t st) {
     ++c->launches;
     CK(c, cudaMemcpyAsync(rb->p, s->grank.p, (size_t)s->n_local * 8, cudaMemcpyDeviceToDevice, st));
     CK(c, cudaGetLastError());
+    uint64_t moved = 0;  // the two columns share the budget
+    CK(c, s->link_cols.spill(c->link_budget / 2, &moved, st));
+    CK(c, s->rank_cols.spill(c->link_budget / 2, &moved, st));
+    c->d2h_bytes += moved;
+    c->spilled_bytes += moved;
     return SPL_OK;
 }
 
@@ -1892,26 +1949,25 @@ int32_t spl_gs_frontier(spl_gsolver *s, const void **recs_dev, const uint64_t **
 
 // link (parent rank << 8 | ordinal) of the state with global rank `grank` in the queue of `level`, if this rank holds it
 int32_t spl_gs_link_at(spl_gsolver *s, int32_t level, int64_t grank, int32_t *found_host, uint64_t *link_host) {
-    if (!s || !found_host || !link_host || level < 0 || level >= (int)s->rank_cols.size()) return SPL_E_INVALID;
+    if (!s || !found_host || !link_host || level < 0 || level >= (int)s->rank_cols.dev.size()) return SPL_E_INVALID;
     spl_ctx *c = s->c;
     if (!s->keep_links) return fail(c, SPL_E_STATE, "spl_gs_link_at: solver was created with keep_links = 0");
     CK(c, enter_device(c));
     *found_host = 0;
     *link_host = 0;
-    const int64_t n = s->level_n[level];
-    const uint64_t *rk = s->rank_cols[level]->as<uint64_t>();
+    const int64_t n = s->rank_cols.n[level];
     int64_t lo = 0, hi = n;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
         uint64_t v = 0;
-        CK(c, cudaMemcpy(&v, rk + mid, 8, cudaMemcpyDeviceToHost));
+        CK(c, s->rank_cols.read(level, mid, &v));
         if ((int64_t)v < grank) lo = mid + 1; else hi = mid;
     }
     if (lo < n) {
         uint64_t v = 0;
-        CK(c, cudaMemcpy(&v, rk + lo, 8, cudaMemcpyDeviceToHost));
+        CK(c, s->rank_cols.read(level, lo, &v));
         if ((int64_t)v == grank) {
-            CK(c, cudaMemcpy(link_host, s->link_cols[level]->as<uint64_t>() + lo, 8, cudaMemcpyDeviceToHost));
+            CK(c, s->link_cols.read(level, lo, link_host));
             *found_host = 1;
         }
     }
@@ -2543,8 +2599,8 @@ int32_t spl_solver_path(spl_solver *s, int64_t *ranks, int32_t *ordinals, int32_
         ranks[l] = r;
         if (l > 0) {
             uint64_t link = 0;
-            CK(c, cudaMemcpy(&link, s->links[l]->as<uint64_t>() + r, 8, cudaMemcpyDeviceToHost));
-            c->d2h_bytes += 8;
+            CK(c, s->links.read(l, r, &link));
+            if (!s->links.host[l]) c->d2h_bytes += 8;
             ordinals[l - 1] = (int32_t)(link & 0xff);
             r = (int64_t)(link >> 8);
         }

@@ -173,6 +173,16 @@ class Engine:
         own State.hash = hash((cards, gems)) (src/solver.py:316, :335-336), collisions merge as in its dict."""
         check(lib.spl_set_identity(self._h, IDENTITY_IDS[identity]), self._h)
 
+    def set_link_budget(self, device_bytes: int = 0):
+        """Device bytes the next solvers may hold in parent-link columns (trail, src/solver.py:449, :459-464) before the
+        oldest levels spill to pinned host memory; 0 = keep everything on the device."""
+        check(lib.spl_set_link_budget(self._h, int(device_bytes)), self._h)
+
+    def spilled_bytes(self) -> int:
+        n = C.c_int64()
+        check(lib.spl_spilled_bytes(self._h, C.byref(n)), self._h)
+        return n.value
+
     def pyhash(self, keys: torch.Tensor) -> torch.Tensor:
         """hash((cards, gems)) per key (src/solver.py:316), int64 view of CPython's value"""
         out = torch.empty(keys.shape[0], dtype=torch.int64, device=self.tdev)

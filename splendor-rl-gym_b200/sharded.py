@@ -129,6 +129,15 @@ class CudaBackend:
             check(rc, self.eng._h)
             return out[:m.value]
 
+    def ident_rows(self, cand):
+        """identity='pyhash': rows whose key is (hash((cards, gems)), 0) -- the reference's own State.hash
+        (src/solver.py:316, :335-336) -- so that routing and the owner's visited set work on that value"""
+        m = cand.shape[0]
+        out = torch.zeros((max(m, 1), 4), dtype=torch.int64, device=self.device)
+        if m:
+            out[:m, 0] = self.eng.pyhash(cand[:, :2].contiguous())
+        return out[:m]
+
     def route_keys(self, cand, world):
         """keys of the candidates grouped by owner rank (arrival order inside a group) + per-owner counts"""
         m = cand.shape[0]
@@ -244,8 +253,11 @@ class ShardedSolver:
 
     def __init__(self, backend, comm: Comm, root_key: int, root_aux: int, goal_pts: int, use_heuristic: bool,
                  heuristic: str, beam_width: int, tie: str = 'stable', noise: str = 'const',
-                 block_parents: int = 1 << 22, keep_links: bool = True):
+                 block_parents: int = 1 << 22, keep_links: bool = True, identity: str = 'key'):
+        if identity not in ('key', 'pyhash'):
+            raise ValueError(f'unknown identity {identity!r}')
         self.b, self.comm = backend, comm
+        self.identity = identity
         self.goal, self.use_h, self.h, self.beam, self.tie, self.noise = goal_pts, use_heuristic, heuristic, beam_width, tie, noise
         self.C = int(block_parents)
         self.keep_links = keep_links
@@ -260,7 +272,7 @@ class ShardedSolver:
         # the root is block 0 (rank 0); its key is registered in the visited set of its owner
         self.front = root if comm.rank == 0 else root[:0]
         self.N = 1
-        send, counts = backend.route_keys(root, comm.world)
+        send, counts = backend.route_keys(self._ident(root), comm.world)
         if counts[comm.rank]:
             backend.dedup_flags(send)
         self.level = 0
@@ -274,6 +286,11 @@ class ShardedSolver:
             self.noise_source = MTNoise()
         self.links = []  # per level: local link column (block-cyclic local order)
         self._save_links()
+
+    def _ident(self, rows):
+        """what the visited set compares: the exact (cards, gems) key, or (identity='pyhash') the reference's 64-bit
+        State.hash of it -- colliding states then share an owner and merge there, first arrival wins, as in its dict"""
+        return rows if self.identity == 'key' else self.b.ident_rows(rows)
 
     # ------------------------------------------------------------------ block-cyclic layout
     def _local_count(self, n_total, g):
@@ -360,7 +377,7 @@ class ShardedSolver:
             m = cand.shape[0]
             t0 = _tick('expand', t0)
             # 3. route keys to their owners
-            send_keys, counts = b.route_keys(cand, G)
+            send_keys, counts = b.route_keys(self._ident(cand), G)
             all_counts = comm.gather_ints(*counts.tolist())  # [src, dst]
             recv_counts = all_counts[:, me]
             t0 = _tick('partition', t0)

@@ -205,14 +205,12 @@ class State:
             # one process per GPU (torchrun): every rank calls solve() collectively; the frontier is
             # sharded by key hash and each level is bit-identical to the single-GPU search
             from .sharded import Comm, CudaBackend, GroupedShardedSolver, ShardedSolver
-            if identity != 'key':
-                raise ValueError("identity='pyhash' is a single-GPU option")
-            if use_heuristic and tie_policy == 'stable' and noise == 'const':
+            if use_heuristic and tie_policy == 'stable' and noise == 'const' and identity == 'key':
                 # queue sharded by card set: gem takes never leave the GPU, only card buys are routed
                 sh = GroupedShardedSolver(eng, Comm(eng.tdev), k, a, goal_pts, heuristic_name, beam_width, noise)
-            else:  # exhaustive BFS, key ties, hash / mt noise: queue sharded by key hash
+            else:  # exhaustive BFS, key ties, hash / mt noise, pyhash identity: queue sharded by key hash
                 sh = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), k, a, goal_pts, use_heuristic, heuristic_name,
-                                   beam_width, tie_policy, noise)
+                                   beam_width, tie_policy, noise, identity=identity)
             try:
                 for info in sh.run():
                     if stats is not None:

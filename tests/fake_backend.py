@@ -57,6 +57,14 @@ class FakeBackend:
             out[:, 3] += rank_base << 8
         return out
 
+    def ident_rows(self, cand):
+        f = _u(cand)
+        rec = np.zeros(f.shape[0], oracle.STATE_DTYPE)
+        rec['lo'], rec['hi'] = f[:, 0], f[:, 1]
+        out = np.zeros((f.shape[0], 4), dtype=np.uint64)
+        out[:, 0] = oracle.pyhash(rec)
+        return torch.from_numpy(out.view(np.int64).copy())
+
     def route_keys(self, cand, world):
         perm, counts = self.owner_partition(cand[:, :2], world)
         self._perm = perm

@@ -314,14 +314,18 @@ def test_verbose_output_matches_reference_format(capsys):
 @pytest.mark.parametrize('cfg', [(255, False, 'simple', 0, 'stable', 'const', 7, 1 << 20), (255, False, 'simple', 0, 'stable', 'const', 7, 3000),
                                  (15, True, 'aggressive', 20_000, 'stable', 'const', None, 1 << 20),
                                  (15, True, 'aggressive', 20_000, 'stable', 'const', None, 4096),
-                                 (15, True, 'balanced', 20_000, 'det', 'hash', None, 5000)])
+                                 (15, True, 'balanced', 20_000, 'det', 'hash', None, 5000),
+                                 (15, True, 'aggressive', 20_000, 'stable', 'const', None, 4096, 'pyhash'),
+                                 (255, False, 'simple', 0, 'stable', 'const', 6, 3000, 'pyhash')])
 def test_sharded_solver_world1_vs_oracle(eng, cfg):
     """The sharded driver (routing, winner bytes, pass-wise select, global ranks) on a single rank, with the
     real CUDA backend, must reproduce the oracle level by level (the 2-rank logic is covered on gloo)."""
     from splendor_rl_gym_b200.sharded import Comm, CudaBackend, ShardedSolver
-    goal, use_h, hname, beam, tie, noise, max_levels, block = cfg
-    sol = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), 0, 0, goal, use_h, hname, beam, tie, noise, block_parents=block)
-    orc = oracle.Solver(goal, use_heuristic=use_h, heuristic_name=hname, beam_width=beam, policy=tie, noise=noise)
+    goal, use_h, hname, beam, tie, noise, max_levels, block = cfg[:8]
+    identity = cfg[8] if len(cfg) > 8 else 'key'  # 'pyhash': routing + visited set on the reference's State.hash (8(f).3)
+    sol = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), 0, 0, goal, use_h, hname, beam, tie, noise, block_parents=block,
+                        identity=identity)
+    orc = oracle.Solver(goal, use_heuristic=use_h, heuristic_name=hname, beam_width=beam, policy=tie, noise=noise, identity=identity)
     while True:
         gi, oi = sol.step(), orc.step()
         fields = ('frontier', 'goal_rank') if gi['ended'] else ('frontier', 'generated', 'unique', 'kept', 'goal_rank', 'visited')
@@ -365,6 +369,40 @@ def test_grouped_sharded_solver_world1_vs_oracle(eng, hname, beam, rounds):
     finally:
         sol.close()
         orc.close()
+
+
+def test_link_columns_spill_to_host_same_path(eng):
+    """spl_set_link_budget: with the per-level parent links forced out to pinned host memory the winning
+    line (src/solver.py:459-464) is the one found with every column on the device -- solver and sharded driver."""
+    from splendor_rl_gym_b200.sharded import Comm, GroupedShardedSolver
+    k, aux = S.State.newgame().record()
+
+    def lines():
+        sol = eng.solver(k, aux, 15, True, 'aggressive', 30_000, 'stable', 'const')
+        sol.run()
+        one = sol.path()
+        sol.close()
+        gs = GroupedShardedSolver(eng, Comm(eng.tdev), 0, 0, 15, 'aggressive', 30_000, 'const', round_parents=1 << 27)
+        try:
+            while not gs.step()['ended']:
+                pass
+            two = gs.path()
+        finally:
+            gs.close()
+        return one, two
+
+    base = lines()
+    before = eng.spilled_bytes()
+    eng.set_link_budget(64 << 10)
+    try:
+        spilled = lines()
+        moved = eng.spilled_bytes() - before
+    finally:
+        eng.set_link_budget(0)
+    assert moved > 3 * 8 * 30_000  # most levels of both solves left the device
+    for a, b in zip(base, spilled):
+        assert list(a[0]) == list(b[0]) and list(a[1]) == list(b[1])
+    assert list(base[0][1]) == list(base[1][1])  # and both drivers walk the same line
 
 
 def test_owner_partition_and_count_less(eng):

@@ -24,11 +24,12 @@ def _worker(rank, world, init_file, cfg, out_file):
     from splendor_rl_gym_b200.sharded import Comm, ShardedSolver
     dist.init_process_group('gloo', init_method=f'file://{init_file}', rank=rank, world_size=world)
     try:
-        goal, use_h, hname, beam, tie, noise, block = cfg
+        goal, use_h, hname, beam, tie, noise, block = cfg[:7]
+        identity = cfg[7] if len(cfg) > 7 else 'key'
         comm = Comm(torch.device('cpu'))
-        sol = ShardedSolver(FakeBackend(), comm, 0, 0, goal, use_h, hname, beam, tie, noise, block_parents=block)
+        sol = ShardedSolver(FakeBackend(), comm, 0, 0, goal, use_h, hname, beam, tie, noise, block_parents=block, identity=identity)
         orc = oracle.Solver(goal, use_heuristic=use_h, heuristic_name=hname, beam_width=beam,
-                            policy=tie, noise=noise)
+                            policy=tie, noise=noise, identity=identity)
         while True:
             gi, oi = sol.step(), orc.step()
             # in the terminating iteration the reference still expands (and then discards) the states
@@ -61,6 +62,8 @@ def _worker(rank, world, init_file, cfg, out_file):
     (2, (6, True, 'aggressive', 257, 'det', 'hash', 50)),         # beam, key tie-break
     (3, (6, True, 'simple', 100, 'stable', 'const', 16)),         # odd world size, mass ties (simple == pure noise)
     (2, (15, True, 'efficiency', 7, 'stable', 'hash', 4)),        # tiny beam: frontier dies out before the goal
+    (2, (6, True, 'balanced', 300, 'stable', 'const', 37, 'pyhash')),  # visited set keyed by the reference's State.hash
+    (2, (4, False, 'simple', 0, 'stable', 'const', 64, 'pyhash')),     # ... exhaustive BFS
 ])
 def test_sharded_matches_oracle(world, cfg):
     with tempfile.TemporaryDirectory() as d:

@@ -29,6 +29,7 @@ ap.add_argument('--slots', type=int, default=0, help='visited-table slots per ra
 ap.add_argument('--no-links', action='store_true')
 ap.add_argument('--grouped', action='store_true', help='queue sharded by card set (GroupedShardedSolver); --block = global ranks per round')
 ap.add_argument('--nodes', type=int, default=0, help='node-table slots per rank (grouped)')
+ap.add_argument('--identity', default='key', help="'pyhash': visited set keyed by the reference's State.hash (key-sharded driver)")
 a = ap.parse_args()
 
 local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -51,7 +52,7 @@ for rep in range(a.reps):
     if check and rep == 0:
         import oracle
         orc = oracle.Solver(255 if a.bfs else a.goal, use_heuristic=use_h, heuristic_name=a.heuristic, beam_width=a.beam,
-                            policy=a.tie, noise=a.noise)
+                            policy=a.tie, noise=a.noise, identity=a.identity)
     torch.cuda.synchronize()
     t0 = time.time()
     if a.grouped:
@@ -59,7 +60,7 @@ for rep in range(a.reps):
                                    keep_links=not a.no_links)
     else:
         sol = ShardedSolver(CudaBackend(eng), comm, 0, 0, 255 if a.bfs else a.goal, use_h, a.heuristic, a.beam, a.tie, a.noise,
-                            block_parents=a.block, keep_links=not a.no_links)
+                            block_parents=a.block, keep_links=not a.no_links, identity=a.identity)
     while True:
         gi = sol.step()
         if rep == 0 and not a.no_oracle:
