@@ -293,30 +293,32 @@ __global__ void __launch_bounds__(TILE, 4) psort_scatter_kernel(const uint64_t *
     }
 }
 
-// ------------------------------------------------------------------ 2b. one-sweep passes (rounds below 2^30 items)
-// The sort key of an item is the top ITEM_KEY_BITS = 30 bits of its card-set hash: three stable passes of 10-bit
-// digits.  One kernel reads the items once and builds the global histogram of all three digits; each pass is then a
-// single kernel: the tile (handed out by an atomic ticket) ranks its values, publishes its per-digit counts and
-// finds its digit bases by a decoupled look-back over the tiles before it -- no per-pass histogram read, no scan
-// launch.  status word (u32, one per tile and digit) = flag << 30 | count; flag 1 = tile count, 2 = inclusive prefix.
-constexpr int ITEM_KEY_LO = 34;                 // items are ordered (and runs are cut) by bits 34..63
-constexpr int OS_BITS = 10, OS_BINS = 1 << OS_BITS, OS_PASSES = 3;
+// ------------------------------------------------------------------ 2b. one-sweep passes (below 2^30 values)
+// Stable LSD radix sort of 64-bit values (optionally with a 32-bit payload) by 10-bit digits.  One kernel reads the
+// values once and builds the global histogram of every digit; each pass is then a single kernel: the tile (handed out
+// by an atomic ticket) ranks its values, publishes its per-digit counts and finds its digit bases by a decoupled
+// look-back over the tiles before it -- no per-pass histogram read, no scan launch.  status word (u32, one per tile
+// and digit) = flag << 30 | count; flag 1 = tile count, 2 = inclusive prefix.
+// The items of a round are ordered (and their runs are cut) by the top 30 bits of the card-set hash: three passes.
+constexpr int ITEM_KEY_LO = 34;
+constexpr int OS_BITS = 10, OS_BINS = 1 << OS_BITS, OS_MAX_PASSES = 7;
 constexpr int OS_DPT = OS_BINS / TILE;          // digits per thread (4, consecutive)
 static_assert(OS_DPT == 4, "the one-sweep pass moves the four digits of a thread as one 16-byte word");
 constexpr int64_t OS_MAX_ITEMS = 1ll << 30;
 
-__global__ void __launch_bounds__(TILE) os_hist_kernel(const uint64_t *__restrict__ v, int64_t n, uint32_t *__restrict__ hist) {
-    __shared__ uint32_t sh[OS_PASSES][OS_BINS];
-    for (int i = threadIdx.x; i < OS_PASSES * OS_BINS; i += TILE) (&sh[0][0])[i] = 0;
+// hist[p][d] += values whose digit p (bits lo_bit + 10 p ...) is d; dynamic shared memory: passes * OS_BINS words
+__global__ void __launch_bounds__(TILE) os_hist_kernel(const uint64_t *__restrict__ v, int64_t n, int lo_bit, int passes,
+                                                       uint32_t *__restrict__ hist) {
+    extern __shared__ uint32_t os_sh[];
+    for (int i = threadIdx.x; i < passes * OS_BINS; i += TILE) os_sh[i] = 0;
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x; i < n; i += (int64_t)gridDim.x * TILE) {
-        const uint64_t x = v[i];
-#pragma unroll
-        for (int p = 0; p < OS_PASSES; ++p) atomicAdd(&sh[p][(uint32_t)(x >> (ITEM_KEY_LO + p * OS_BITS)) & (OS_BINS - 1)], 1u);
+        const uint64_t x = v[i] >> lo_bit;
+        for (int p = 0; p < passes; ++p) atomicAdd(&os_sh[p * OS_BINS + ((uint32_t)(x >> (p * OS_BITS)) & (OS_BINS - 1))], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < OS_PASSES * OS_BINS; i += TILE) {
-        const uint32_t c = (&sh[0][0])[i];
+    for (int i = threadIdx.x; i < passes * OS_BINS; i += TILE) {
+        const uint32_t c = os_sh[i];
         if (c) atomicAdd(hist + i, c);
     }
 }
@@ -344,10 +346,13 @@ struct OsSmem {
     uint16_t dbase[OS_BINS];
     uint32_t warp_sums[TILE / 32 + 1];
     uint32_t tile;
+    uint32_t stage_p[SORT_TILE];  // PAIR only (last member: the value-only launch leaves it out)
 };
-__global__ void __launch_bounds__(TILE, 4) os_scatter_kernel(const uint64_t *__restrict__ v_in, int64_t n, int shift,
-                                                             const uint32_t *__restrict__ base /*[OS_BINS]*/, uint32_t *status,
-                                                             Counters *ctr, int ticket_id, uint64_t *__restrict__ v_out) {
+template <bool PAIR>
+__global__ void __launch_bounds__(TILE, PAIR ? 3 : 4) os_scatter_kernel(const uint64_t *__restrict__ v_in, const uint32_t *__restrict__ p_in,
+                                                                        int64_t n, int shift, const uint32_t *__restrict__ base /*[OS_BINS]*/,
+                                                                        uint32_t *status, Counters *ctr, int ticket_id,
+                                                                        uint64_t *__restrict__ v_out, uint32_t *__restrict__ p_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OsSmem &S = *reinterpret_cast<OsSmem *>(smem_raw);
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -357,11 +362,13 @@ __global__ void __launch_bounds__(TILE, 4) os_scatter_kernel(const uint64_t *__r
     const uint32_t tile = S.tile;
     const int64_t tbase = (int64_t)tile * SORT_TILE, wbase = tbase + (int64_t)w * (32 * SORT_ITEMS);
     uint64_t v[SORT_ITEMS];
+    uint32_t pl[PAIR ? SORT_ITEMS : 1];
     uint16_t off[SORT_ITEMS];  // position of the value among the warp's values with the same digit (stable)
 #pragma unroll
     for (int q = 0; q < SORT_ITEMS; ++q) {
         const int64_t i = wbase + q * 32 + lane;
         v[q] = i < n ? v_in[i] : 0;
+        if (PAIR) pl[q] = i < n ? p_in[i] : 0;
     }
 #pragma unroll
     for (int q = 0; q < SORT_ITEMS; ++q) {
@@ -414,7 +421,11 @@ __global__ void __launch_bounds__(TILE, 4) os_scatter_kernel(const uint64_t *__r
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < SORT_ITEMS; ++q) {  // stable placement inside the tile
-        if (wbase + q * 32 + lane < n) S.stage[S.whist[w][(uint32_t)(v[q] >> shift) & (OS_BINS - 1)] + off[q]] = v[q];
+        if (wbase + q * 32 + lane < n) {
+            const uint32_t at = S.whist[w][(uint32_t)(v[q] >> shift) & (OS_BINS - 1)] + off[q];
+            S.stage[at] = v[q];
+            if (PAIR) S.stage_p[at] = pl[q];
+        }
     }
     // look-back over the tiles before this one (they hold earlier tickets, so they are resident or finished)
     uint32_t ex[OS_DPT] = {0, 0, 0, 0};
@@ -450,7 +461,9 @@ __global__ void __launch_bounds__(TILE, 4) os_scatter_kernel(const uint64_t *__r
     for (uint32_t i = threadIdx.x; i < cnt_tile; i += TILE) {
         const uint64_t x = S.stage[i];
         const uint32_t d = (uint32_t)(x >> shift) & (OS_BINS - 1);
-        v_out[S.gbase[d] + (i - S.dbase[d])] = x;
+        const uint32_t to = S.gbase[d] + (i - S.dbase[d]);
+        v_out[to] = x;
+        if (PAIR) p_out[to] = S.stage_p[i];
     }
 }
 

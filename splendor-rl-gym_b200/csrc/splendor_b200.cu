@@ -91,7 +91,7 @@ struct spl_ctx {
     int identity = IDENT_KEY;  // visited-table identity of the speedrun solver (spl_set_identity)  // levels left before the dictionary path is tried again after a miss
     DevBuf status[3];
     // scratch
-    DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2, os_hist;
+    DevBuf off, cand_slot, tmp_rec, tmp_rec2, sk, y[2], idx[2], kl[2], kh[2], matrix, matrix2, os_hist, os_status;
     DevBuf pool_front, pool_uniq, pool_grank;  // frontier buffers lent to the active solver
     DevBuf rcfg, rcand, rvmask, ridx64, rtmp;  // realistic mode scratch
     RBucket *rtable = nullptr;  // realistic mode: exact-key visited table (64-byte buckets, one state each)
@@ -275,7 +275,8 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(m2_group_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offsetof(WarpSmem, bsort)));
     CKC(cudaFuncSetAttribute(m2_group_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
     CKC(cudaFuncSetAttribute(m2_group_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
-    CKC(cudaFuncSetAttribute(os_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem)));
+    CKC(cudaFuncSetAttribute(os_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offsetof(OsSmem, stage_p)));
+    CKC(cudaFuncSetAttribute(os_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem)));
     CKC(cudaFuncSetAttribute(gs_buys_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RouteSmem)));
     CKC(cudaMalloc(&c->d_dict2, sizeof(ScoreDict)));
     CKC(cudaMalloc(&c->d_dest, 2 * MAX_RANKS * 8));
@@ -559,6 +560,8 @@ static int run_dict_select(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, i
     return SPL_OK;
 }
 
+static int onesweep_sort(spl_ctx *c, uint64_t *const k[2], uint32_t *const pl[2], int64_t n, int lo_bit, int nbits, int *cur, cudaStream_t st);
+
 // one stable LSD pass over `kept` elements: digit = (dig >> shift) & 255
 static int sort_pass(spl_ctx *c, int wide, int cur, const uint64_t *dig, int64_t kept, int shift, unsigned nt,
                      size_t msz, cudaStream_t st) {
@@ -690,9 +693,15 @@ static int do_cut_sort(spl_ctx *c, const uint64_t *sk, const uint64_t *kb, int k
             for (int shift = 0; shift < 41; shift += SORT_BITS)
                 if ((vary_hi >> shift) & 0xff) { CKS(c, sort_pass(c, 1, cur, c->kh[cur].as<uint64_t>(), kept, shift, nt, msz, st)); cur ^= 1; }
         }
-        for (int shift = 0; shift < nbits; shift += SORT_BITS) {
-            CKS(c, sort_pass(c, det == 1 && !pack, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
-            cur ^= 1;
+        if (!(det == 1 && !pack) && kept < OS_MAX_ITEMS) {  // (sort word, slot) pairs: one-sweep passes of 10 bits
+            uint64_t *const yk[2] = {c->y[0].as<uint64_t>(), c->y[1].as<uint64_t>()};
+            uint32_t *const yi[2] = {c->idx[0].as<uint32_t>(), c->idx[1].as<uint32_t>()};
+            CKS(c, onesweep_sort(c, yk, yi, kept, 0, nbits, &cur, st));
+        } else {
+            for (int shift = 0; shift < nbits; shift += SORT_BITS) {
+                CKS(c, sort_pass(c, det == 1 && !pack, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
+                cur ^= 1;
+            }
         }
     }
     if (det == 2 && kept > 0) {  // keys were in rank order already: the stable score sort kept them so; rebuild the key words
@@ -1225,30 +1234,45 @@ static int ensure_nodes(spl_ctx *c, uint64_t need, cudaStream_t st) {
 }
 
 // stable LSD sort of packed 64-bit items on bits [lo_bit, 64): result in c->y[*cur]
+// One-sweep stable LSD sort (spl_m2.cuh 2b) of k[*cur][0..n) by bits lo_bit .. lo_bit + nbits - 1, ping-ponging between
+// k[0] / k[1]; with a payload column (pl != nullptr) the pairs move together.  n < OS_MAX_ITEMS.
+static int onesweep_sort(spl_ctx *c, uint64_t *const k[2], uint32_t *const pl[2], int64_t n, int lo_bit, int nbits, int *cur, cudaStream_t st) {
+    const int passes = (nbits + OS_BITS - 1) / OS_BITS;
+    if (n <= 1 || passes <= 0) return SPL_OK;
+    if (passes > OS_MAX_PASSES || n >= OS_MAX_ITEMS) return fail(c, SPL_E_INVALID, "internal: one-sweep sort of %lld values, %d bits", (long long)n, nbits);
+    const unsigned snt = nblk(n, SORT_TILE);
+    const size_t status_bytes = (size_t)snt * OS_BINS * 4;
+    CK(c, c->os_hist.ensure(OS_MAX_PASSES * OS_BINS * 4, 0, st));
+    CK(c, c->os_status.ensure(status_bytes, 0, st));
+    CK(c, cudaMemsetAsync(c->os_hist.p, 0, (size_t)passes * OS_BINS * 4, st));
+    os_hist_kernel<<<std::min<unsigned>(148 * 8, nblk(n)), TILE, (size_t)passes * OS_BINS * 4, st>>>(k[*cur], n, lo_bit, passes, c->os_hist.as<uint32_t>());
+    os_base_kernel<<<passes, OS_BINS, 0, st>>>(c->os_hist.as<uint32_t>());
+    c->launches += 2;
+    for (int p = 0; p < passes; ++p) {
+        CK(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, st));
+        CKS(c, reset_ticket(c, 2, st));
+        if (pl)
+            os_scatter_kernel<true><<<snt, TILE, sizeof(OsSmem), st>>>(k[*cur], pl[*cur], n, lo_bit + p * OS_BITS, c->os_hist.as<uint32_t>() + p * OS_BINS,
+                                                                       c->os_status.as<uint32_t>(), c->d_ctr, 2, k[*cur ^ 1], pl[*cur ^ 1]);
+        else
+            os_scatter_kernel<false><<<snt, TILE, offsetof(OsSmem, stage_p), st>>>(k[*cur], nullptr, n, lo_bit + p * OS_BITS,
+                                                                                   c->os_hist.as<uint32_t>() + p * OS_BINS,
+                                                                                   c->os_status.as<uint32_t>(), c->d_ctr, 2, k[*cur ^ 1], nullptr);
+        ++c->launches;
+        CK(c, cudaGetLastError());
+        *cur ^= 1;
+    }
+    return SPL_OK;
+}
+
 // Stable sort of the round's packed items by their key bits ITEM_KEY_LO..63: three one-sweep passes of 10-bit digits
 // (rounds below 2^30 items), else 8-bit LSD passes with per-pass histogram + scan.
 static int sort_items(spl_ctx *c, int64_t n_items, int *cur, cudaStream_t st) {
     const unsigned snt = nblk(n_items, SORT_TILE);
     static const bool no_onesweep = getenv("SPL_NO_ONESWEEP") != nullptr;
-    if (n_items > 1 && n_items < OS_MAX_ITEMS && !no_onesweep) {
-        const size_t status_bytes = (size_t)snt * OS_BINS * 4;
-        CK(c, c->os_hist.ensure(OS_PASSES * OS_BINS * 4, 0, st));
-        CK(c, c->matrix.ensure(status_bytes, 0, st));
-        CK(c, cudaMemsetAsync(c->os_hist.p, 0, OS_PASSES * OS_BINS * 4, st));
-        os_hist_kernel<<<std::min<unsigned>(148 * 8, nblk(n_items)), TILE, 0, st>>>(c->y[*cur].as<uint64_t>(), n_items, c->os_hist.as<uint32_t>());
-        os_base_kernel<<<OS_PASSES, OS_BINS, 0, st>>>(c->os_hist.as<uint32_t>());
-        c->launches += 2;
-        for (int p = 0; p < OS_PASSES; ++p) {
-            CK(c, cudaMemsetAsync(c->matrix.p, 0, status_bytes, st));
-            CKS(c, reset_ticket(c, 2, st));
-            os_scatter_kernel<<<snt, TILE, sizeof(OsSmem), st>>>(c->y[*cur].as<uint64_t>(), n_items, ITEM_KEY_LO + p * OS_BITS,
-                                                                 c->os_hist.as<uint32_t>() + p * OS_BINS, c->matrix.as<uint32_t>(), c->d_ctr, 2,
-                                                                 c->y[*cur ^ 1].as<uint64_t>());
-            ++c->launches;
-            CK(c, cudaGetLastError());
-            *cur ^= 1;
-        }
-        return SPL_OK;
+    if (n_items < OS_MAX_ITEMS && !no_onesweep) {
+        uint64_t *const k[2] = {c->y[0].as<uint64_t>(), c->y[1].as<uint64_t>()};
+        return onesweep_sort(c, k, nullptr, n_items, ITEM_KEY_LO, 64 - ITEM_KEY_LO, cur, st);
     }
     const int lo_bit = ITEM_KEY_LO;
     const size_t msz = (size_t)SORT_BINS * snt;
@@ -1833,9 +1857,15 @@ int32_t spl_gs_cut(spl_gsolver *s, int32_t have_tie_threshold, int64_t *kept_loc
         const size_t msz = (size_t)SORT_BINS * nt;
         CK(c, c->matrix.ensure(msz * 4, 0, st));
         CK(c, c->matrix2.ensure(msz * 4, 0, st));
-        for (int shift = 0; shift < nbits; shift += SORT_BITS) {
-            CKS(c, sort_pass(c, 0, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
-            cur ^= 1;
+        if (kept < OS_MAX_ITEMS) {
+            uint64_t *const yk[2] = {c->y[0].as<uint64_t>(), c->y[1].as<uint64_t>()};
+            uint32_t *const yi[2] = {c->idx[0].as<uint32_t>(), c->idx[1].as<uint32_t>()};
+            CKS(c, onesweep_sort(c, yk, yi, kept, 0, nbits, &cur, st));
+        } else {
+            for (int shift = 0; shift < nbits; shift += SORT_BITS) {
+                CKS(c, sort_pass(c, 0, cur, c->y[cur].as<uint64_t>(), kept, shift, nt, msz, st));
+                cur ^= 1;
+            }
         }
     }
     s->cut_cur = cur;
@@ -1880,24 +1910,12 @@ int32_t spl_gs_rank_sort(spl_gsolver *s, const uint64_t *y_dev, int64_t n, int32
     gs_iota_kernel<<<nblk(n), TILE, 0, st>>>(c->kh[0].as<uint32_t>(), n);
     ++c->launches;
     int cur = 0;
-    const unsigned nt = nblk(n, SORT_TILE);
-    const size_t msz = (size_t)SORT_BINS * nt;
-    CK(c, c->matrix.ensure(msz * 4, 0, st));
-    CK(c, c->matrix2.ensure(msz * 4, 0, st));
-    const unsigned st_tiles = nblk((int64_t)msz, TILE * SCAN_ITEMS);
-    if (n > 1)
-        for (int shift = 0; shift < y_bits; shift += SORT_BITS) {
-            sort_hist_kernel<<<nt, TILE, 0, st>>>(c->kl[cur].as<uint64_t>(), n, shift, c->matrix.as<uint32_t>(), nt);
-            CKS(c, prep_status(c, 1, st_tiles, st));
-            CKS(c, reset_ticket(c, 2, st));
-            scan_u32_kernel<<<st_tiles, TILE, 0, st>>>(c->matrix.as<uint32_t>(), c->matrix2.as<uint32_t>(), (int64_t)msz,
-                                                        c->status[1].as<uint64_t>(), c->d_ctr, 2);
-            sort_scatter_kernel<false><<<nt, TILE, 0, st>>>(c->kl[cur].as<uint64_t>(), c->kl[cur].as<uint64_t>(), c->kh[cur].as<uint32_t>(), n, shift,
-                                                             c->matrix2.as<uint32_t>(), nt, c->kl[cur ^ 1].as<uint64_t>(), c->kh[cur ^ 1].as<uint32_t>(),
-                                                             nullptr, nullptr, nullptr, nullptr);
-            c->launches += 3;
-            cur ^= 1;
-        }
+    if (n >= OS_MAX_ITEMS) return fail(c, SPL_E_INVALID, "spl_gs_rank_sort: %lld sort words (limit 2^30 per rank)", (long long)n);
+    {
+        uint64_t *const k[2] = {c->kl[0].as<uint64_t>(), c->kl[1].as<uint64_t>()};
+        uint32_t *const pl[2] = {c->kh[0].as<uint32_t>(), c->kh[1].as<uint32_t>()};
+        CKS(c, onesweep_sort(c, k, pl, n, 0, y_bits, &cur, st));
+    }
     gs_scatter_ranks_kernel<<<nblk(n), TILE, 0, st>>>(c->kh[cur].as<uint32_t>(), n, base, ranks_out_dev);
     ++c->launches;
     CK(c, cudaGetLastError());
