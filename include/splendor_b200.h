@@ -156,6 +156,13 @@ int32_t spl_launch_count(spl_ctx *ctx, int64_t *n_host);
 /* host<->device bytes copied by this context so far (bench.py's e2e accounting) */
 int32_t spl_transfer_bytes(spl_ctx *ctx, int64_t *h2d_host, int64_t *d2h_host);
 
+/* Device buffers that the other processes of this node can map (CUDA IPC), for spl_gs_round_buys_peer: the owner
+ * allocates and publishes the 64-byte handle, every peer opens it once (peer access over NVLink is enabled on open). */
+int32_t spl_ipc_alloc(spl_ctx *ctx, uint64_t bytes, void **ptr_dev_out, uint8_t handle_out[64]);
+int32_t spl_ipc_open(spl_ctx *ctx, const uint8_t handle[64], void **ptr_dev_out);
+int32_t spl_ipc_close(spl_ctx *ctx, void *ptr_dev);
+int32_t spl_ipc_free(spl_ctx *ctx, void *ptr_dev);
+
 /* ---- stage operators (caller-owned device buffers) ---------------------------------------- */
 
 /* State.__iter__ for a batch (src/solver.py:357-388): all successors of parents
@@ -278,6 +285,12 @@ int32_t spl_gs_round_begin(spl_gsolver *s, int64_t rank_lo, int64_t rank_hi, int
                            void *stream);
 /* the round's buy records into send_dev (destination d owns [sum(counts[0..d)), +counts[d])) */
 int32_t spl_gs_round_buys(spl_gsolver *s, void *send_dev, void *stream);
+/* the same records stored straight into the receive buffers of their owners over NVLink peer mappings (the store is
+ * the transfer; no send buffer, no all-to-all): recv_dev_of_rank[d] = rank d's receive buffer as mapped into this
+ * process (spl_ipc_open; this rank's own buffer for d == rank), offset_at_rank[d] = records of lower ranks that
+ * precede this rank's there (sum of counts[r][d], r < rank).  Callers fence with a stream-ordered collective before
+ * anyone reads its buffer. */
+int32_t spl_gs_round_buys_peer(spl_gsolver *s, void *const *recv_dev_of_rank, const int64_t *offset_at_rank, void *stream);
 /* owner side (:447-450): local parents + the n_recv records received -> first-arrival dedup per card set, winners + scores */
 int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv, int64_t *n_new_host, void *stream);
 int32_t spl_gs_counters(spl_gsolver *s, int64_t *n_uniq_host, int64_t *generated_host, int64_t *visited_host);

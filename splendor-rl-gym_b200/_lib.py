@@ -99,6 +99,11 @@ def _load():
         'spl_gs_goal': (i32, [vp, C.POINTER(i64), C.POINTER(i64), vp]),
         'spl_gs_round_begin': (i32, [vp, i64, i64, vp, C.POINTER(i64), vp]),
         'spl_gs_round_buys': (i32, [vp, vp, vp]),
+        'spl_gs_round_buys_peer': (i32, [vp, vp, vp, vp]),
+        'spl_ipc_alloc': (i32, [vp, u64, C.POINTER(vp), vp]),
+        'spl_ipc_open': (i32, [vp, vp, C.POINTER(vp)]),
+        'spl_ipc_close': (i32, [vp, vp]),
+        'spl_ipc_free': (i32, [vp, vp]),
         'spl_gs_round_group': (i32, [vp, vp, i64, C.POINTER(i64), vp]),
         'spl_gs_counters': (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         'spl_gs_stage_ms': (i32, [vp, vp]),

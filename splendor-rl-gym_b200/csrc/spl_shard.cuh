@@ -88,16 +88,18 @@ struct RouteSmem {
     uint32_t warp_sums[TILE / 32 + 1];
     uint32_t cnt[MAX_RANKS];
     unsigned long long base[MAX_RANKS];
+    Rec *dst[MAX_RANKS];
 };
 __global__ void __launch_bounds__(TILE) gs_buys_route_kernel(const Rec *__restrict__ front, int64_t np,
                                                              const uint64_t *__restrict__ grank,
                                                              const DevTables *__restrict__ tabs,
                                                              const uint32_t *__restrict__ takes_idx, uint32_t world,
-                                                             Rec *__restrict__ send, unsigned long long *cursor) {
+                                                             Rec *const *__restrict__ dst, unsigned long long *cursor) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RouteSmem &S = *reinterpret_cast<RouteSmem *>(smem_raw);
     const unsigned tid = threadIdx.x;
     load_tabs(S.tabs, tabs);
+    if (tid < world) S.dst[tid] = dst[tid];
     __syncthreads();
     const int64_t p0 = (int64_t)blockIdx.x * TILE, p = p0 + tid;
     uint64_t bm_lo = 0, bm_hi = 0;
@@ -157,7 +159,9 @@ __global__ void __launch_bounds__(TILE) gs_buys_route_kernel(const Rec *__restri
             const uint32_t ord = w0 + i - S.prefb[j];
             const uint64_t caux = aux + saved + ((uint64_t)((cd >> 15) & 7) << 16) + (1ull << (24 + 5 * ((cd >> 18) & 7)));
             Rec r{klo, khi, caux, (grank[p0 + j] << 8) | ord};
-            st_rec(send + S.base[S.where[i] >> 24] + (S.where[i] & 0xffffffu), r);
+            // dst[d]: this rank's range of destination d's records -- a slice of the local send buffer (NCCL exchange) or
+            // of rank d's receive buffer itself, mapped over NVLink (the store IS the transfer)
+            st_rec(S.dst[S.where[i] >> 24] + S.base[S.where[i] >> 24] + (S.where[i] & 0xffffffu), r);
         }
     }
 }

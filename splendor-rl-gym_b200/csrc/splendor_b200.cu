@@ -86,7 +86,7 @@ struct spl_ctx {
     SelState *d_sel = nullptr, *h_sel = nullptr;
     uint32_t *d_hist = nullptr;
     ScoreDict *d_dict = nullptr, *d_dict2 = nullptr;  // d_dict2: the merged (global) dictionary of the sharded cut
-    unsigned long long *d_dest = nullptr;             // [2][MAX_RANKS]: per-destination record counts / send cursors
+    unsigned long long *d_dest = nullptr;             // [3][MAX_RANKS]: per-destination record counts / write cursors / base pointers
     int dict_skip = 0;
     int identity = IDENT_KEY;  // visited-table identity of the speedrun solver (spl_set_identity)  // levels left before the dictionary path is tried again after a miss
     DevBuf status[3];
@@ -279,7 +279,7 @@ int32_t spl_create(const spl_config *cfg, spl_ctx **out) {
     CKC(cudaFuncSetAttribute(os_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem)));
     CKC(cudaFuncSetAttribute(gs_buys_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RouteSmem)));
     CKC(cudaMalloc(&c->d_dict2, sizeof(ScoreDict)));
-    CKC(cudaMalloc(&c->d_dest, 2 * MAX_RANKS * 8));
+    CKC(cudaMalloc(&c->d_dest, 3 * MAX_RANKS * 8));
     {
         c->max_node_bytes = cfg->max_node_bytes ? cfg->max_node_bytes : (uint64_t)(free_b * 0.5);
         uint64_t nn = cfg->node_slots ? cfg->node_slots : (1ull << 12);
@@ -1613,6 +1613,22 @@ int32_t spl_gs_round_begin(spl_gsolver *s, int64_t rank_lo, int64_t rank_hi, int
 }
 
 // the round's buy records into send_dev: destination d owns [sum(counts[0..d)), +counts[d])
+// the round's buy records, destination d's at dst[d] + (0 .. counts[d]) in no particular order
+static int gs_route(spl_gsolver *s, void *const *dst, cudaStream_t st) {
+    spl_ctx *c = s->c;
+    unsigned long long h[2 * MAX_RANKS] = {0};  // cursors (relative to each destination's base), then the bases
+    for (int g = 0; g < s->world; ++g) h[MAX_RANKS + g] = (unsigned long long)(uintptr_t)dst[g];
+    CK(c, cudaMemcpyAsync(c->d_dest + MAX_RANKS, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    CK(c, cudaStreamSynchronize(st));  // h is a stack array
+    c->h2d_bytes += sizeof(h);
+    gs_buys_route_kernel<<<nblk(s->r_np), TILE, sizeof(RouteSmem), st>>>(
+        s->front.as<Rec>() + s->r_p0, s->r_np, s->grank.as<uint64_t>() + s->r_p0, c->d_tabs, c->d_takes_idx, (uint32_t)s->world,
+        reinterpret_cast<Rec *const *>(c->d_dest + 2 * MAX_RANKS), c->d_dest + MAX_RANKS);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return SPL_OK;
+}
+
 int32_t spl_gs_round_buys(spl_gsolver *s, void *send_dev, void *stream) {
     if (!s) return SPL_E_INVALID;
     spl_ctx *c = s->c;
@@ -1620,16 +1636,61 @@ int32_t spl_gs_round_buys(spl_gsolver *s, void *send_dev, void *stream) {
     CK(c, enter_device(c));
     if (s->r_np == 0 || s->r_buys == 0) return SPL_OK;
     if (!send_dev) return fail(c, SPL_E_INVALID, "spl_gs_round_buys: null send buffer");
-    unsigned long long cur[MAX_RANKS] = {0};
-    for (int g = 1; g < s->world; ++g) cur[g] = cur[g - 1] + (unsigned long long)s->counts[g - 1];
-    CK(c, cudaMemcpyAsync(c->d_dest + MAX_RANKS, cur, MAX_RANKS * 8, cudaMemcpyHostToDevice, st));
-    CK(c, cudaStreamSynchronize(st));  // cur is a stack array
-    c->h2d_bytes += MAX_RANKS * 8;
-    gs_buys_route_kernel<<<nblk(s->r_np), TILE, sizeof(RouteSmem), st>>>(
-        s->front.as<Rec>() + s->r_p0, s->r_np, s->grank.as<uint64_t>() + s->r_p0, c->d_tabs, c->d_takes_idx, (uint32_t)s->world,
-        reinterpret_cast<Rec *>(send_dev), c->d_dest + MAX_RANKS);
-    ++c->launches;
-    CK(c, cudaGetLastError());
+    void *dst[MAX_RANKS] = {nullptr};
+    int64_t at = 0;
+    for (int g = 0; g < s->world; ++g) { dst[g] = reinterpret_cast<Rec *>(send_dev) + at; at += s->counts[g]; }
+    return gs_route(s, dst, st);
+}
+
+int32_t spl_gs_round_buys_peer(spl_gsolver *s, void *const *recv_dev_of_rank, const int64_t *offset_at_rank, void *stream) {
+    if (!s || !recv_dev_of_rank || !offset_at_rank) return SPL_E_INVALID;
+    spl_ctx *c = s->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, enter_device(c));
+    if (s->r_np == 0 || s->r_buys == 0) return SPL_OK;
+    void *dst[MAX_RANKS] = {nullptr};
+    for (int g = 0; g < s->world; ++g) {
+        if (s->counts[g] && (!recv_dev_of_rank[g] || offset_at_rank[g] < 0)) return fail(c, SPL_E_INVALID, "spl_gs_round_buys_peer: no buffer for rank %d", g);
+        dst[g] = reinterpret_cast<Rec *>(recv_dev_of_rank[g]) + offset_at_rank[g];
+    }
+    return gs_route(s, dst, st);
+}
+
+// ---- device buffers other processes of this node can map (CUDA IPC): the receive side of spl_gs_round_buys_peer
+int32_t spl_ipc_alloc(spl_ctx *c, uint64_t bytes, void **ptr_out, uint8_t handle_out[64]) {
+    if (!c || !ptr_out || !handle_out || !bytes) return SPL_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries CUDA IPC handles as 64 bytes");
+    CK(c, enter_device(c));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, SPL_E_NOMEM, "spl_ipc_alloc: %llu bytes: %s", (unsigned long long)bytes, cudaGetErrorString(e)); }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return fail(c, SPL_E_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    *ptr_out = p;
+    return SPL_OK;
+}
+int32_t spl_ipc_open(spl_ctx *c, const uint8_t handle[64], void **ptr_out) {
+    if (!c || !handle || !ptr_out) return SPL_E_INVALID;
+    CK(c, enter_device(c));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, SPL_E_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+    return SPL_OK;
+}
+int32_t spl_ipc_close(spl_ctx *c, void *ptr) {
+    if (!c || !ptr) return SPL_E_INVALID;
+    CK(c, enter_device(c));
+    CK(c, cudaIpcCloseMemHandle(ptr));
+    return SPL_OK;
+}
+int32_t spl_ipc_free(spl_ctx *c, void *ptr) {
+    if (!c || !ptr) return SPL_E_INVALID;
+    CK(c, enter_device(c));
+    CK(c, cudaDeviceSynchronize());
+    CK(c, cudaFree(ptr));
     return SPL_OK;
 }
 

@@ -546,6 +546,56 @@ class ShardedSolver:
 
 
 
+class PeerRecv:
+    """This rank's receive buffer for routed buy records, mapped into every other rank of the node (CUDA IPC through
+    spl_ipc_*): the routing kernel of rank r stores the records owned by rank d straight into d's buffer over NVLink
+    (spl_gs_round_buys_peer), so a round has no send buffer and no all-to-all.  One buffer per Engine, grown
+    collectively (every rank sees the same gathered counts, hence takes the same decision)."""
+
+    def __init__(self, eng: Engine, comm: Comm):
+        self.eng, self.comm = eng, comm
+        self.cap = 0            # records (32 B)
+        self.local = None       # this rank's buffer
+        self.ptrs = None        # ptrs[d]: rank d's buffer as mapped here
+
+    def _fence(self):
+        torch.cuda.synchronize(self.eng.tdev)
+        self.comm.all_reduce(torch.zeros(1, dtype=torch.int64, device=self.eng.tdev), dist.ReduceOp.SUM)
+        torch.cuda.synchronize(self.eng.tdev)
+
+    def release(self):
+        if self.local is None:
+            return
+        for g, p in enumerate(self.ptrs):
+            if g != self.comm.rank:
+                check(lib.spl_ipc_close(self.eng._h, C.c_void_p(p)), self.eng._h)
+        self._fence()  # nobody maps the buffer any more
+        check(lib.spl_ipc_free(self.eng._h, C.c_void_p(self.local)), self.eng._h)
+        self.local, self.ptrs, self.cap = None, None, 0
+
+    def ensure(self, records: int):
+        """collective: every rank passes the same number"""
+        if self.local is not None and records <= self.cap:
+            return
+        self.release()
+        cap = max(int(records * 1.25), 1 << 20)
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        check(lib.spl_ipc_alloc(self.eng._h, cap * 32, C.byref(ptr), handle), self.eng._h)
+        words = np.frombuffer(bytes(handle), dtype=np.int64)
+        allh = self.comm.gather_ints(*[int(x) for x in words])  # [rank, 8]
+        ptrs = []
+        for g in range(self.comm.world):
+            if g == self.comm.rank:
+                ptrs.append(ptr.value)
+                continue
+            hb = (C.c_uint8 * 64).from_buffer_copy(np.ascontiguousarray(allh[g], dtype=np.int64).tobytes())
+            pp = C.c_void_p()
+            check(lib.spl_ipc_open(self.eng._h, hb, C.byref(pp)), self.eng._h)
+            ptrs.append(pp.value)
+        self.local, self.ptrs, self.cap = ptr.value, ptrs, cap
+        self._fence()  # every mapping exists before anyone stores through one
+
+
 class GroupedShardedSolver:
     """Beam search of State.solve (src/solver.py:390-464) over a queue sharded BY CARD SET (spl_gs_* entry points,
     csrc/spl_shard.cuh): a queue state lives on the rank that owns its cards, so its gem-take successors are
@@ -576,6 +626,12 @@ class GroupedShardedSolver:
         self.goal_rank = -1
         self.infos = []
         self.noise_source = None
+        # buy records go to their owners by peer stores from the routing kernel (SPL_NO_P2P=1: send buffer + NCCL all-to-all)
+        self.peer = None
+        if comm.on and not os.environ.get('SPL_NO_P2P'):
+            if getattr(eng, '_peer_recv', None) is None:
+                eng._peer_recv = PeerRecv(eng, comm)
+            self.peer = eng._peer_recv
 
     def close(self):
         if getattr(self, '_h', None):
@@ -625,14 +681,27 @@ class GroupedShardedSolver:
             counts = np.array(counts[:], dtype=np.int64)
             t0 = _tick('count', t0)
             allc = comm.gather_ints(*counts.tolist())          # [src, dst]
-            send = torch.empty((max(int(counts.sum()), 1), 4), dtype=torch.int64, device=dev)
-            check(lib.spl_gs_round_buys(self._h, send.data_ptr(), self._st()), eng._h)
-            t0 = _tick('buys', t0)
-            recv = comm.all_to_all_rows(send[:int(counts.sum())], counts, allc[:, me])
-            t0 = _tick('a2a', t0)
             n_new = C.c_int64()
-            check(lib.spl_gs_round_group(self._h, recv.data_ptr() if recv.shape[0] else None, recv.shape[0], C.byref(n_new), self._st()), eng._h)
-            del send, recv
+            if self.peer is not None:
+                # every rank has finished reading the previous round's records (its counts above came after a stream
+                # sync); the routing kernel stores each record into its owner's buffer, rank-major as an all-to-all would
+                self.peer.ensure(int(allc.sum(axis=0).max()))
+                n_recv = int(allc[:, me].sum())
+                offs = (C.c_int64 * G)(*[int(x) for x in allc[:me].sum(axis=0)])
+                ptrs = (C.c_void_p * G)(*self.peer.ptrs)
+                check(lib.spl_gs_round_buys_peer(self._h, ptrs, offs, self._st()), eng._h)
+                t0 = _tick('buys', t0)
+                comm.all_reduce(torch.zeros(1, dtype=torch.int64, device=dev), dist.ReduceOp.SUM)  # all stores have landed
+                t0 = _tick('a2a', t0)
+                check(lib.spl_gs_round_group(self._h, C.c_void_p(self.peer.local) if n_recv else None, n_recv, C.byref(n_new), self._st()), eng._h)
+            else:
+                send = torch.empty((max(int(counts.sum()), 1), 4), dtype=torch.int64, device=dev)
+                check(lib.spl_gs_round_buys(self._h, send.data_ptr(), self._st()), eng._h)
+                t0 = _tick('buys', t0)
+                recv = comm.all_to_all_rows(send[:int(counts.sum())], counts, allc[:, me])
+                t0 = _tick('a2a', t0)
+                check(lib.spl_gs_round_group(self._h, recv.data_ptr() if recv.shape[0] else None, recv.shape[0], C.byref(n_new), self._st()), eng._h)
+                del send, recv
             t0 = _tick('group', t0)
         nu, gen, vis = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib.spl_gs_counters(self._h, C.byref(nu), C.byref(gen), C.byref(vis)), eng._h)
