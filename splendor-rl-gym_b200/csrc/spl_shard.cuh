@@ -85,6 +85,8 @@ struct RouteSmem {
     uint32_t prefb[TILE + 1];
     uint16_t blist[BUY_WIN];
     uint32_t where[BUY_WIN];  // destination << 24 | index among this window's records for that destination
+    uint16_t order[BUY_WIN];  // window records grouped by destination: consecutive threads store consecutive slots
+    uint32_t dstart[MAX_RANKS + 1];
     uint32_t warp_sums[TILE / 32 + 1];
     uint32_t cnt[MAX_RANKS];
     unsigned long long base[MAX_RANKS];
@@ -147,8 +149,17 @@ __global__ void __launch_bounds__(TILE) gs_buys_route_kernel(const Rec *__restri
         }
         __syncthreads();
         if (tid < world && S.cnt[tid]) S.base[tid] = atomicAdd(&cursor[tid], (unsigned long long)S.cnt[tid]);
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (uint32_t d = 0; d < world; ++d) { S.dstart[d] = run; run += S.cnt[d]; }
+        }
         __syncthreads();
-        for (uint32_t i = tid; i < nbw; i += TILE) {
+        for (uint32_t i = tid; i < nbw; i += TILE) S.order[S.dstart[S.where[i] >> 24] + (S.where[i] & 0xffffffu)] = (uint16_t)i;
+        __syncthreads();
+        // one destination after the other, slot after slot: a warp stores 1 KB of consecutive records (over NVLink when
+        // the destination is a peer)
+        for (uint32_t t = tid; t < nbw; t += TILE) {
+            const uint32_t i = S.order[t];
             const uint32_t ent = S.blist[i], j = ent >> 7;
             const int pos = ent & 127;
             const uint64_t lo = S.lo[j], aux = S.aux[j];

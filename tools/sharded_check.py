@@ -95,6 +95,8 @@ for rep in range(a.reps):
 from splendor_rl_gym_b200 import sharded as _sh
 if _sh.TIMING and comm.rank == 0:
     tot = sum(_sh.PHASES.values())
+    if a.grouped:
+        print('rank-0 stage ms (last rep): ' + ', '.join(f"{k}={sum(i.get('ms_' + k, 0.0) for i in sol.infos):.1f}" for k in ('sort', 'thread', 'warp', 'cta')))
     print('phases (s, last rep): ' + ', '.join(f'{k}={v:.3f} ({100 * v / tot:.0f}%)' for k, v in _sh.PHASES.items()))
 if comm.on:
     dist.destroy_process_group()
