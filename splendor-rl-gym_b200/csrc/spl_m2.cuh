@@ -652,6 +652,8 @@ __device__ __forceinline__ void bm_step(const GroupArgs &A, WarpStage &W, uint64
     }
     bool win = false;
     if (lead) {
+        // (64-bit OR on shared memory compiles to a CAS loop, a quarter of this kernel's instructions; the native 32-bit
+        // ATOMS.OR with a returned value was measured and is slower here: 97 vs 78 ms per beam-30M solve)
         const unsigned long long bit = 1ull << (rk & 63);
         win = !(atomicOr(reinterpret_cast<unsigned long long *>(&bm[rk >> 6]), bit) & bit);
     }
@@ -742,8 +744,11 @@ struct WarpSmem {
 // parent window and a buy-record window of 32 lanes each, once per card set it holds (almost always one; several
 // only when two sets share a 32-bit sort key).  Persistent grid: warp w takes list entries w, w + W, ...
 constexpr int MAX_SETS = 4;  // card sets under one sort key that the thread / warp kernels can tell apart
+#ifndef SPL_WARP_CTAS
+#define SPL_WARP_CTAS 4  // resident CTAs per SM of the warp kernel (64 registers per thread; 3 and 5 measured slower)
+#endif
 template <bool UNORDERED>
-__global__ void __launch_bounds__(TILE, 4) m2_group_warp_kernel(GroupArgs A) {
+__global__ void __launch_bounds__(TILE, SPL_WARP_CTAS) m2_group_warp_kernel(GroupArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem &S = *reinterpret_cast<WarpSmem *>(smem_raw);
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1121,7 +1126,7 @@ __global__ void __launch_bounds__(TILE) m2_group_big_kernel(GroupArgs A) {
                     kmin = min(kmin, k); kmax = max(kmax, k);
                 }
                 ++pos;
-                atomicOr(reinterpret_cast<unsigned long long *>(&S.bm[rk >> 6]), 1ull << (rk & 63));
+                atomicOr(reinterpret_cast<unsigned *>(S.bm) + (rk >> 5), 1u << (rk & 31));
             }
             __syncthreads();
             if (tid < NODE_BM_WORDS) N[2 + tid] = S.bm[tid];

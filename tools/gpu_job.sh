@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $T tools/sharded_check.py --grouped --beam 300000 2>&1 | grep "world="
-SPL_TIMING=1 timeout 300 $T tools/sharded_check.py --grouped --beam 60000000 --no-oracle --no-links --reps 2 2>&1 | grep -v "^\*\*\|OMP" | tail -3
-SPL_NO_P2P=1 SPL_TIMING=1 timeout 300 $T tools/sharded_check.py --grouped --beam 60000000 --no-oracle --no-links --reps 2 2>&1 | grep -v "^\*\*\|OMP" | tail -1
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_baseline_sizes.py -m gpu -q -x -k "not beam_3m" > gpurun_out/r2ap_pytest.log 2>&1
+tail -2 gpurun_out/r2ap_pytest.log
+SPL_DEBUG=1 QUIET=1 timeout 300 python tools/explore.py --beam 30000000 --reps 2 > gpurun_out/r2ap_debug_30m.log 2>&1; grep -E "rep|SUMMARY" gpurun_out/r2ap_debug_30m.log | tail -2
+grep -E "grouped\] L1[34]" gpurun_out/r2ap_debug_30m.log | tail -4 | cut -c150-400
