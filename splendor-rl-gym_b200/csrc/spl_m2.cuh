@@ -654,8 +654,9 @@ __device__ __forceinline__ void bm_step(const GroupArgs &A, WarpStage &W, uint64
     if (lead) {
         // (64-bit OR on shared memory compiles to a CAS loop, a quarter of this kernel's instructions; the native 32-bit
         // ATOMS.OR with a returned value was measured and is slower here: 97 vs 78 ms per beam-30M solve)
+        // Most candidates are duplicates: a set bit is final, so only clear ones pay for the atomic.
         const unsigned long long bit = 1ull << (rk & 63);
-        win = !(atomicOr(reinterpret_cast<unsigned long long *>(&bm[rk >> 6]), bit) & bit);
+        if (!(bm[rk >> 6] & bit)) win = !(atomicOr(reinterpret_cast<unsigned long long *>(&bm[rk >> 6]), bit) & bit);
     }
     const unsigned wb = __ballot_sync(0xffffffffu, win);
     if (win) {
