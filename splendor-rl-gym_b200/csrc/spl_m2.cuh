@@ -569,10 +569,16 @@ __device__ __forceinline__ uint64_t parent_rank(const GroupArgs &A, uint32_t id)
 
 // per-warp winner staging: records are collected in shared memory and written out 17..48 at a time behind one
 // global atomic (dense output, few same-address atomics)
+constexpr int M2_WARPS_ = TILE / 32;
 struct WarpStage {
-    uint64_t *lo, *hi, *aux, *link, *sk;  // [SM_STAGE] each (shared memory of this warp)
-    uint32_t cnt;                        // warp-uniform
+    uint64_t *st;                        // this warp's slice of st[5][warps][SM_STAGE] in shared memory: one pointer, the
+    uint32_t cnt;                        // five columns sit at compile-time strides (cnt: warp-uniform)
     uint64_t kmin, kmax;
+    __device__ __forceinline__ uint64_t &lo(uint32_t i) const { return st[i]; }
+    __device__ __forceinline__ uint64_t &hi(uint32_t i) const { return st[1 * M2_WARPS_ * SM_STAGE + i]; }
+    __device__ __forceinline__ uint64_t &aux(uint32_t i) const { return st[2 * M2_WARPS_ * SM_STAGE + i]; }
+    __device__ __forceinline__ uint64_t &link(uint32_t i) const { return st[3 * M2_WARPS_ * SM_STAGE + i]; }
+    __device__ __forceinline__ uint64_t &sk(uint32_t i) const { return st[4 * M2_WARPS_ * SM_STAGE + i]; }
 };
 __device__ __forceinline__ void stage_flush(const GroupArgs &A, WarpStage &W) {
     const unsigned lane = threadIdx.x & 31;
@@ -581,9 +587,9 @@ __device__ __forceinline__ void stage_flush(const GroupArgs &A, WarpStage &W) {
     if (lane == 0) base = atomicAdd(&A.ctr->n_emitted, (unsigned long long)W.cnt);
     base = __shfl_sync(0xffffffffu, base, 0) + A.out_base;
     for (uint32_t i = lane; i < W.cnt; i += 32) {
-        Rec r{W.lo[i], W.hi[i], W.aux[i], W.link[i]};
+        Rec r{W.lo(i), W.hi(i), W.aux(i), W.link(i)};
         st_rec(A.out + base + i, r);
-        if (A.out_sk) A.out_sk[base + i] = W.sk[i];
+        if (A.out_sk) A.out_sk[base + i] = W.sk(i);
     }
     W.cnt = 0;
     __syncwarp();
@@ -661,10 +667,10 @@ __device__ __forceinline__ void bm_step(const GroupArgs &A, WarpStage &W, uint64
     const unsigned wb = __ballot_sync(0xffffffffu, win);
     if (win) {
         const uint32_t at = W.cnt + __popc(wb & ((1u << lane) - 1));
-        W.lo[at] = clo; W.hi[at] = chi; W.aux[at] = caux; W.link[at] = t;
+        W.lo(at) = clo; W.hi(at) = chi; W.aux(at) = caux; W.link(at) = t;
         if (A.out_sk) {
             const uint64_t k = flip_f64((uint64_t)__double_as_longlong(score_state(A.h, A.noise_mode, clo, chi & HI_KEY_MASK, caux, A.L)));
-            W.sk[at] = k;
+            W.sk(at) = k;
             W.kmin = min(W.kmin, k); W.kmax = max(W.kmax, k);
         }
     }
@@ -733,18 +739,20 @@ __device__ __forceinline__ void warp_epilogue(const GroupArgs &A, WarpStage &W, 
     }
 }
 
+constexpr int WARP_BATCH = 4; // runs a warp of the warp kernel draws per ticket
+constexpr int MAX_SETS = 4;  // card sets under one sort key that the thread / warp kernels can tell apart
 constexpr int BSORT_MAX = 512;  // buy records of one run the warp kernel can put into arrival order itself
 struct WarpSmem {
     SmemTabs tabs;
     uint64_t bm[M2_WARPS][NODE_BM_WORDS + 2];
     uint64_t st[5][M2_WARPS][SM_STAGE];  // lo, hi, aux, link, sk
+    uint64_t done[M2_WARPS][MAX_SETS][2]; // card sets of the current run walked so far (rarely more than one)
     uint64_t bsort[M2_WARPS][BSORT_MAX]; // UNORDERED only (last member: the arrival-ordered launch leaves it out)
 };
 
 // Class CLS_WARP of the dispatch (THREAD_W < candidates <= WARP_W): one warp per run.  The run is streamed through a
 // parent window and a buy-record window of 32 lanes each, once per card set it holds (almost always one; several
 // only when two sets share a 32-bit sort key).  Persistent grid: warp w takes list entries w, w + W, ...
-constexpr int MAX_SETS = 4;  // card sets under one sort key that the thread / warp kernels can tell apart
 #ifndef SPL_WARP_CTAS
 #define SPL_WARP_CTAS 4  // resident CTAs per SM of the warp kernel (64 registers per thread; 3 and 5 measured slower)
 #endif
@@ -756,10 +764,20 @@ __global__ void __launch_bounds__(TILE, SPL_WARP_CTAS) m2_group_warp_kernel(Grou
     load_tabs(S.tabs, A.tabs);
     __syncthreads();
     uint64_t *bm = S.bm[w];
-    WarpStage W{S.st[0][w], S.st[1][w], S.st[2][w], S.st[3][w], S.st[4][w], 0, ~0ull, 0};
+    WarpStage W{S.st[0][w], 0, ~0ull, 0};
     const uint32_t n_list = A.ctr->n_cls[CLS_WARP];
     uint32_t n_fresh = 0;
-    for (uint32_t j = blockIdx.x * M2_WARPS + w; j < n_list; j += gridDim.x * M2_WARPS) {
+    // Runs weigh 17 .. 1024 candidates and their order in the list is whatever the dispatch kernel's atomics made it:
+    // warps draw batches of WARP_BATCH runs from a ticket (the next batch's ticket is in flight while this one is
+    // walked) instead of striding over the list, so the launch ends when the work does, not with its unluckiest warp.
+    uint32_t next_base = 0;
+    if (lane == 0) next_base = atomicAdd(&A.ctr->ticket[2], (unsigned)WARP_BATCH);
+    for (;;) {
+        const uint32_t base = __shfl_sync(0xffffffffu, next_base, 0);
+        if (base >= n_list) break;
+        if (lane == 0) next_base = atomicAdd(&A.ctr->ticket[2], (unsigned)WARP_BATCH);
+        const uint32_t j_end = min(base + (uint32_t)WARP_BATCH, n_list);
+      for (uint32_t j = base; j < j_end; ++j) {
         const uint32_t r = A.cls_list[CLS_WARP][j];
         const uint32_t s = A.run_start[r], e = A.run_start[r + 1];
         // parents [s, pe), buy records [pe, e)
@@ -796,7 +814,7 @@ __global__ void __launch_bounds__(TILE, SPL_WARP_CTAS) m2_group_warp_kernel(Grou
                     __syncwarp();
                 }
         }
-        uint64_t d0[MAX_SETS], d1[MAX_SETS];  // card sets done so far
+        uint64_t (*done)[2] = S.done[w];  // card sets done so far (shared memory: keeps 16 registers out of the walk)
         int n_done = 0;
         uint32_t lead = s;
         while (lead != 0xFFFFFFFFu) {
@@ -823,7 +841,7 @@ __global__ void __launch_bounds__(TILE, SPL_WARP_CTAS) m2_group_warp_kernel(Grou
                     const bool ok = valid && m0 == M0 && m1 == M1;
                     bool other = valid && !ok;  // a card set not walked yet?
 #pragma unroll
-                    for (int d = 0; d < MAX_SETS; ++d) other = other && !(d < n_done && d0[d] == m0 && d1[d] == m1);
+                    for (int d = 0; d < MAX_SETS; ++d) other = other && !(d < n_done && done[d][0] == m0 && done[d][1] == m1);
                     const unsigned om = __ballot_sync(0xffffffffu, other);
                     if (om) next_lead = min(next_lead, pnext + (uint32_t)__ffs(om) - 1);
                     pmask = __ballot_sync(0xffffffffu, ok);
@@ -842,7 +860,7 @@ __global__ void __launch_bounds__(TILE, SPL_WARP_CTAS) m2_group_warp_kernel(Grou
                     const bool ok = valid && m0 == M0 && m1 == M1;
                     bool other = valid && !ok;
 #pragma unroll
-                    for (int d = 0; d < MAX_SETS; ++d) other = other && !(d < n_done && d0[d] == m0 && d1[d] == m1);
+                    for (int d = 0; d < MAX_SETS; ++d) other = other && !(d < n_done && done[d][0] == m0 && done[d][1] == m1);
                     const unsigned om = __ballot_sync(0xffffffffu, other);
                     if (om) {  // item position of the first record of a card set not walked yet
                         const uint32_t j = bnext - pe + (uint32_t)__ffs(om) - 1;
@@ -883,13 +901,13 @@ __global__ void __launch_bounds__(TILE, SPL_WARP_CTAS) m2_group_warp_kernel(Grou
             node_close(N, bm);
             if (next_lead != 0xFFFFFFFFu) {
                 if (n_done == MAX_SETS) { if (lane == 0) atomicExch(&A.ctr->error, 3u); break; }
-#pragma unroll
-                for (int d = 0; d < MAX_SETS; ++d)
-                    if (d == n_done) { d0[d] = M0; d1[d] = M1; }
+                if (lane == 0) { done[n_done][0] = M0; done[n_done][1] = M1; }
+                __syncwarp();
                 ++n_done;
             }
             lead = next_lead;
         }
+      }
     }
     warp_epilogue(A, W, n_fresh);
 }

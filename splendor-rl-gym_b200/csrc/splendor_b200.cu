@@ -1374,6 +1374,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         // dispatch + thread kernel over all runs, then the warp kernel and the CTA kernel over the runs it queued
         m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
         CK(c, cudaEventRecord(c->ev[4], st));
+        CKS(c, reset_ticket(c, 2, st));  // the warp kernel draws its runs from ticket 2
         m2_group_warp_kernel<false><<<148 * SPL_WARP_CTAS, TILE, offsetof(WarpSmem, bsort), st>>>(A);
         CK(c, cudaEventRecord(c->ev[5], st));
         CK(c, cudaEventRecord(c->ev[6], st));
@@ -1747,6 +1748,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     CK(c, cudaEventRecord(c->ev[1], st));
     m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
     CK(c, cudaEventRecord(c->ev[2], st));
+    CKS(c, reset_ticket(c, 2, st));
     m2_group_warp_kernel<true><<<148 * SPL_WARP_CTAS, TILE, sizeof(WarpSmem), st>>>(A);
     CK(c, cudaEventRecord(c->ev[3], st));
     m2_group_big_kernel<<<148 * 5, TILE, sizeof(BigSmem), st>>>(A);
