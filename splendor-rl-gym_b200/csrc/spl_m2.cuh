@@ -739,7 +739,10 @@ __device__ __forceinline__ void warp_epilogue(const GroupArgs &A, WarpStage &W, 
     }
 }
 
-constexpr int WARP_BATCH = 4; // runs a warp of the warp kernel draws per ticket
+#ifndef SPL_WARP_BATCH
+#define SPL_WARP_BATCH 8  // measured per beam-30M solve: 1: 290, 2: 267, 4: 257, 8: 254, 16: 268, 32: 262, 64: 276 ms
+#endif
+constexpr int WARP_BATCH = SPL_WARP_BATCH; // runs a warp of the warp kernel draws per ticket
 constexpr int MAX_SETS = 4;  // card sets under one sort key that the thread / warp kernels can tell apart
 constexpr int BSORT_MAX = 512;  // buy records of one run the warp kernel can put into arrival order itself
 struct WarpSmem {
