@@ -235,12 +235,21 @@ class Runner:
         if comm.world == 1:
             return eng.solver(self.k, self.aux, a.goal, a.config != 'C2', a.heuristic, beam, a.tie, a.noise, keep_links=keep_links)
         from splendor_rl_gym_b200.sharded import CudaBackend, GroupedShardedSolver, ShardedSolver
-        if a.config != 'C2' and a.tie == 'stable' and a.noise == 'const':
+        if a.config != 'C2' and a.tie == 'stable' and a.noise == 'const' and not getattr(self, 'key_sharded', False):
             return GroupedShardedSolver(eng, comm, self.k, self.aux, a.goal, a.heuristic, beam, a.noise, keep_links=keep_links)
         return ShardedSolver(CudaBackend(eng), comm, self.k, self.aux, a.goal, a.config != 'C2', a.heuristic, beam, a.tie, a.noise, keep_links=keep_links)
 
     def run(self, beam, digest=False):
         """-> (per-level infos, sha256 over every level's queue or None)"""
+        if self.comm.world > 1 and not getattr(self, 'key_sharded', False):
+            from splendor_rl_gym_b200.sharded import DictionaryOverflow
+            try:
+                return self._run(beam, digest)
+            except DictionaryOverflow:  # e.g. `balanced` at wide beams: as State.solve() does, rerun on the key-sharded driver
+                self.key_sharded = True
+        return self._run(beam, digest)
+
+    def _run(self, beam, digest=False):
         a = self.a
         sol = self.solver(beam)
         h = hashlib.sha256() if digest else None
@@ -450,7 +459,8 @@ def run_b200(a):
                    'beam': a.beam, 'goal': a.goal, 'heuristic': a.heuristic,
                    'parallelism': (('single GPU, ' + ('card-set-grouped level' if a.config in ('C1', 'C3', 'C4') else 'key-table level')) if world == 1 else
                                    f'{world} independent replicas (realistic mode does not shard)' if replicas else
-                                   f'queue sharded by card set over {world} GPUs: gem takes local, card buys routed (NCCL all-to-all), '
+                                   f'queue sharded by card set over {world} GPUs: gem takes local, card buys stored into their owner\'s '
+                                   f'receive buffer over NVLink by the routing kernel (CUDA IPC peer mappings; SPL_NO_P2P=1: NCCL all-to-all), '
                                    f'merged-dictionary beam cut, sample-sort global ranks')},
         'time_to_solve_s': ms / a.steps * 1e-3,
         'generated_per_s': float(gen) * (world if replicas else 1) * a.steps / (ms * 1e-3) if gen else None,

@@ -546,6 +546,12 @@ class ShardedSolver:
 
 
 
+class DictionaryOverflow(RuntimeError):
+    """A level holds more distinct scores than the score dictionary of the card-set-sharded beam cut (2048; `balanced`
+    and `efficiency` at wide beams): the caller reruns the search on ShardedSolver, whose cut is a radix select.  The
+    merged dictionary is the same on every rank, so every rank raises at the same level."""
+
+
 class PeerRecv:
     """This rank's receive buffer for routed buy records, mapped into every other rank of the node (CUDA IPC through
     spl_ipc_*): the routing kernel of rank r stores the records owned by rank d straight into d's buffer over NVLink
@@ -725,7 +731,10 @@ class GroupedShardedSolver:
         else:
             alld = local.reshape(1, -1)
         need = C.c_int32()
-        check(lib.spl_gs_threshold(self._h, alld.data_ptr(), self.beam, u_total, C.byref(need), self._st()), eng._h)
+        rc = lib.spl_gs_threshold(self._h, alld.data_ptr(), self.beam, u_total, C.byref(need), self._st())
+        if rc == -6:  # SPL_E_CAPACITY
+            raise DictionaryOverflow(f'level {self.level}: more than 2048 distinct scores')
+        check(rc, eng._h)
         if need.value:  # split the ties of the threshold score by arrival order
             lt = C.c_int32()
             check(lib.spl_gs_tie_begin(self._h, C.byref(lt), self._st()), eng._h)

@@ -204,21 +204,32 @@ class State:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             # one process per GPU (torchrun): every rank calls solve() collectively; the frontier is
             # sharded by key hash and each level is bit-identical to the single-GPU search
-            from .sharded import Comm, CudaBackend, GroupedShardedSolver, ShardedSolver
+            from .sharded import Comm, CudaBackend, DictionaryOverflow, GroupedShardedSolver, ShardedSolver
+
+            def key_sharded():  # exhaustive BFS, key ties, hash / mt noise, pyhash identity: queue sharded by key hash
+                return ShardedSolver(CudaBackend(eng), Comm(eng.tdev), k, a, goal_pts, use_heuristic, heuristic_name,
+                                     beam_width, tie_policy, noise, identity=identity)
+
+            def run(sh):
+                try:
+                    infos = list(sh.run())
+                    return infos, sh.path()[1]
+                finally:
+                    if hasattr(sh, 'close'):
+                        sh.close()
             if use_heuristic and tie_policy == 'stable' and noise == 'const' and identity == 'key':
                 # queue sharded by card set: gem takes never leave the GPU, only card buys are routed
                 sh = GroupedShardedSolver(eng, Comm(eng.tdev), k, a, goal_pts, heuristic_name, beam_width, noise)
-            else:  # exhaustive BFS, key ties, hash / mt noise, pyhash identity: queue sharded by key hash
-                sh = ShardedSolver(CudaBackend(eng), Comm(eng.tdev), k, a, goal_pts, use_heuristic, heuristic_name,
-                                   beam_width, tie_policy, noise, identity=identity)
-            try:
-                for info in sh.run():
-                    if stats is not None:
-                        stats.append(info)
-                _, ordinals = sh.path()
-            finally:
-                if hasattr(sh, 'close'):
-                    sh.close()
+                try:
+                    infos, ordinals = run(sh)
+                except DictionaryOverflow:  # too many distinct scores for the dictionary cut (every rank gets here together)
+                    sh = key_sharded()
+                    infos, ordinals = run(sh)
+            else:
+                sh = key_sharded()
+                infos, ordinals = run(sh)
+            if stats is not None:
+                stats.extend(infos)
             if sh.noise_source is not None:
                 sh.noise_source.finish()
             path = [self]

@@ -371,6 +371,23 @@ def test_grouped_sharded_solver_world1_vs_oracle(eng, hname, beam, rounds):
         orc.close()
 
 
+def test_grouped_sharded_solver_reports_dictionary_overflow(eng):
+    """`balanced` at beam 300 000 has more distinct scores per level than the merged score dictionary holds: the driver
+    says so (State.solve() and bench.py then rerun on the key-sharded driver) and leaves the context usable."""
+    from splendor_rl_gym_b200.sharded import Comm, DictionaryOverflow, GroupedShardedSolver
+    sol = GroupedShardedSolver(eng, Comm(eng.tdev), 0, 0, 15, 'balanced', 300_000, 'const')
+    try:
+        with pytest.raises(DictionaryOverflow):
+            while not sol.step()['ended']:
+                pass
+    finally:
+        sol.close()
+    k, aux = S.State.newgame().record()
+    again = eng.solver(k, aux, 15, True, 'balanced', 2_000, 'stable', 'const')
+    assert again.run()[-1]['ended']
+    again.close()
+
+
 def test_link_columns_spill_to_host_same_path(eng):
     """spl_set_link_budget: with the per-level parent links forced out to pinned host memory the winning
     line (src/solver.py:459-464) is the one found with every column on the device -- solver and sharded driver."""

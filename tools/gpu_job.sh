@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
-for v in 16 32 64; do
-SPLENDOR_B200_LIB=$GRAFT_REPO_ROOT/gpurun_variants/lib_wb$v.so QUIET=1 timeout 300 python tools/explore.py --beam 30000000 --reps 3 2>&1 | grep -E "SUMMARY" | tail -1
-done
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "overflow or spill or grouped" 2>&1 | tail -3
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+timeout 600 $T bench.py --gpus 2 --config C4 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2g_bench_c4_n2.json 2> gpurun_out/r2g_bench_c4_n2.err; tail -c 400 gpurun_out/r2g_bench_c4_n2.json; grep -v "^\*\*\|OMP\|^$" gpurun_out/r2g_bench_c4_n2.err | grep -A8 Traceback | head -20
