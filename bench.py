@@ -367,16 +367,21 @@ def run_b200(a):
         return S.State.newgame().solve(goal_pts=a.goal, use_heuristic=True, heuristic_name=a.heuristic, beam_width=a.beam, verbose=False,
                                        tie_policy=a.tie, noise=a.noise, engine=eng, stats=stats)
 
-    if a.warmup:
-        api_solve([])  # untimed: the API path keeps parent links, whose per-level columns are allocated on first use
+    for _ in range(min(a.warmup, 3)):
+        # untimed: the API path keeps parent links, whose per-level columns are allocated on first use; on several GPUs
+        # the second link-keeping solve of a process was still seen at 1-3 s (seconds_each_solve_rank0 shows the rest)
+        api_solve([])
     h0, d0 = eng.transfer_bytes()
     st = []
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     te0 = time.perf_counter()
+    per_solve = []
     for _ in range(a.steps):
+        ts0 = time.perf_counter()
         path = api_solve(st)
+        per_solve.append(round(time.perf_counter() - ts0, 4))
     torch.cuda.synchronize()
     te = time.perf_counter() - te0
     h1, d1 = eng.transfer_bytes()
@@ -387,7 +392,7 @@ def run_b200(a):
     e2e = {'value': float(e2e_exp) / float(e2e_t.item()), 'unit': 'expanded states/s',
            'h2d_bytes_per_step': (h1 - h0) // a.steps, 'd2h_bytes_per_step': (d1 - d0) // a.steps,
            'bytes_note': 'rank 0, counted: library copies (spl_transfer_bytes) + the Python layer\'s path-replay tensors',
-           'seconds_per_solve': float(e2e_t.item()) / a.steps}
+           'seconds_per_solve': float(e2e_t.item()) / a.steps, 'seconds_each_solve_rank0': per_solve}
     if a.config == 'C5' and path:
         e2e.update(plies=len(path) - 1, winner=path[-1].get_winner(), final_pts=[p.pts for p in path[-1].players])
     elif path:
@@ -459,6 +464,8 @@ def run_b200(a):
                    'beam': a.beam, 'goal': a.goal, 'heuristic': a.heuristic,
                    'parallelism': (('single GPU, ' + ('card-set-grouped level' if a.config in ('C1', 'C3', 'C4') else 'key-table level')) if world == 1 else
                                    f'{world} independent replicas (realistic mode does not shard)' if replicas else
+                                   f'queue sharded by key hash over {world} GPUs (key-sharded driver: candidates routed with NCCL all-to-all, radix-select beam cut; '
+                                   f'the card-set-sharded driver was tried first and reported more than 2048 distinct scores per level)' if getattr(runner, 'key_sharded', False) else
                                    f'queue sharded by card set over {world} GPUs: gem takes local, card buys stored into their owner\'s '
                                    f'receive buffer over NVLink by the routing kernel (CUDA IPC peer mappings; SPL_NO_P2P=1: NCCL all-to-all), '
                                    f'merged-dictionary beam cut, sample-sort global ranks')},

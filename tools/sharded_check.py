@@ -47,8 +47,10 @@ use_h = a.bfs == 0
 check = comm.rank == 0 and not a.no_oracle
 from splendor_rl_gym_b200 import sharded as _sh0
 for rep in range(a.reps):
-    if rep == a.reps - 1 and rep > 0:
-        _sh0.PHASES.clear()  # phase times of the last (warm) repetition only
+    if rep > 0:
+        if _sh0.TIMING and comm.rank == 0:
+            print(f'  phases of rep {rep - 1}: ' + ', '.join(f'{k}={v:.3f}' for k, v in _sh0.PHASES.items()), flush=True)
+        _sh0.PHASES.clear()  # the summary line below shows the last (warm) repetition
     if check and rep == 0:
         import oracle
         orc = oracle.Solver(255 if a.bfs else a.goal, use_heuristic=use_h, heuristic_name=a.heuristic, beam_width=a.beam,
