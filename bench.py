@@ -368,8 +368,8 @@ def run_b200(a):
                                        tie_policy=a.tie, noise=a.noise, engine=eng, stats=stats)
 
     for _ in range(min(a.warmup, 3)):
-        # untimed: the API path keeps parent links, whose per-level columns are allocated on first use; on several GPUs
-        # the second link-keeping solve of a process was still seen at 1-3 s (seconds_each_solve_rank0 shows the rest)
+        # untimed: the API path keeps parent links, whose per-level columns are allocated on first use
+        # (e2e.seconds_each_solve_rank0 lists the timed solves one by one)
         api_solve([])
     h0, d0 = eng.transfer_bytes()
     st = []

@@ -1121,6 +1121,24 @@ int32_t spl_count_less(spl_ctx *c, int32_t words, int32_t inclusive, const uint6
 }  // extern "C"
 
 // ------------------------------------------------------------------ fused solver
+// A pooled link column for `bytes`: the smallest pooled buffer that holds them, else the largest (it is regrown with
+// 1/16 headroom -- queue lengths wobble by a fraction of a percent from level to level and from rank to rank, and
+// every regrowth is a cudaMalloc plus a device-synchronising cudaFree in the middle of a level).
+static DevBuf *take_link_buf(spl_ctx *c, size_t bytes) {
+    if (c->pool_links.empty()) return new DevBuf();
+    size_t best = c->pool_links.size(), big = 0;
+    for (size_t i = 0; i < c->pool_links.size(); ++i) {
+        const size_t cap = c->pool_links[i]->cap;
+        if (cap >= bytes && (best == c->pool_links.size() || cap < c->pool_links[best]->cap)) best = i;
+        if (cap > c->pool_links[big]->cap) big = i;
+    }
+    const size_t pick = best != c->pool_links.size() ? best : big;
+    DevBuf *b = c->pool_links[pick];
+    c->pool_links.erase(c->pool_links.begin() + (long)pick);
+    return b;
+}
+static size_t link_bytes(int64_t n) { return (size_t)n * 8 + (size_t)n / 2; }
+
 // Parent-link columns (src/solver.py:459-464 walks them back from the goal): one per level, 8 B per queue entry.  Past
 // spl_set_link_budget's device budget the oldest columns move to pinned host memory; the path walk
 // reads a spilled column in place.
@@ -1185,12 +1203,11 @@ struct spl_solver {
 
 static int save_links(spl_solver *s, cudaStream_t st) {
     spl_ctx *c = s->c;
-    DevBuf *b;
-    if (c->pool_links.empty()) b = new DevBuf();
-    else { b = c->pool_links.back(); c->pool_links.pop_back(); }
+    const bool keep = s->keep_links && s->n_front > 0;
+    DevBuf *b = take_link_buf(c, keep ? (size_t)s->n_front * 8 : 0);
     s->links.push(b, s->keep_links ? s->n_front : 0);
-    if (!s->keep_links || s->n_front == 0) return SPL_OK;
-    CK(c, b->ensure((size_t)s->n_front * 8, 0, st));
+    if (!keep) return SPL_OK;
+    if (b->cap < (size_t)s->n_front * 8) CK(c, b->ensure(link_bytes(s->n_front), 0, st));
     if (s->realistic)
         r_links_kernel<<<nblk(s->n_front), TILE, 0, st>>>(s->front.as<RRec>(), s->n_front, b->as<uint64_t>());
     else
@@ -1459,14 +1476,14 @@ struct spl_gsolver {
 
 static int gs_save_links(spl_gsolver *s, cudaStream_t st) {
     spl_ctx *c = s->c;
-    DevBuf *lb, *rb;  // reuse the columns of earlier solves on this context (smallest first: the queue grows)
-    if (c->pool_links.empty()) lb = new DevBuf(); else { lb = c->pool_links.back(); c->pool_links.pop_back(); }
-    if (c->pool_links.empty()) rb = new DevBuf(); else { rb = c->pool_links.back(); c->pool_links.pop_back(); }
+    const bool keep = s->keep_links && s->n_local > 0;
+    const size_t need = keep ? (size_t)s->n_local * 8 : 0;
+    DevBuf *lb = take_link_buf(c, need), *rb = take_link_buf(c, need);  // columns of earlier solves on this context
     s->link_cols.push(lb, s->keep_links ? s->n_local : 0);
     s->rank_cols.push(rb, s->keep_links ? s->n_local : 0);
-    if (!s->keep_links || s->n_local == 0) return SPL_OK;
-    CK(c, lb->ensure((size_t)s->n_local * 8, 0, st));
-    CK(c, rb->ensure((size_t)s->n_local * 8, 0, st));
+    if (!keep) return SPL_OK;
+    if (lb->cap < need) CK(c, lb->ensure(link_bytes(s->n_local), 0, st));
+    if (rb->cap < need) CK(c, rb->ensure(link_bytes(s->n_local), 0, st));
     unpack_rec_kernel<<<nblk(s->n_local), TILE, 0, st>>>(s->front.as<Rec>(), s->n_local, nullptr, nullptr, lb->as<uint64_t>());
     ++c->launches;
     CK(c, cudaMemcpyAsync(rb->p, s->grank.p, (size_t)s->n_local * 8, cudaMemcpyDeviceToDevice, st));
