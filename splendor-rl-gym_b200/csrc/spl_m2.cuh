@@ -925,6 +925,7 @@ constexpr int TINY_ITEMS = 16;
 #define SPL_BIG_W 1024
 #endif
 constexpr uint32_t BIG_W = SPL_BIG_W;
+template <bool UNORDERED>
 __global__ void __launch_bounds__(TILE) m2_group_tiny_kernel(GroupArgs A, uint32_t n_runs) {
     __shared__ uint32_t warp_sums[TILE / 32 + 1];
     __shared__ uint64_t s_base;
@@ -973,14 +974,16 @@ __global__ void __launch_bounds__(TILE) m2_group_tiny_kernel(GroupArgs A, uint32
                     if (j < (int)cnt) {
                         const uint32_t g = (gp[j >> 1] >> (16 * (j & 1))) & 0x7fffu;
                         bool dup = false;
-                        if (!A.unordered) {  // records in arrival order: an earlier record with the same gems wins
+                        if (!UNORDERED) {  // records in arrival order: an earlier record with the same gems wins
 #pragma unroll
                             for (int i = 0; i < j; ++i) dup = dup || ((gp[i >> 1] >> (16 * (i & 1))) & 0x7fffu) == g;
                         } else {             // any order: the record with the smaller arrival index wins
+                            uint32_t eq = 0;  // the other records with this gem hand (rare): compare arrival indices
 #pragma unroll
                             for (int i = 0; i < TINY_ITEMS; ++i)
-                                if (i != j && i < (int)cnt && ((gp[i >> 1] >> (16 * (i & 1))) & 0x7fffu) == g)
-                                    dup = dup || A.brec[item_id(A, s + i) - A.np].link < A.brec[item_id(A, s + j) - A.np].link;
+                                if (i != j && i < (int)cnt && ((gp[i >> 1] >> (16 * (i & 1))) & 0x7fffu) == g) eq |= 1u << i;
+                            for (; eq && !dup; eq &= eq - 1)
+                                dup = A.brec[item_id(A, s + (__ffs(eq) - 1)) - A.np].link < A.brec[item_id(A, s + j) - A.np].link;
                         }
                         if (!dup && (fresh || !node_bit(N, __ldg(A.gemrank + g)))) winmask |= 1u << j;
                     }

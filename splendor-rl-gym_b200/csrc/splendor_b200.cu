@@ -1389,7 +1389,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         A.h = s->heuristic; A.noise_mode = s->noise; A.L = c->luts; A.ctr = c->d_ctr;
         CK(c, cudaEventRecord(c->ev[2], st));
         // dispatch + thread kernel over all runs, then the warp kernel and the CTA kernel over the runs it queued
-        m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
+        m2_group_tiny_kernel<false><<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
         CK(c, cudaEventRecord(c->ev[4], st));
         CKS(c, reset_ticket(c, 2, st));  // the warp kernel draws its runs from ticket 2
         m2_group_warp_kernel<false><<<148 * SPL_WARP_CTAS, TILE, offsetof(WarpSmem, bsort), st>>>(A);
@@ -1763,7 +1763,7 @@ int32_t spl_gs_round_group(spl_gsolver *s, const void *recv_dev, int64_t n_recv,
     A.cls_list[CLS_CTA] = c->cls_list.as<uint32_t>() + n_runs;
     A.h = s->heuristic; A.noise_mode = s->noise; A.L = c->luts; A.ctr = c->d_ctr;
     CK(c, cudaEventRecord(c->ev[1], st));
-    m2_group_tiny_kernel<<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
+    m2_group_tiny_kernel<true><<<nblk((int64_t)n_runs), TILE, 0, st>>>(A, (uint32_t)n_runs);
     CK(c, cudaEventRecord(c->ev[2], st));
     CKS(c, reset_ticket(c, 2, st));
     m2_group_warp_kernel<true><<<148 * SPL_WARP_CTAS, TILE, sizeof(WarpSmem), st>>>(A);

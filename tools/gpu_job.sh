@@ -1,9 +1,10 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cli.py -m gpu -q -x 2>&1 | tail -2
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-timeout 600 $T bench.py --gpus 2 --warmup 1 --no-cpu-baseline --no-parity > gpurun_out/r2h_bench_n2.json 2> gpurun_out/r2h_bench_n2.err
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r2i_pytest_full.log 2>&1; tail -2 gpurun_out/r2i_pytest_full.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/r2i_bench_n1.json 2> gpurun_out/r2i_bench_n1.err
 python - <<'PY'
 import json
-d=json.loads([l for l in open('gpurun_out/r2h_bench_n2.json') if l.startswith('{')][-1])
-print(d['ms_per_step'], d['e2e']['seconds_each_solve_rank0'], d['e2e']['value'])
+d=json.loads([l for l in open('gpurun_out/r2i_bench_n1.json') if l.startswith('{')][-1])
+print('value %.4e'%d['value'], d['ms_per_step'], d['stage_ms_per_step'], 'frac', d['roofline']['frac'], 'traffic', d['roofline']['traffic'], 'e2e %.4e'%d['e2e']['value'], d['e2e']['seconds_each_solve_rank0'], d['parity_check']['ok'])
 PY
+timeout 600 python bench.py --impl reference --steps 1 --warmup 0 2>/dev/null | tail -c 400
