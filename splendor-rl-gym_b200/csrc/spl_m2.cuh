@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TILE) m2_count_kernel(const Rec *__restrict__ 
         derive_parent(s, takes_idx, r.lo, r.hi, r.aux, bl, bh, nb, tk);
         ntk = tk & 0xff;
         mask_words(r.lo, r.hi, m0, m1);
-        iv[p] = (mask_hash(m0, m1) & 0xFFFFFFFF00000000ull) | (uint64_t)p;  // item = sort key << 32 | item id
+        iv[p] = (mask_hash(m0, m1) & 0xFFFFFFFF00000000ull) | (uint64_t)p;  // item = high half of the card-set hash << 32 | item id (ordered by its top 30 bits)
         ntk8[p] = (uint8_t)ntk;
     }
     uint32_t total, total_tk;
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(TILE) m2_runs_kernel(const uint64_t *__restric
 struct GroupArgs {
     const Rec *front;              // the round's parents (rank order)
     const Rec *brec;               // the round's buy records
-    const uint64_t *iv;            // sorted items: sort key << 32 | item id (id < np: parent, else np + buy index)
+    const uint64_t *iv;            // sorted items: hash half << 32 | item id (id < np: parent, else np + buy index)
     const uint32_t *run_start, *run_wpre;
     uint32_t np;
     int64_t rank_base;             // global rank of parent 0 of the round (when the parents' ranks are contiguous) ...
@@ -755,7 +755,7 @@ struct WarpSmem {
 
 // Class CLS_WARP of the dispatch (THREAD_W < candidates <= WARP_W): one warp per run.  The run is streamed through a
 // parent window and a buy-record window of 32 lanes each, once per card set it holds (almost always one; several
-// only when two sets share a 32-bit sort key).  Persistent grid: warp w takes list entries w, w + W, ...
+// only when two sets share a 30-bit sort key).  Persistent grid: warps draw batches of list entries from a ticket.
 #ifndef SPL_WARP_CTAS
 #define SPL_WARP_CTAS 4  // resident CTAs per SM of the warp kernel (64 registers per thread; 3 and 5 measured slower)
 #endif

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TILE) gs_buys_route_kernel(const Rec *__restri
     }
 }
 
-// items of the records received in a round: sort key << 32 | (np + index)
+// items of the records received in a round: hash half << 32 | (np + index)
 __global__ void __launch_bounds__(TILE) gs_recv_items_kernel(const Rec *__restrict__ recv, int64_t n, uint32_t np,
                                                              uint64_t *__restrict__ iv) {
     const int64_t j = (int64_t)blockIdx.x * TILE + threadIdx.x;

@@ -1328,7 +1328,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         CK(c, cudaEventRecord(c->ev[0], st));
         CK(c, c->boff2.ensure((size_t)np * 4 + 4, 0, st));
         CK(c, c->ntk8.ensure((size_t)np + 8, 0, st));
-        // items of the round = parents + buy records (packed: sort key << 32 | item id); the array is sized for the
+        // items of the round = parents + buy records (packed: hash half << 32 | item id); the array is sized for the
         // parents first and grown (contents kept) once the buys are counted
         CK(c, c->y[0].ensure((size_t)np * 8 + 8, 0, st));
         CKS(c, prep_status(c, 0, nt, st));
@@ -1371,7 +1371,7 @@ static int grouped_expand(spl_solver *s, const Rec *front, int64_t n, int64_t *n
         CK(c, cudaEventRecord(c->ev[1], st));
         CKS(c, read_ctr(c, st));
         const uint64_t n_runs = c->h_ctr->n_runs;
-        // every run holds at least one card set; more than one only when two sets share a 32-bit key
+        // every run holds at least one card set; more than one only when two sets share the 30 sorted hash bits
         CKS(c, ensure_nodes(c, n_runs + n_runs / 8 + 64, st));
         CK(c, c->cls_list.ensure((size_t)n_runs * 8 + 16, 0, st));
         CK(c, s->uniq.ensure((size_t)(n_slots + (int64_t)total) * 32, (size_t)n_slots * 32, st));
