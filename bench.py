@@ -11,7 +11,9 @@ rules' constant tables: synthetic by construction):
     C3 (default)  BASELINE configs[2]: speedrun goal 15, `aggressive`, beam 30 M per GPU (N GPUs: 30 M x N), noise
                   `const`, ties by arrival order (`stable`)
     C1            configs[0]: goal 10, `simple`, beam 300 000 (the reference's own CPU-runnable case)
-    C4            configs[3]: goal 15, `balanced` (or --heuristic efficiency), beam 12.5 M per GPU (8 GPUs: 100 M)
+    C4            configs[3]: goal 15, `balanced` (or --heuristic efficiency), beam 12.5 M per GPU (8 GPUs: 100 M); on N > 1 the
+                  card-set-sharded driver reports more than 2048 distinct scores per level and the search reruns on the
+                  key-sharded driver, as State.solve() does (named in config.parallelism)
     C2            configs[1]: exhaustive BFS to --bfs-depth levels (queue sharded by key hash on N > 1)
     C5            configs[4]: realistic mode, --players 2|3, goal 15, market seed 0, --beam 20000 | 2000000 (one GPU per
                   replica: realistic mode is not sharded)
@@ -21,7 +23,8 @@ rules' constant tables: synthetic by construction):
                   with host inputs/outputs: root record H2D, per-level counters and the winning line D2H, path replay
                   -- wall clock around the call; bytes as counted by the library and the Python layer
     roofline      dominant stage of the level (per-run dedup kernels of the card-set-grouped level): algorithmic bytes
-                  / CUDA-event time
+                  / CUDA-event time; traffic = measured DRAM bytes per launch of those kernels
+                  (profiles/dedup_stage_traffic.json, from the committed ncu launch list; N = 1, C3)
     parity_check  one untimed search at a CPU-feasible width through the SAME solver class, every level's queue
                   (records in rank order) hashed and compared with the CPU oracle's (rank 0 runs the oracle)
     cpu_baseline  the CPU oracle (C port of the reference algorithm, 1 thread) on a bounded sample of the same workload;
