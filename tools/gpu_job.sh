@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 100 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -1
-timeout 100 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "grouped or spill or overflow" 2>&1 | tail -1
+SPL_TIMING=1 timeout 100 python tools/sharded_check.py --grouped --beam 30000000 --no-oracle --no-links --reps 2 2>&1 | grep -v "^\*\*\|OMP" | tail -3 | tee gpurun_out/r2i_world1.log
